@@ -1,0 +1,259 @@
+// blend_forward.cu -- persistent, warp-specialised front-to-back alpha blend for sm_100a.
+//
+// Semantics: /root/reference/.../rasterization/include/kernels_forward.cuh:362-498 and
+// kernels_inference.cuh:348-463 (B1-B8 in SURVEY.md §8.1): 16x12 tiles, each of six warps owns an
+// 8x4 sub-tile, alpha = o * exp(min(q, 0)), skip alpha < 1/255, no 0.99 clamp, "blend, then test
+// T < 1e-4", background added at the end, planar CHW float image.
+//
+// New design:
+//  * persistent CTAs pull tiles from an atomic queue; a dedicated producer warp streams each tile's
+//    tile-contiguous 48-byte records into a 4-stage shared-memory ring with 1-D bulk async copies
+//    (cp.async.bulk + mbarrier complete_tx, i.e. TMA; SASS UBLKCP), six consumer warps blend;
+//  * the per-stage header (tile id, offset, count) travels with the data, so the producer runs ahead
+//    across tile boundaries and the consumers never touch global memory for scheduling;
+//  * sub-tile culling is two-level: the reference's strict bounding-box overlap, then the exact
+//    "maximum of the Gaussian inside the rectangle" test on the 8x4 sub-tile (the same predicate the
+//    reference uses for 16x12 tiles); both only remove pairs whose alpha is below 1/255;
+//  * no bucket checkpoints are written: the backward pass recomputes transmittance front-to-back.
+#include "fgs_device.cuh"
+#include "fgs_host.h"
+
+namespace fgs {
+
+namespace {
+
+constexpr int kBatch = 64;                                // records per bulk copy (3 KB)
+constexpr int kStages = 4;
+constexpr int kConsumerThreads = kBlendWarps * 32;        // 192
+constexpr int kFwdThreads = kConsumerThreads + 32;        // + producer warp
+
+struct StageHdr {
+    int tile;      // -1: end of stream
+    int offset;    // index of the first record of this batch inside the tile's list
+    int count;     // records in this batch
+    int pad;
+};
+
+struct __align__(128) FwdSmem {
+    Rec recs[kStages][kBatch];
+    StageHdr hdr[kStages];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    volatile int skip_tile;
+};
+
+template <bool kTraining>
+__global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendFwdArgs a, const Cam cam) {
+    __shared__ FwdSmem sm;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kBlendWarps);
+        }
+        sm.skip_tile = -1;
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kBlendWarps) {
+        // ================================ producer warp ================================
+        if (lane != 0) return;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (;;) {
+            const int tile = (int)atomicAdd(a.queue, 1u);
+            if (tile >= a.n_tiles) break;
+            const uint2 range = a.tile_ranges[tile];
+            const int n = (int)(range.y - range.x);
+            const int nb = n > 0 ? (n + kBatch - 1) / kBatch : 1;
+            for (int b = 0; b < nb; ++b) {
+                if (b > 0 && sm.skip_tile == tile) break;
+                mbar_wait(&sm.empty[stage], phase ^ 1u);
+                const int cnt = min(kBatch, n - b * kBatch);
+                sm.hdr[stage].tile = tile;
+                sm.hdr[stage].offset = b * kBatch;
+                sm.hdr[stage].count = cnt > 0 ? cnt : 0;
+                if (cnt > 0) {
+                    mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)cnt * (uint32_t)sizeof(Rec));
+                    bulk_g2s(&sm.recs[stage][0], a.inst_recs + range.x + (uint32_t)(b * kBatch),
+                             (uint32_t)cnt * (uint32_t)sizeof(Rec), &sm.full[stage]);
+                } else {
+                    mbar_arrive(&sm.full[stage]);
+                }
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        mbar_wait(&sm.empty[stage], phase ^ 1u);
+        sm.hdr[stage].tile = -1;
+        sm.hdr[stage].offset = 0;
+        sm.hdr[stage].count = 0;
+        mbar_arrive(&sm.full[stage]);
+        return;
+    }
+
+    // ================================== consumer warps ==================================
+    const float3 bg = make_float3(__ldg(cam.bg), __ldg(cam.bg + 1), __ldg(cam.bg + 2));
+    int cur_tile = -1;
+    bool tile_finished = false;  // all 192 pixels done -> ignore the rest of this tile's batches
+    // per-pixel state
+    float cr = 0.f, cg = 0.f, cb = 0.f, T = 1.f;
+    uint32_t n_last = 0;
+    bool done = true, inside = false;
+    float px = 0.f, py = 0.f;
+    uint32_t pix_x = 0, pix_y = 0;
+    uint32_t sub_x0 = 0, sub_y0 = 0;
+
+    auto finalize = [&]() {
+        if (inside) {
+            cr += T * bg.x;
+            cg += T * bg.y;
+            cb += T * bg.z;
+            const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
+            if (kTraining) {
+                const uint32_t np = (uint32_t)cam.img_w * (uint32_t)cam.img_h;
+                a.image[pidx] = cr;
+                a.image[np + pidx] = cg;
+                a.image[2 * np + pidx] = cb;
+                a.final_T[pidx] = T;
+                a.n_processed[pidx] = n_last;
+            } else {
+                if (a.clamp_output) {
+                    cr = __saturatef(cr);
+                    cg = __saturatef(cg);
+                    cb = __saturatef(cb);
+                }
+                if (a.to_chw) {
+                    const uint32_t np = (uint32_t)cam.img_w * (uint32_t)cam.img_h;
+                    a.image[pidx] = cr;
+                    a.image[np + pidx] = cg;
+                    a.image[2 * np + pidx] = cb;
+                } else {
+                    a.image[3 * pidx] = cr;
+                    a.image[3 * pidx + 1] = cg;
+                    a.image[3 * pidx + 2] = cb;
+                }
+            }
+        }
+        if (kTraining) {
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, n_last);
+            if (lane == 0 && wmax > 0) atomicMax(&a.tile_max_n[cur_tile], wmax);
+        }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        mbar_wait(&sm.full[stage], phase);
+        const int tile = sm.hdr[stage].tile;
+        const int offset = sm.hdr[stage].offset;
+        const int count = sm.hdr[stage].count;
+        if (tile != cur_tile) {
+            if (cur_tile >= 0) finalize();
+            if (tile < 0) break;
+            cur_tile = tile;
+            tile_finished = false;
+            const uint32_t tile_x = (uint32_t)tile % (uint32_t)cam.grid_w, tile_y = (uint32_t)tile / (uint32_t)cam.grid_w;
+            sub_x0 = tile_x * kTileW + (uint32_t)(warp & 1) * kSubW;
+            sub_y0 = tile_y * kTileH + (uint32_t)(warp >> 1) * kSubH;
+            pix_x = sub_x0 + (uint32_t)(lane & 7);
+            pix_y = sub_y0 + (uint32_t)(lane >> 3);
+            inside = pix_x < (uint32_t)cam.img_w && pix_y < (uint32_t)cam.img_h;
+            px = (float)pix_x + 0.5f;
+            py = (float)pix_y + 0.5f;
+            cr = cg = cb = 0.f;
+            T = 1.f;
+            n_last = 0;
+            done = !inside;
+        }
+        if (!tile_finished && count > 0) {
+            const Rec* recs = &sm.recs[stage][0];
+            if (!__all_sync(0xffffffffu, done)) {
+                for (int g0 = 0; g0 < count; g0 += 32) {
+                    const int j = g0 + lane;
+                    bool hit = false;
+                    if (j < count) {
+                        const float4 q2 = recs[j].q2;
+                        const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+                        // strict bounding-box / sub-tile overlap (kernels_forward.cuh:445-451)
+                        hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
+                              sub_y0 < (by >> 16);
+                        if (hit) {
+                            const float4 q0 = recs[j].q0;
+                            const float4 q1 = recs[j].q1;
+                            hit = rect_contributes(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, (float)sub_x0,
+                                                   (float)sub_y0, (float)(kSubW - 1), (float)(kSubH - 1),
+                                                   __logf(q1.y * kMinAlphaRcp));
+                        }
+                    }
+                    uint32_t pending = __ballot_sync(0xffffffffu, hit);
+                    while (pending) {
+                        const int jj = g0 + __ffs((int)pending) - 1;
+                        pending &= pending - 1;
+                        const float4 q0 = recs[jj].q0;
+                        const float4 q1 = recs[jj].q1;
+                        const float colb = recs[jj].q2.x;
+                        if (!done) {
+                            const float dx = q0.x - px, dy = q0.y - py;
+                            const float power = blend_power(q0.z, q0.w, q1.x, dx, dy);
+                            const float gauss = __expf(fminf(power, 0.0f));
+                            const float alpha = __fmul_rn(q1.y, gauss);
+                            if (alpha >= kMinAlpha) {
+                                const float w = __fmul_rn(T, alpha);
+                                cr = fmaf(w, fmaxf(q1.z, 0.0f), cr);
+                                cg = fmaf(w, fmaxf(q1.w, 0.0f), cg);
+                                cb = fmaf(w, fmaxf(colb, 0.0f), cb);
+                                T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                n_last = (uint32_t)(offset + jj + 1);
+                                if (T < kTransmittanceThreshold) done = true;
+                            }
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
+            }
+            // tile-wide early termination vote (kernels_forward.cuh:420)
+            if (named_bar_and(1, kConsumerThreads, done)) {
+                tile_finished = true;
+                if (tid == 0) sm.skip_tile = cur_tile;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_blend_forward(const BlendFwdArgs& a, const Cam& cam, cudaStream_t stream) {
+    if (a.n_tiles <= 0) return cudaSuccess;
+    static int s_grid_train = 0, s_grid_inf = 0;
+    int& grid = a.training ? s_grid_train : s_grid_inf;
+    if (grid == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (a.training)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_forward_kernel<true>, kFwdThreads, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_forward_kernel<false>, kFwdThreads, 0);
+        if (occ < 1) occ = 1;
+        grid = sms * occ;
+    }
+    const int g = grid < a.n_tiles ? grid : a.n_tiles;
+    if (a.training)
+        blend_forward_kernel<true><<<g, kFwdThreads, 0, stream>>>(a, cam);
+    else
+        blend_forward_kernel<false><<<g, kFwdThreads, 0, stream>>>(a, cam);
+    return cudaGetLastError();
+}
+
+}  // namespace fgs

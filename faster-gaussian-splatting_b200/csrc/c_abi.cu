@@ -1,0 +1,424 @@
+// c_abi.cu -- host drivers and the extern "C" surface declared in include/fgs_b200.h.
+//
+// Mirrors the reference's torch-free host layer (rasterization/src/forward.cu:11-259,
+// backward.cu:8-125, inference.cu:11-226, adam/src/adam.cu:36-71) with a different pipeline:
+//   preprocess -> [async read-back of (V, I)] -> onesweep depth sort -> chained-scan offsets
+//   -> (wait for I) -> instances -> onesweep tile sort -> ranges + record gather -> persistent blend.
+// One host wait per forward (the reference blocks three times), hidden behind the depth sort; all
+// work goes to the caller's stream; no bucket buffers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fgs_b200.h"
+#include "fgs_device.cuh"
+#include "fgs_host.h"
+
+namespace fgs {
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(cudaError_t e, const char* where) {
+    std::snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+int fail_arg(const char* msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg);
+    return -1;
+}
+#define FGS_TRY(expr, where)                           \
+    do {                                               \
+        cudaError_t e_ = (expr);                       \
+        if (e_ != cudaSuccess) return fail(e_, where); \
+    } while (0)
+
+int bits_for(int max_value) {  // number of bits needed to represent max_value (>= 1)
+    int b = 1;
+    while ((max_value >> b) != 0 && b < 32) ++b;
+    return b;
+}
+
+// ---- scratch layouts (recomputed from sizes only, like buffer_utils.h:30-43) --------------------
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 128);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+    size_t bytes() { return align_up(off, 128); }
+};
+
+struct PrimitiveLayout {
+    uint32_t* counters;
+    Rec* recs;
+    uint32_t* n_touched;
+    uint32_t* keys[2];
+    uint32_t* idx[2];
+    uint32_t* offsets;
+    uint32_t* hist;
+    uint32_t* lookback;
+    uint32_t* scan_lookback;
+    size_t bytes;
+    PrimitiveLayout(char* blob, int n) {
+        Carver c(blob);
+        const size_t nn = (size_t)(n > 0 ? n : 1);
+        counters = c.take<uint32_t>(kCtrCount);
+        recs = c.take<Rec>(nn);
+        n_touched = c.take<uint32_t>(nn);
+        keys[0] = c.take<uint32_t>(nn);
+        keys[1] = c.take<uint32_t>(nn);
+        idx[0] = c.take<uint32_t>(nn);
+        idx[1] = c.take<uint32_t>(nn);
+        offsets = c.take<uint32_t>(nn);
+        hist = c.take<uint32_t>(4 * kRadixMax);
+        lookback = c.take<uint32_t>(radix_sort_lookback_words(n, 32));
+        scan_lookback = c.take<uint32_t>(offsets_scan_lookback_words(n));
+        bytes = c.bytes();
+    }
+};
+
+struct TileLayout {
+    uint2* ranges;
+    uint32_t* tile_max_n;
+    float* final_T;
+    uint32_t* n_processed;
+    size_t bytes;
+    TileLayout(char* blob, int n_tiles, int n_pixels, bool training) {
+        Carver c(blob);
+        ranges = c.take<uint2>((size_t)n_tiles);
+        tile_max_n = c.take<uint32_t>((size_t)n_tiles);
+        final_T = training ? c.take<float>((size_t)n_pixels) : nullptr;
+        n_processed = training ? c.take<uint32_t>((size_t)n_pixels) : nullptr;
+        bytes = c.bytes();
+    }
+};
+
+template <typename KeyT>
+struct InstanceLayout {
+    Rec* inst_recs;
+    KeyT* keys[2];
+    uint32_t* vals[2];
+    uint32_t* hist;
+    uint32_t* lookback;
+    size_t bytes;
+    InstanceLayout(char* blob, int n_inst, int end_bit) {
+        Carver c(blob);
+        const size_t ni = (size_t)(n_inst > 0 ? n_inst : 1);
+        inst_recs = c.take<Rec>(ni);  // first: the only part the backward reads
+        keys[0] = c.take<KeyT>(ni);
+        keys[1] = c.take<KeyT>(ni);
+        vals[0] = c.take<uint32_t>(ni);
+        vals[1] = c.take<uint32_t>(ni);
+        hist = c.take<uint32_t>(4 * kRadixMax);
+        lookback = c.take<uint32_t>(radix_sort_lookback_words(n_inst, end_bit));
+        bytes = c.bytes();
+    }
+};
+
+Cam make_cam(const fgs_settings& s, const float* w2c, const float* cam_position, const float* bg_color) {
+    Cam c{};
+    c.w2c = w2c;
+    c.cam_pos = cam_position;
+    c.bg = bg_color;
+    c.width = (float)s.width;
+    c.height = (float)s.height;
+    c.focal_x = s.focal_x;
+    c.focal_y = s.focal_y;
+    c.center_x = s.center_x;
+    c.center_y = s.center_y;
+    c.near_plane = s.near_plane;
+    c.far_plane = s.far_plane;
+    c.grid_w = div_up(s.width, kTileW);
+    c.grid_h = div_up(s.height, kTileH);
+    c.img_w = s.width;
+    c.img_h = s.height;
+    c.active_sh_bases = s.active_sh_bases;
+    c.total_sh_rest = s.total_sh_bases_rest;
+    c.proper_aa = s.proper_antialiasing;
+    return c;
+}
+
+// pinned read-back slot + event, created once per process
+struct Readback {
+    uint32_t* host = nullptr;
+    cudaEvent_t event = nullptr;
+};
+Readback& readback() {
+    static Readback rb;
+    return rb;
+}
+cudaError_t ensure_readback() {
+    Readback& rb = readback();
+    if (rb.host) return cudaSuccess;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&rb.host), 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    return cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming);
+}
+
+template <typename KeyT>
+int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl, const TileLayout& tl,
+                   const uint32_t* sorted_idx, int n_visible, int n_instances, int n_tiles, int end_bit,
+                   const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
+    InstanceLayout<KeyT> sizing(nullptr, n_instances, end_bit);
+    char* blob = resize(user_instance, sizing.bytes);
+    if (!blob) return fail_arg("instance buffer resize callback returned NULL");
+    InstanceLayout<KeyT> il(blob, n_instances, end_bit);
+    if (n_instances > 0) {
+        FGS_TRY(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, il.keys[0], il.vals[0],
+                                              pl.counters + kCtrVisible, n_visible, cam.grid_w, stream),
+                "create_instances");
+        bool in_alt = false;
+        FGS_TRY(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
+                                       n_instances, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
+                                       &in_alt, stream),
+                "tile sort");
+        FGS_TRY(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
+                                               tl.ranges, n_instances, stream),
+                "ranges_and_gather");
+    }
+    BlendFwdArgs a{};
+    a.inst_recs = il.inst_recs;
+    a.tile_ranges = tl.ranges;
+    a.image = image;
+    a.final_T = tl.final_T;
+    a.n_processed = tl.n_processed;
+    a.tile_max_n = tl.tile_max_n;
+    a.queue = pl.counters + kCtrTileQueue;
+    a.n_tiles = n_tiles;
+    a.training = training;
+    a.to_chw = to_chw;
+    a.clamp_output = clamp_output;
+    FGS_TRY(launch_blend_forward(a, cam, stream), "blend_forward");
+    return 0;
+}
+
+int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
+                 const float* scales, const float* rotations, const float* opacities, const float* sh0,
+                 const float* sh_rest, const float* w2c, const float* cam_position, const float* bg_color, float* image,
+                 int n, const fgs_settings* s, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
+                 fgs_forward_state* state_out) {
+    if (!resize || !s || !image) return fail_arg("fgs_forward: NULL argument");
+    if (s->width <= 0 || s->height <= 0) return fail_arg("fgs_forward: empty image");
+    if (s->total_sh_bases_rest < 0 || s->total_sh_bases_rest > 15) return fail_arg("fgs_forward: sh_rest must have <= 15 bases");
+    const Cam cam = make_cam(*s, w2c, cam_position, bg_color);
+    const int n_tiles = cam.grid_w * cam.grid_h;
+    const int n_pixels = s->width * s->height;
+    const int end_bit = bits_for(n_tiles - 1);
+    FGS_TRY(ensure_readback(), "readback alloc");
+
+    TileLayout tsz(nullptr, n_tiles, n_pixels, training);
+    char* tile_blob = resize(user_tile, tsz.bytes);
+    if (!tile_blob) return fail_arg("tile buffer resize callback returned NULL");
+    TileLayout tl(tile_blob, n_tiles, n_pixels, training);
+    PrimitiveLayout psz(nullptr, n);
+    char* prim_blob = resize(user_primitive, psz.bytes);
+    if (!prim_blob) return fail_arg("primitive buffer resize callback returned NULL");
+    PrimitiveLayout pl(prim_blob, n);
+
+    FGS_TRY(cudaMemsetAsync(pl.counters, 0, sizeof(uint32_t) * kCtrCount, stream), "memset counters");
+    // ranges and tile_max_n are adjacent in the layout only up to alignment: clear both explicitly
+    FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
+    FGS_TRY(cudaMemsetAsync(tl.tile_max_n, 0, sizeof(uint32_t) * n_tiles, stream), "memset tile_max_n");
+
+    FGS_TRY(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.keys[0],
+                              pl.idx[0], pl.counters, n, cam, !training, stream),
+            "preprocess");
+    Readback& rb = readback();
+    FGS_TRY(cudaMemcpyAsync(rb.host, pl.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "count read-back");
+    FGS_TRY(cudaEventRecord(rb.event, stream), "event record");
+
+    // depth order: bits [0, 32) of the positive float depth (sign bit is always 0 after the near cull)
+    bool in_alt = false;
+    FGS_TRY(radix_sort_pairs<uint32_t>(pl.keys[0], pl.keys[1], pl.idx[0], pl.idx[1], pl.counters + kCtrVisible, n, 32,
+                                       pl.hist, pl.lookback, pl.counters + kCtrTicket0, &in_alt, stream),
+            "depth sort");
+    const uint32_t* sorted_idx = pl.idx[in_alt ? 1 : 0];
+    FGS_TRY(launch_offsets_scan(sorted_idx, pl.n_touched, pl.offsets, pl.counters + kCtrVisible, n, pl.scan_lookback,
+                                pl.counters + kCtrTicket0 + 4, stream),
+            "offsets scan");
+
+    FGS_TRY(cudaEventSynchronize(rb.event), "count read-back wait");
+    const int n_visible = (int)rb.host[0];
+    const int n_instances = (int)rb.host[1];
+    if (n_instances < 0) return fail_arg("fgs_forward: more than 2^31 instances");
+    if (state_out) {
+        state_out->n_instances = n_instances;
+        state_out->n_buckets = 0;
+        state_out->selector = 0;
+        state_out->n_visible = n_visible;
+    }
+    if (end_bit <= 16)
+        return finish_forward<uint16_t>(resize, user_instance, pl, tl, sorted_idx, n_visible, n_instances, n_tiles,
+                                        end_bit, cam, image, training, to_chw, clamp_output, stream);
+    return finish_forward<uint32_t>(resize, user_instance, pl, tl, sorted_idx, n_visible, n_instances, n_tiles, end_bit,
+                                    cam, image, training, to_chw, clamp_output, stream);
+}
+
+int backward_impl(const float* grad_image, const float* image, const float* means, const float* scales,
+                  const float* rotations, const float* opacities, const float* sh_rest, const float* w2c,
+                  const float* cam_position, const float* bg_color, const char* primitive_buffers,
+                  const char* tile_buffers, const char* instance_buffers, PreBwdArgs pa, void* grad2d_scratch,
+                  float* densification_info, int n, const fgs_settings* s, const fgs_forward_state* state,
+                  cudaStream_t stream) {
+    if (!s || !state) return fail_arg("fgs_backward: NULL argument");
+    if (n <= 0) return 0;
+    const Cam cam = make_cam(*s, w2c, cam_position, bg_color);
+    const int n_tiles = cam.grid_w * cam.grid_h;
+    const int n_pixels = s->width * s->height;
+    const int end_bit = bits_for(n_tiles - 1);
+    PrimitiveLayout pl(const_cast<char*>(primitive_buffers), n);
+    TileLayout tl(const_cast<char*>(tile_buffers), n_tiles, n_pixels, true);
+    const Rec* inst_recs = end_bit <= 16
+                               ? InstanceLayout<uint16_t>(const_cast<char*>(instance_buffers), state->n_instances, end_bit).inst_recs
+                               : InstanceLayout<uint32_t>(const_cast<char*>(instance_buffers), state->n_instances, end_bit).inst_recs;
+    Grad2D* grad2d = reinterpret_cast<Grad2D*>(grad2d_scratch);
+    FGS_TRY(cudaMemsetAsync(grad2d, 0, sizeof(Grad2D) * (size_t)n, stream), "memset grad2d");
+    if (state->n_instances > 0) {
+        FGS_TRY(cudaMemsetAsync(pl.counters + kCtrTileQueueBwd, 0, sizeof(uint32_t), stream), "memset queue");
+        BlendBwdArgs ba{};
+        ba.inst_recs = inst_recs;
+        ba.tile_ranges = tl.ranges;
+        ba.image = image;
+        ba.grad_image = grad_image;
+        ba.final_T = tl.final_T;
+        ba.n_processed = tl.n_processed;
+        ba.tile_max_n = tl.tile_max_n;
+        ba.grad2d = grad2d;
+        ba.queue = pl.counters + kCtrTileQueueBwd;
+        ba.n_tiles = n_tiles;
+        FGS_TRY(launch_blend_backward(ba, cam, stream), "blend_backward");
+    }
+    pa.means = means;
+    pa.scales = scales;
+    pa.rotations = rotations;
+    pa.opacities = opacities;
+    pa.sh_rest = sh_rest;
+    pa.n_touched = pl.n_touched;
+    pa.grad2d = grad2d;
+    pa.densification_info = densification_info;
+    pa.n = n;
+    FGS_TRY(launch_preprocess_backward(pa, cam, stream), "preprocess_backward");
+    return 0;
+}
+
+}  // namespace
+}  // namespace fgs
+
+using namespace fgs;
+
+extern "C" {
+
+int fgs_abi_version(void) { return FGS_B200_ABI_VERSION; }
+const char* fgs_last_error(void) { return g_err; }
+
+int fgs_forward(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
+                const float* scales, const float* rotations, const float* opacities, const float* sh_coefficients_0,
+                const float* sh_coefficients_rest, const float* w2c, const float* cam_position, const float* bg_color,
+                float* image, int32_t n_primitives, const fgs_settings* settings, void* stream,
+                fgs_forward_state* state_out) {
+    return forward_impl(resize, user_primitive, user_tile, user_instance, means, scales, rotations, opacities,
+                        sh_coefficients_0, sh_coefficients_rest, w2c, cam_position, bg_color, image, n_primitives,
+                        settings, true, true, false, reinterpret_cast<cudaStream_t>(stream), state_out);
+}
+
+int fgs_inference(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
+                  const float* scales, const float* rotations, const float* opacities, const float* sh_coefficients_0,
+                  const float* sh_coefficients_rest, const float* w2c, const float* cam_position, const float* bg_color,
+                  float* image, int32_t n_primitives, const fgs_settings* settings, int32_t to_chw, int32_t clamp_output,
+                  void* stream) {
+    return forward_impl(resize, user_primitive, user_tile, user_instance, means, scales, rotations, opacities,
+                        sh_coefficients_0, sh_coefficients_rest, w2c, cam_position, bg_color, image, n_primitives,
+                        settings, false, to_chw != 0, clamp_output != 0, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+size_t fgs_grad2d_scratch_bytes(int32_t n_primitives) {
+    return sizeof(Grad2D) * (size_t)(n_primitives > 0 ? n_primitives : 1);
+}
+
+int fgs_backward(const float* grad_image, const float* image, const float* means, const float* scales,
+                 const float* rotations, const float* opacities, const float* sh_coefficients_rest, const float* w2c,
+                 const float* cam_position, const float* bg_color, const char* primitive_buffers,
+                 const char* tile_buffers, const char* instance_buffers, float* grad_means, float* grad_scales,
+                 float* grad_rotations, float* grad_opacities, float* grad_sh_coefficients_0,
+                 float* grad_sh_coefficients_rest, void* grad2d_scratch, float* densification_info, int32_t n_primitives,
+                 const fgs_settings* settings, const fgs_forward_state* state, void* stream) {
+    PreBwdArgs pa{};
+    pa.g_means = grad_means;
+    pa.g_scales = grad_scales;
+    pa.g_rotations = grad_rotations;
+    pa.g_opacities = grad_opacities;
+    pa.g_sh0 = grad_sh_coefficients_0;
+    pa.g_sh_rest = grad_sh_coefficients_rest;
+    pa.fused = false;
+    return backward_impl(grad_image, image, means, scales, rotations, opacities, sh_coefficients_rest, w2c, cam_position,
+                         bg_color, primitive_buffers, tile_buffers, instance_buffers, pa, grad2d_scratch,
+                         densification_info, n_primitives, settings, state, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fgs_backward_adam(const float* grad_image, const float* image, float* const params[6], float* const exp_avg[6],
+                      float* const exp_avg_sq[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
+                      double eps, const float* w2c, const float* cam_position, const float* bg_color,
+                      const char* primitive_buffers, const char* tile_buffers, const char* instance_buffers,
+                      void* grad2d_scratch, float* densification_info, int32_t n_primitives, const fgs_settings* settings,
+                      const fgs_forward_state* state, void* stream) {
+    PreBwdArgs pa{};
+    pa.fused = true;
+    for (int t = 0; t < 6; ++t) {
+        pa.p[t] = params[t];
+        pa.m[t] = exp_avg[t];
+        pa.v[t] = exp_avg_sq[t];
+        // bias corrections in double on the host, adam.cu:54-56
+        const double bc1_rcp = 1.0 / (1.0 - std::pow(beta1, (double)step[t]));
+        const double bc2_sqrt_rcp = 1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step[t]));
+        pa.hyper.step_size[t] = (float)(lr[t] * bc1_rcp);
+        pa.hyper.bias2_sqrt_rcp[t] = (float)bc2_sqrt_rcp;
+    }
+    pa.hyper.beta1 = (float)beta1;
+    pa.hyper.beta2 = (float)beta2;
+    pa.hyper.eps = (float)eps;
+    // the kernel reads the pre-update parameters: means/scales/rotations/opacities/sh_rest ARE params[]
+    return backward_impl(grad_image, image, params[0], params[1], params[2], params[3], params[5], w2c, cam_position,
+                         bg_color, primitive_buffers, tile_buffers, instance_buffers, pa, grad2d_scratch,
+                         densification_info, n_primitives, settings, state, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* exp_avg_sq, size_t n_elements,
+                  int32_t step_count, double learning_rate, double beta1, double beta2, double epsilon, void* stream) {
+    const double bc1_rcp = 1.0 / (1.0 - std::pow(beta1, (double)step_count));
+    const double bc2_sqrt_rcp = 1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step_count));
+    FGS_TRY(launch_adam(param_grad, param, exp_avg, exp_avg_sq, n_elements, (float)(learning_rate * bc1_rcp),
+                        (float)beta1, (float)beta2, (float)epsilon, (float)bc2_sqrt_rcp,
+                        reinterpret_cast<cudaStream_t>(stream)),
+            "adam_step");
+    return 0;
+}
+
+size_t fgs_sort_scratch_bytes(int32_t n_max, int32_t end_bit) {
+    return sizeof(uint32_t) * (4 * kRadixMax + radix_sort_lookback_words(n_max, end_bit) + 8) + 512;
+}
+
+int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
+                       int32_t n_max, int32_t end_bit, void* scratch, size_t scratch_bytes, int32_t* result_in_alt,
+                       void* stream) {
+    if (scratch_bytes < fgs_sort_scratch_bytes(n_max, end_bit)) return fail_arg("fgs_sort_pairs_u32: scratch too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Carver c(reinterpret_cast<char*>(scratch));
+    uint32_t* tickets = c.take<uint32_t>(8);
+    uint32_t* hist = c.take<uint32_t>(4 * kRadixMax);
+    uint32_t* lookback = c.take<uint32_t>(radix_sort_lookback_words(n_max, end_bit));
+    FGS_TRY(cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), st), "memset tickets");
+    bool in_alt = false;
+    FGS_TRY(radix_sort_pairs<uint32_t>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, hist, lookback, tickets,
+                                       &in_alt, st),
+            "radix_sort_pairs");
+    if (result_in_alt) *result_in_alt = in_alt ? 1 : 0;
+    return 0;
+}
+
+}  // extern "C"

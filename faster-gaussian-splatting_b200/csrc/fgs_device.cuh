@@ -1,0 +1,165 @@
+// fgs_device.cuh -- shared device-side definitions of the B200 Gaussian rasterizer.
+//
+// Semantics restated from the reference (cited per item); the code, data layout and
+// kernel decomposition are new and sm_100a-only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fgs {
+
+// ---- constants: rasterization_config.h:10-22,55-60 -------------------------------------------------
+constexpr float kDilation = 0.3f;
+constexpr float kDilationAA = 0.1f;
+constexpr float kMinCov2dDet = 1e-6f;
+constexpr float kMinAlpha = 1.0f / 255.0f;
+constexpr float kMinAlphaRcp = 255.0f;
+constexpr float kOneMinusAlphaEps = 1e-6f;
+constexpr float kTransmittanceThreshold = 1e-4f;
+constexpr int kTileW = 16;
+constexpr int kTileH = 12;
+constexpr int kSubW = 8;   // a warp owns an 8x4 sub-tile, lane -> (lane % 8, lane / 8)
+constexpr int kSubH = 4;
+constexpr int kTilePixels = kTileW * kTileH;   // 192
+constexpr int kBlendWarps = kTilePixels / 32;  // 6
+
+// ---- per-Gaussian 2D record (48 B, three float4) ---------------------------------------------------
+// q0 = (mean2d.x, mean2d.y, conic.x, conic.y)
+// q1 = (conic.z, opacity, color.r, color.g)          colour is stored UNCLAMPED (kernels_forward.cuh:197)
+// q2 = (color.b, bits(xmin | xmax << 16), bits(ymin | ymax << 16), bits(primitive index))
+struct __align__(16) Rec {
+    float4 q0, q1, q2;
+};
+static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
+
+// 2D gradient record accumulated by the blend backward (12 floats, three float4 so that one
+// REDG.F32x4 covers a third of it):
+// g0 = (dL/dmean2d.x, dL/dmean2d.y, dL/dconic.x, dL/dconic.y[per-entry, see kernels_backward.cuh:443-447])
+// g1 = (dL/dconic.z, dL/dopacity[w.r.t. raw logit unless AA], dL/dcolor.r, dL/dcolor.g)
+// g2 = (dL/dcolor.b, 0, 0, 0)
+struct __align__(16) Grad2D {
+    float4 g0, g1, g2;
+};
+static_assert(sizeof(Grad2D) == 48, "Grad2D must be 48 bytes");
+
+// Camera / launch constants passed by value to kernels (host struct mirrored in include/fgs_b200.h).
+struct Cam {
+    const float* w2c;      // DEVICE pointer: row-major world->camera matrix, rows 0..2 are read (12 floats)
+    const float* cam_pos;  // DEVICE pointer: 3 floats
+    const float* bg;       // DEVICE pointer: 3 floats
+    float width, height;
+    float focal_x, focal_y, center_x, center_y;
+    float near_plane, far_plane;
+    int   grid_w, grid_h;
+    int   img_w, img_h;
+    int   active_sh_bases;
+    int   total_sh_rest;      // sh_rest.size(1)
+    int   proper_aa;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---- exact tile test: kernel_utils.cuh:71-114 ("will_primitive_contribute") -------------------------
+// mean is the 2D mean shifted by -0.5 (pixel-centre coordinates), conic = (A, B, C).
+// Rectangle of pixel centres [rx0, rx0 + ext_x] x [ry0, ry0 + ext_y]; the reference uses it with
+// 16x12 tiles (ext = 15, 11); the blend kernels reuse it on 8x4 sub-tiles (ext = 7, 3).
+__device__ __forceinline__ bool rect_contributes(float mx, float my, float A, float B, float C,
+                                                 float rx0, float ry0, float ext_x, float ext_y, float tau) {
+    const float rx1 = rx0 + ext_x, ry1 = ry0 + ext_y;
+    const float x_min_diff = rx0 - mx;
+    const float x_left = x_min_diff >= 0.0f ? 1.0f : 0.0f;
+    const float not_in_x = x_left + (mx > rx1 ? 1.0f : 0.0f);
+    const float y_min_diff = ry0 - my;
+    const float y_above = y_min_diff >= 0.0f ? 1.0f : 0.0f;
+    const float not_in_y = y_above + (my > ry1 ? 1.0f : 0.0f);
+    if (not_in_x + not_in_y == 0.0f) return true;
+    const float cx = x_left != 0.0f ? rx0 : rx1;
+    const float cy = y_above != 0.0f ? ry0 : ry1;
+    const float diff_x = mx - cx, diff_y = my - cy;
+    const float dx = copysignf(ext_x, x_min_diff);
+    const float dy = copysignf(ext_y, y_min_diff);
+    const float tx = not_in_y * __saturatef((dx * A * diff_x + dx * B * diff_y) / (dx * A * dx));
+    const float ty = not_in_x * __saturatef((dy * B * diff_x + dy * C * diff_y) / (dy * C * dy));
+    const float ex = mx - (cx + tx * dx), ey = my - (cy + ty * dy);
+    const float power = 0.5f * (A * ex * ex + C * ey * ey) + B * ex * ey;
+    return power <= tau;
+}
+
+__device__ __forceinline__ bool tile_contributes(float mx, float my, float A, float B, float C,
+                                                 uint32_t tile_x, uint32_t tile_y, float tau) {
+    return rect_contributes(mx, my, A, B, C, (float)(tile_x * kTileW), (float)(tile_y * kTileH),
+                            (float)(kTileW - 1), (float)(kTileH - 1), tau);
+}
+
+// tile rectangle of a screen-space bounding box: kernel_utils.cuh:61-68
+__device__ __forceinline__ void tile_bounds_of(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax,
+                                               uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
+    tx0 = xmin / kTileW;
+    tx1 = (xmax + kTileW - 1) / kTileW;
+    ty0 = ymin / kTileH;
+    ty1 = (ymax + kTileH - 1) / kTileH;
+}
+
+// ---- mbarrier + bulk async copy (TMA 1-D bulk; SASS: UBLKCP / SYNCS) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; src/dst 16-B aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// named barrier over a subset of the CTA, with an AND reduction of a predicate (BAR.RED.AND)
+__device__ __forceinline__ bool named_bar_and(int id, int nthreads, bool pred) {
+    int r;
+    asm volatile(
+        "{ .reg .pred q, pr; setp.ne.s32 q, %3, 0; barrier.cta.red.and.pred pr, %1, %2, q; selp.s32 %0, 1, 0, pr; }"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"((int)pred)
+        : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+
+// q = -1/2 (A dx^2 + C dy^2) - B dx dy (kernels_forward.cuh:461).  The operation order is pinned
+// with explicit round-to-nearest intrinsics so that the forward and the backward kernel evaluate
+// bit-identical alphas (the backward replays the forward's skip/stop decisions).
+__device__ __forceinline__ float blend_power(float A, float B, float C, float dx, float dy) {
+    const float s = __fmaf_rn(C, __fmul_rn(dy, dy), __fmul_rn(A, __fmul_rn(dx, dx)));
+    return __fmaf_rn(-0.5f, s, -__fmul_rn(B, __fmul_rn(dx, dy)));
+}
+
+}  // namespace fgs

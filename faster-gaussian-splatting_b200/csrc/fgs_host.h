@@ -1,0 +1,127 @@
+// fgs_host.h -- host-side declarations shared by the kernels' launchers and the C-ABI drivers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "fgs_device.cuh"
+
+namespace fgs {
+
+// device counter block (uint32 each); zeroed at the start of every forward
+enum : int {
+    kCtrVisible = 0,    // V: number of visible Gaussians
+    kCtrInstances = 1,  // I: number of (Gaussian, tile) instances
+    kCtrTileQueue = 2,  // persistent blend-forward tile queue
+    kCtrTileQueueBwd = 3,
+    kCtrTicket0 = 4,    // tickets for the chained-scan kernels (one per launch): 4..15
+    kCtrCount = 16
+};
+
+constexpr int kSortBlock = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortBlock * kSortItems;  // keys per block per pass
+constexpr int kRadixMax = 256;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- launchers ---------------------------------------------------------------------------------------
+cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
+                              const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
+                              uint32_t* n_touched, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
+                              int n, const Cam& cam, bool inference, cudaStream_t stream);
+
+// LSD radix sort of (key, value) pairs, onesweep style (one read + one write of the data per pass).
+// `n_dev` points at the element count on the device, `n_max` bounds it on the host (grid sizing).
+// Keys are KeyT in {uint16_t, uint32_t}; bits [0, end_bit) are sorted.  `hist` needs
+// passes * 256 uint32, `lookback` needs passes * div_up(n_max, kSortTile) * 256 uint32; both are
+// zeroed inside.  Returns in *result_in_alt whether the sorted data ended in the *_alt buffers.
+template <typename KeyT>
+cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
+                             int n_max, int end_bit, uint32_t* hist, uint32_t* lookback, uint32_t* tickets,
+                             bool* result_in_alt, cudaStream_t stream);
+size_t radix_sort_lookback_words(int n_max, int end_bit);
+int radix_sort_passes(int end_bit);
+
+// offsets[i] = exclusive prefix sum over i of n_touched[sorted_idx[i]], i < *n_dev
+cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_touched, uint32_t* offsets,
+                                const uint32_t* n_dev, int n_max, uint32_t* lookback, uint32_t* ticket,
+                                cudaStream_t stream);
+size_t offsets_scan_lookback_words(int n_max);
+
+template <typename KeyT>
+cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
+                                    KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
+                                    int grid_w, cudaStream_t stream);
+
+// per-tile [start, end) ranges from the tile-sorted keys + gather of the 48-byte records into
+// instance order (tile-contiguous, so the blend kernels can bulk-copy them)
+template <typename KeyT>
+cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
+                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, cudaStream_t stream);
+
+struct BlendFwdArgs {
+    const Rec* inst_recs;
+    const uint2* tile_ranges;
+    float* image;             // (3,H,W) or (H,W,3)
+    float* final_T;           // per pixel, training only
+    uint32_t* n_processed;    // per pixel, training only
+    uint32_t* tile_max_n;     // per tile, training only
+    uint32_t* queue;          // tile queue counter
+    int n_tiles;
+    bool training;
+    bool to_chw;
+    bool clamp_output;
+};
+cudaError_t launch_blend_forward(const BlendFwdArgs& a, const Cam& cam, cudaStream_t stream);
+
+struct BlendBwdArgs {
+    const Rec* inst_recs;
+    const uint2* tile_ranges;
+    const float* image;
+    const float* grad_image;
+    const float* final_T;
+    const uint32_t* n_processed;
+    const uint32_t* tile_max_n;
+    Grad2D* grad2d;           // indexed by primitive index, zeroed by the caller
+    uint32_t* queue;
+    int n_tiles;
+};
+cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream);
+
+struct AdamHyper {
+    float step_size[6];            // lr / (1 - beta1^t) per tensor: means, scales, rotations, opacities, sh0, sh_rest
+    float bias2_sqrt_rcp[6];       // 1 / sqrt(1 - beta2^t)
+    float beta1, beta2, eps;
+};
+struct PreBwdArgs {
+    const float* means;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* sh_rest;
+    const uint32_t* n_touched;
+    const Grad2D* grad2d;
+    float* densification_info;     // (2,N) or nullptr
+    // unfused: gradient outputs (every row written, zeros for invisible Gaussians)
+    float* g_means;
+    float* g_scales;
+    float* g_rotations;
+    float* g_opacities;
+    float* g_sh0;
+    float* g_sh_rest;
+    // fused backward + Adam: parameters and moments updated in place, no gradient tensors
+    float* p[6];
+    float* m[6];
+    float* v[6];
+    AdamHyper hyper;
+    bool fused;
+    int n;
+};
+cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream);
+
+cudaError_t launch_adam(const float* grad, float* param, float* exp_avg, float* exp_avg_sq, size_t n, float step_size,
+                        float beta1, float beta2, float eps, float bias2_sqrt_rcp, cudaStream_t stream);
+
+}  // namespace fgs

@@ -1,0 +1,208 @@
+"""`_C`: the native-module surface of the reference, served by libfgs_b200.so.
+
+Same function names, argument order, argument meaning and return tuples as the reference's
+pybind11 module (/root/reference/FasterGSCudaBackend/FasterGSCudaBackend/torch_bindings/bindings.cpp:12-21,
+rasterization/include/rasterization_api.h:8-106, adam/include/adam.h:7-16), so that the reference's
+own torch_bindings/*.py run unchanged on top of this module.  torch is used for device memory and
+the current stream only; all computation happens in the hand-written sm_100a kernels behind the
+C ABI (include/fgs_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+_lib = _capi.load()
+
+# ---- scratch management: the C ABI grows caller-owned buffers through callbacks ----------------
+_PRIMITIVE, _TILE, _INSTANCE = 1, 2, 3
+_current: dict[int, torch.Tensor] = {}
+_current_device = None
+
+
+def _resize(user, nbytes):
+    t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_current_device)
+    _current[int(user)] = t
+    return t.data_ptr()
+
+
+_resize_cb = _capi.ResizeFn(_resize)
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def _check_param(t: torch.Tensor, name: str) -> None:
+    # the reference only checks this in debug builds (rasterization_api.cu:35-41); here it is always on
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(f"Input tensor '{name}' must be a contiguous CUDA float tensor.")
+
+
+def _aux(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _settings(active_sh_bases, total_rest, width, height, fx, fy, cx, cy, near, far, aa) -> _capi.Settings:
+    return _capi.Settings(int(active_sh_bases), int(total_rest), int(width), int(height), float(fx), float(fy),
+                          float(cx), float(cy), float(near), float(far), int(bool(aa)))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c, cam_position,
+            bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+            proper_antialiasing):
+    """rasterization_api.h:8-28.  Returns (image, primitive_buffers, tile_buffers, instance_buffers,
+    bucket_buffers, n_instances, n_buckets, selector); the buffers are opaque."""
+    global _current_device
+    for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
+                    (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
+        _check_param(t, name)
+    dev = means.device
+    with torch.cuda.device(dev):
+        n = means.shape[0]
+        total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
+        image = torch.empty((3, int(height), int(width)), dtype=torch.float32, device=dev)
+        w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
+        st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                       far_plane, proper_antialiasing)
+        state = _capi.ForwardState()
+        _current_device = dev
+        _current.clear()
+        rc = _lib.fgs_forward(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales), _ptr(rotations),
+                              _ptr(opacities), _ptr(sh_coefficients_0), _ptr(sh_coefficients_rest), _ptr(w2c_c),
+                              _ptr(pos_c), _ptr(bg_c), _ptr(image), n, C.byref(st), _stream(), C.byref(state))
+        _capi.check(rc, 'forward')
+        empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        prim, tile, inst = (_current.pop(k, empty) for k in (_PRIMITIVE, _TILE, _INSTANCE))
+    return image, prim, tile, inst, empty, state.n_instances, state.n_buckets, state.selector
+
+
+def _backward_common(image, primitive_buffers, w2c, cam_position, bg_color, grad_image, densification_info,
+                     sh_coefficients_rest, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y,
+                     near_plane, far_plane, proper_antialiasing, n_instances):
+    dev = image.device
+    n_total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
+    st = _settings(active_sh_bases, n_total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                   far_plane, proper_antialiasing)
+    state = _capi.ForwardState(int(n_instances), 0, 0, 0)
+    w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
+    gi = grad_image.to(dtype=torch.float32).contiguous()
+    dens_ptr = None
+    if densification_info is not None and densification_info.numel() > 0:
+        if not (densification_info.is_cuda and densification_info.dtype == torch.float32
+                and densification_info.is_contiguous()):
+            raise RuntimeError("'densification_info' must be a contiguous CUDA float tensor.")
+        dens_ptr = _ptr(densification_info)
+    return dev, st, state, w2c_c, pos_c, bg_c, gi, dens_ptr
+
+
+def backward(densification_info, grad_image, image, means, scales, rotations, opacities, sh_coefficients_rest,
+             primitive_buffers, tile_buffers, instance_buffers, bucket_buffers, w2c, cam_position, bg_color,
+             active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+             proper_antialiasing, n_instances, n_buckets, instance_primitive_indices_selector):
+    """rasterization_api.h:30-59.  Returns the six gradient tensors."""
+    dev, st, state, w2c_c, pos_c, bg_c, gi, dens_ptr = _backward_common(
+        image, primitive_buffers, w2c, cam_position, bg_color, grad_image, densification_info, sh_coefficients_rest,
+        active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+        proper_antialiasing, n_instances)
+    with torch.cuda.device(dev):
+        n = means.shape[0]
+        grads = [torch.empty_like(p) for p in (means, scales, rotations, opacities)]
+        g_sh0 = torch.empty((n, 1, 3), dtype=torch.float32, device=dev)
+        g_rest = torch.empty_like(sh_coefficients_rest)
+        scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)
+        rc = _lib.fgs_backward(_ptr(gi), _ptr(image), _ptr(means), _ptr(scales), _ptr(rotations), _ptr(opacities),
+                               _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c),
+                               _ptr(primitive_buffers), _ptr(tile_buffers), _ptr(instance_buffers), _ptr(grads[0]),
+                               _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(g_sh0), _ptr(g_rest),
+                               _ptr(scratch), dens_ptr, n, C.byref(st), C.byref(state), _stream())
+        _capi.check(rc, 'backward')
+    return grads[0], grads[1], grads[2], grads[3], g_sh0, g_rest
+
+
+def backward_adam(densification_info, grad_image, image, params, exp_avgs, exp_avg_sqs, steps, lrs, beta1, beta2, eps,
+                  primitive_buffers, tile_buffers, instance_buffers, w2c, cam_position, bg_color, active_sh_bases,
+                  width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane, proper_antialiasing,
+                  n_instances) -> None:
+    """FasterGSFused semantics: backward + FusedAdam.step in one pass (include/fgs_b200.h).
+    `params`, `exp_avgs`, `exp_avg_sqs`: six tensors each in the order means, scales, rotations,
+    opacities, sh_coefficients_0, sh_coefficients_rest; updated in place."""
+    dev, st, state, w2c_c, pos_c, bg_c, gi, dens_ptr = _backward_common(
+        image, primitive_buffers, w2c, cam_position, bg_color, grad_image, densification_info, params[5],
+        active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+        proper_antialiasing, n_instances)
+    for group in (params, exp_avgs, exp_avg_sqs):
+        for t in group:
+            _check_param(t, 'param/state')
+    with torch.cuda.device(dev):
+        n = params[0].shape[0]
+        scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)
+        arr = lambda ts: (C.c_void_p * 6)(*[_ptr(t) for t in ts])
+        rc = _lib.fgs_backward_adam(_ptr(gi), _ptr(image), arr(params), arr(exp_avgs), arr(exp_avg_sqs),
+                                    (C.c_int32 * 6)(*[int(s) for s in steps]),
+                                    (C.c_double * 6)(*[float(l) for l in lrs]), float(beta1), float(beta2), float(eps),
+                                    _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(primitive_buffers), _ptr(tile_buffers),
+                                    _ptr(instance_buffers), _ptr(scratch), dens_ptr, n, C.byref(st), C.byref(state),
+                                    _stream())
+        _capi.check(rc, 'backward_adam')
+
+
+def inference(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c, cam_position,
+              bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+              proper_antialiasing, to_chw, clamp_output):
+    """rasterization_api.h:61-83."""
+    global _current_device
+    for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
+                    (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
+        _check_param(t, name)
+    dev = means.device
+    with torch.cuda.device(dev):
+        n = means.shape[0]
+        total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
+        shape = (3, int(height), int(width)) if to_chw else (int(height), int(width), 3)
+        image = torch.empty(shape, dtype=torch.float32, device=dev)
+        w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
+        st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                       far_plane, proper_antialiasing)
+        _current_device = dev
+        _current.clear()
+        rc = _lib.fgs_inference(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales), _ptr(rotations),
+                                _ptr(opacities), _ptr(sh_coefficients_0), _ptr(sh_coefficients_rest), _ptr(w2c_c),
+                                _ptr(pos_c), _ptr(bg_c), _ptr(image), n, C.byref(st), int(bool(to_chw)),
+                                int(bool(clamp_output)), _stream())
+        _capi.check(rc, 'inference')
+        # scratch must outlive the enqueued kernels: the caching allocator keeps it stream-ordered
+        _current.clear()
+    return image
+
+
+def adam_step(param_grad, param, exp_avg, exp_avg_sq, step_count, learning_rate, beta1, beta2, epsilon) -> None:
+    """adam/include/adam.h:7-16."""
+    for t, name in ((param_grad, 'param_grad'), (param, 'param'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
+        _check_param(t, name)
+    with torch.cuda.device(param.device):
+        rc = _lib.fgs_adam_step(_ptr(param_grad), _ptr(param), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
+                                int(step_count), float(learning_rate), float(beta1), float(beta2), float(epsilon),
+                                _stream())
+        _capi.check(rc, 'adam_step')
+
+
+def _not_on_hot_path(name):
+    def fn(*_args, **_kwargs):
+        raise NotImplementedError(
+            f'fgs_b200._C.{name}: outside the accelerated hot path of this round (SURVEY.md §8f "next" rows)')
+    fn.__name__ = name
+    return fn
+
+
+pruning_scores = _not_on_hot_path('pruning_scores')
+update_3d_filter = _not_on_hot_path('update_3d_filter')
+relocation_adjustment = _not_on_hot_path('relocation_adjustment')
+add_noise = _not_on_hot_path('add_noise')

@@ -1,0 +1,102 @@
+"""ctypes binding of libfgs_b200.so (the C ABI declared in include/fgs_b200.h).
+
+The library is the product: there is no Python/torch fallback.  If it cannot be loaded the import
+fails loudly (the reference raises Framework.ExtensionError in the same situation,
+/root/reference/FasterGSCudaBackend/__init__.py:19-20).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / 'lib' / 'libfgs_b200.so'
+
+ResizeFn = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class Settings(C.Structure):
+    """struct fgs_settings"""
+    _fields_ = [
+        ('active_sh_bases', C.c_int32),
+        ('total_sh_bases_rest', C.c_int32),
+        ('width', C.c_int32),
+        ('height', C.c_int32),
+        ('focal_x', C.c_float),
+        ('focal_y', C.c_float),
+        ('center_x', C.c_float),
+        ('center_y', C.c_float),
+        ('near_plane', C.c_float),
+        ('far_plane', C.c_float),
+        ('proper_antialiasing', C.c_int32),
+    ]
+
+
+class ForwardState(C.Structure):
+    """struct fgs_forward_state"""
+    _fields_ = [
+        ('n_instances', C.c_int32),
+        ('n_buckets', C.c_int32),
+        ('selector', C.c_int32),
+        ('n_visible', C.c_int32),
+    ]
+
+
+_P = C.c_void_p
+_PtrArr6 = C.c_void_p * 6
+_I32Arr6 = C.c_int32 * 6
+_F64Arr6 = C.c_double * 6
+
+# name -> (restype, argtypes); must list every function declared in include/fgs_b200.h
+SIGNATURES = {
+    'fgs_abi_version': (C.c_int, []),
+    'fgs_last_error': (C.c_char_p, []),
+    'fgs_forward': (C.c_int, [ResizeFn, _P, _P, _P] + [_P] * 9 + [_P, C.c_int32, C.POINTER(Settings), _P,
+                                                                    C.POINTER(ForwardState)]),
+    'fgs_grad2d_scratch_bytes': (C.c_size_t, [C.c_int32]),
+    'fgs_backward': (C.c_int, [_P] * 10 + [_P] * 3 + [_P] * 6 + [_P, _P, C.c_int32, C.POINTER(Settings),
+                                                                    C.POINTER(ForwardState), _P]),
+    'fgs_backward_adam': (C.c_int, [_P, _P, _PtrArr6, _PtrArr6, _PtrArr6, _I32Arr6, _F64Arr6, C.c_double,
+                                     C.c_double, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
+                                     C.POINTER(Settings), C.POINTER(ForwardState), _P]),
+    'fgs_inference': (C.c_int, [ResizeFn, _P, _P, _P] + [_P] * 9 + [_P, C.c_int32, C.POINTER(Settings), C.c_int32,
+                                                                      C.c_int32, _P]),
+    'fgs_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, _P]),
+    'fgs_sort_pairs_u32': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,
+                                      C.POINTER(C.c_int32), _P]),
+    'fgs_sort_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library (building it first if only the sources are present and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() or os.environ.get('FGS_B200_REBUILD'):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('fgs_b200_build', _PKG.parent / 'build.py')
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build(force=bool(os.environ.get('FGS_B200_REBUILD')))
+    if not LIB_PATH.exists():
+        raise ImportError(f'fgs_b200: {LIB_PATH} is missing and could not be built; there is no fallback path')
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fgs_abi_version() != 1:
+        raise ImportError('fgs_b200: ABI version mismatch between libfgs_b200.so and the Python binding')
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().fgs_last_error().decode(errors='replace')
+        raise RuntimeError(f'fgs_b200 {what} failed (status {status}): {msg}')

@@ -1,0 +1,122 @@
+"""Python operator API of the rasterizer: same names, arguments and behaviour as the reference's
+torch_bindings/rasterization.py (RasterizerSettings :8-38, _Rasterize :41-110, diff_rasterize
+:113-132, rasterize :135-156, update_pruning_scores :159-178), backed by fgs_b200._C.
+
+Additional entry point `diff_rasterize_fused` gives the FasterGSFused behaviour (README.md:37):
+the backward pass applies the FusedAdam update in the same kernel and returns no gradients."""
+from typing import Any, NamedTuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from .. import _C
+
+
+class RasterizerSettings(NamedTuple):
+    w2c: torch.Tensor  # affine transformation from model/world space to view space
+    cam_position: torch.Tensor  # camera position in world space
+    bg_color: torch.Tensor  # background color in RGB format
+    active_sh_bases: int  # number of spherical harmonics bases to use for color computation
+    width: int  # width of the image plane in pixels
+    height: int  # height of the image plane in pixels
+    focal_x: float  # focal length in x direction in pixels
+    focal_y: float  # focal length in y direction in pixels
+    center_x: float  # x coordinate of the image center in pixels (positive -> right)
+    center_y: float  # y coordinate of the image center in pixels (positive -> down)
+    near_plane: float  # near clipping plane distance
+    far_plane: float  # far clipping plane distance
+    proper_antialiasing: bool  # whether to use proper antialiasing
+
+    def as_tuple(self) -> tuple:
+        return tuple(self)
+
+
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                densification_info, rasterizer_settings: RasterizerSettings) -> torch.Tensor:
+        (image, primitive_buffers, tile_buffers, instance_buffers, bucket_buffers,
+         n_instances, n_buckets, selector) = _C.forward(
+            means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+            *rasterizer_settings.as_tuple())
+        ctx.rasterizer_settings = rasterizer_settings
+        ctx.buffer_state = (n_instances, n_buckets, selector)
+        ctx.save_for_backward(image, means, scales, rotations, opacities, sh_coefficients_rest,
+                              primitive_buffers, tile_buffers, instance_buffers, bucket_buffers)
+        ctx.densification_info = densification_info
+        ctx.mark_non_differentiable(densification_info)
+        return image
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx: Any, grad_image: torch.Tensor):
+        grads = _C.backward(ctx.densification_info, grad_image, *ctx.saved_tensors,
+                            *ctx.rasterizer_settings.as_tuple(), *ctx.buffer_state)
+        return (*grads, None, None)
+
+
+class _RasterizeFused(torch.autograd.Function):
+    """Forward identical to _Rasterize; backward = gradient + Adam update in one kernel.  The six
+    parameters must be leaves managed by `optimizer` (one tensor per group).  No gradients are
+    returned, so a following `optimizer.step()` is a no-op for them (adam.py:17-18)."""
+
+    @staticmethod
+    def forward(ctx: Any, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                densification_info, rasterizer_settings: RasterizerSettings, optimizer) -> torch.Tensor:
+        (image, primitive_buffers, tile_buffers, instance_buffers, _bucket_buffers,
+         n_instances, _n_buckets, _selector) = _C.forward(
+            means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+            *rasterizer_settings.as_tuple())
+        ctx.rasterizer_settings = rasterizer_settings
+        ctx.n_instances = n_instances
+        ctx.params = (means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest)
+        ctx.optimizer = optimizer
+        ctx.save_for_backward(image, primitive_buffers, tile_buffers, instance_buffers)
+        ctx.densification_info = densification_info
+        ctx.mark_non_differentiable(densification_info)
+        return image
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx: Any, grad_image: torch.Tensor):
+        image, primitive_buffers, tile_buffers, instance_buffers = ctx.saved_tensors
+        opt = ctx.optimizer
+        params = [p.detach() for p in ctx.params]
+        groups = [opt.group_of(p) for p in ctx.params]
+        states = [opt._state_for(p) for p in ctx.params]
+        betas, eps = groups[0]['betas'], groups[0]['eps']
+        for g in groups:
+            if g['betas'] != betas or g['eps'] != eps:
+                raise RuntimeError('diff_rasterize_fused: all six param groups must share betas and eps')
+        for s in states:
+            s['step'] += 1
+        _C.backward_adam(ctx.densification_info, grad_image, image, params,
+                         [s['exp_avg'] for s in states], [s['exp_avg_sq'] for s in states],
+                         [s['step'] for s in states], [g['lr'] for g in groups], betas[0], betas[1], eps,
+                         primitive_buffers, tile_buffers, instance_buffers,
+                         *ctx.rasterizer_settings.as_tuple(), ctx.n_instances)
+        return (None,) * 9
+
+
+def diff_rasterize(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                   densification_info, rasterizer_settings: RasterizerSettings) -> torch.Tensor:
+    return _Rasterize.apply(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                            densification_info, rasterizer_settings)
+
+
+def diff_rasterize_fused(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                         densification_info, rasterizer_settings: RasterizerSettings, optimizer) -> torch.Tensor:
+    return _RasterizeFused.apply(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                                 densification_info, rasterizer_settings, optimizer)
+
+
+def rasterize(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+              rasterizer_settings: RasterizerSettings, to_chw: bool, clamp_output: bool = True) -> torch.Tensor:
+    return _C.inference(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                        *rasterizer_settings.as_tuple(), to_chw, clamp_output)
+
+
+def update_pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                          rasterizer_settings: RasterizerSettings) -> torch.Tensor:
+    return _C.pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
+                             *rasterizer_settings.as_tuple())

@@ -1,0 +1,127 @@
+/* fgs_b200.h -- C ABI of the B200-native Gaussian rasterizer (libfgs_b200.so).
+ *
+ * Drop-in boundary for the hot path of nerficg-project/faster-gaussian-splatting.  The reference
+ * exposes this path as a pybind11 module over torch::Tensor (torch_bindings/bindings.cpp:12-21);
+ * below it sits a torch-free layer taking raw device pointers and `std::function<char*(size_t)>`
+ * resize callbacks (rasterization/include/forward.h:10-36, backward.h:8-44, inference.h:9-36,
+ * adam/include/adam.h:7-16).  This header restates exactly that layer as plain C: pointers, sizes,
+ * a CUDA stream and C callbacks -- no torch types.
+ *
+ * Conventions
+ *  - every `const float*` / `float*` is a DEVICE pointer to contiguous float32 data, including
+ *    w2c / cam_position / bg_color (the reference's kernels dereference them on the device too,
+ *    rasterization_api.cu:68-70);
+ *  - parameter layouts are the reference's: means (N,3), scales (N,3) raw log-scales, rotations (N,4)
+ *    unnormalised (w,x,y,z), opacities (N,1) logits, sh0 (N,1,3), sh_rest (N,R,3), image (3,H,W);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (the reference uses the
+ *    legacy default stream);
+ *  - scratch memory is owned by the caller and grown through `fgs_resize_fn` callbacks
+ *    (utils/torch_utils.h:6-12): the callback must return a device pointer, aligned to >= 128 bytes,
+ *    to at least `bytes` bytes that stay valid until the matching backward has run; the contents are
+ *    opaque and only ever passed back to fgs_backward*;
+ *  - return value: 0 on success, otherwise a cudaError_t value (or -1 for argument errors); the text
+ *    is available from fgs_last_error().  The reference's release build has no error checking at all
+ *    (utils/utils.h:8-15); the Python layer turns a non-zero status into RuntimeError like the
+ *    reference's debug build does.
+ *  - not thread-safe per process (same as the reference's function-local static stream,
+ *    rasterization/src/forward.cu:47-53).
+ */
+#ifndef FGS_B200_H_
+#define FGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGS_B200_ABI_VERSION 1
+
+/* std::function<char*(size_t)> of forward.h:11-14 as a C callback */
+typedef char* (*fgs_resize_fn)(void* user, size_t bytes);
+
+/* Scalar camera / render settings: RasterizerSettings minus the three device tensors
+ * (torch_bindings/rasterization.py:8-21). */
+typedef struct fgs_settings {
+    int32_t active_sh_bases;     /* 1, 4, 9 or 16 */
+    int32_t total_sh_bases_rest; /* sh_rest.size(1) */
+    int32_t width;
+    int32_t height;
+    float focal_x;
+    float focal_y;
+    float center_x;
+    float center_y;
+    float near_plane;
+    float far_plane;
+    int32_t proper_antialiasing;
+} fgs_settings;
+
+/* Opaque forward state handed to the backward (the reference's n_instances / n_buckets / selector
+ * ints, rasterization_api.h:8-28). */
+typedef struct fgs_forward_state {
+    int32_t n_instances;
+    int32_t n_buckets;   /* always 0: this implementation keeps no bucket checkpoints */
+    int32_t selector;    /* always 0 */
+    int32_t n_visible;
+} fgs_forward_state;
+
+int fgs_abi_version(void);
+const char* fgs_last_error(void);
+
+/* forward.h:10-36 -- differentiable forward.  Writes image (3,H,W). */
+int fgs_forward(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance,
+                const float* means, const float* scales, const float* rotations, const float* opacities,
+                const float* sh_coefficients_0, const float* sh_coefficients_rest, const float* w2c,
+                const float* cam_position, const float* bg_color, float* image, int32_t n_primitives,
+                const fgs_settings* settings, void* stream, fgs_forward_state* state_out);
+
+/* backward.h:8-44 -- writes the six gradient tensors (every row; zeros for invisible Gaussians).
+ * `grad2d_scratch` is a caller-provided device buffer of fgs_grad2d_scratch_bytes(n) bytes (the
+ * reference's grad_mean2d / grad_conic helpers, rasterization_api.cu:133-134); it is zeroed inside.
+ * `densification_info` is (2,N) or NULL. */
+size_t fgs_grad2d_scratch_bytes(int32_t n_primitives);
+int fgs_backward(const float* grad_image, const float* image, const float* means, const float* scales,
+                 const float* rotations, const float* opacities, const float* sh_coefficients_rest,
+                 const float* w2c, const float* cam_position, const float* bg_color,
+                 const char* primitive_buffers, const char* tile_buffers, const char* instance_buffers,
+                 float* grad_means, float* grad_scales, float* grad_rotations, float* grad_opacities,
+                 float* grad_sh_coefficients_0, float* grad_sh_coefficients_rest, void* grad2d_scratch,
+                 float* densification_info, int32_t n_primitives, const fgs_settings* settings,
+                 const fgs_forward_state* state, void* stream);
+
+/* FasterGSFused semantics (README.md:37; branch not in the reference tree): backward followed by
+ * FusedAdam.step on the six tensors, in one pass -- parameters / exp_avg / exp_avg_sq are updated
+ * in place and no gradient tensor is materialised.  Tensor order everywhere: means, scales,
+ * rotations, opacities, sh_coefficients_0, sh_coefficients_rest.  `step` is the 1-based Adam step
+ * of each tensor AFTER this update (adam.py:29). */
+int fgs_backward_adam(const float* grad_image, const float* image, float* const params[6],
+                      float* const exp_avg[6], float* const exp_avg_sq[6], const int32_t step[6],
+                      const double lr[6], double beta1, double beta2, double eps, const float* w2c,
+                      const float* cam_position, const float* bg_color, const char* primitive_buffers,
+                      const char* tile_buffers, const char* instance_buffers, void* grad2d_scratch,
+                      float* densification_info, int32_t n_primitives, const fgs_settings* settings,
+                      const fgs_forward_state* state, void* stream);
+
+/* inference.h:9-36 -- forward without backward state; image is (3,H,W) if to_chw else (H,W,3). */
+int fgs_inference(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance,
+                  const float* means, const float* scales, const float* rotations, const float* opacities,
+                  const float* sh_coefficients_0, const float* sh_coefficients_rest, const float* w2c,
+                  const float* cam_position, const float* bg_color, float* image, int32_t n_primitives,
+                  const fgs_settings* settings, int32_t to_chw, int32_t clamp_output, void* stream);
+
+/* adam.h:7-16 -- one dense Adam step on one tensor of n_elements floats. */
+int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* exp_avg_sq,
+                  size_t n_elements, int32_t step_count, double learning_rate, double beta1, double beta2,
+                  double epsilon, void* stream);
+
+/* Building blocks exported for the unit tests (each is one stage of fgs_forward). */
+int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                       const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,
+                       size_t scratch_bytes, int32_t* result_in_alt, void* stream);
+size_t fgs_sort_scratch_bytes(int32_t n_max, int32_t end_bit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGS_B200_H_ */
