@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json: train iters/s @ 1M Gaussians, 1080p).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one training iteration of the reference's Trainer loop (Trainer.py:170-201) on one view:
+diff_rasterize forward + L1 loss + backward + FusedAdam.step + zero_grad, through the public Python
+operator API (the call a user of the reference makes).  Synthetic scene of the named shape
+(fgs_b200/synthetic.py), random-init parameters, fp32 arithmetic.
+
+Prints ONE JSON line on rank 0.  Keys: see DESIGN.md "Measurement".  With N > 1 every rank renders its
+own view of an N-view batch (weak scaling), gradients are summed with one NCCL all-reduce per tensor
+and every rank applies the identical Adam step; value = views trained per second over all ranks.
+`--impl reference` runs the UNMODIFIED reference CUDA backend from baseline/_ref through the same loop
+(north_star: "next to the reference's own CUDA path"); if it is not installed, the CPU oracle port
+is timed instead and the line says so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / 'faster-gaussian-splatting_b200'))
+sys.path.insert(0, str(ROOT))
+
+N_GAUSSIANS, WIDTH, HEIGHT, SH_BASES, N_VIEWS = 1_000_000, 1920, 1080, 16, 8
+LRS = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]  # means, scales, rotations, opacities, sh0, sh_rest (Trainer.py:56-66)
+METRIC = 'train_iters_per_sec_1M_gaussians_1080p'
+
+
+def peak_hbm_gbs():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def algorithmic_bytes(N, V, I, P, T, S=45):
+    """compulsory bytes per stage and per unfused training iteration."""
+    st = {
+        'preprocess': 44 * N + (12 + 4 * S) * V + 4 * N + 56 * V,
+        'depth sort': 16 * V,
+        'create_instances': 48 * V + 6 * I,
+        'tile sort': 12 * I,
+        'ranges_and_gather': 2 * I + 8 * T,
+        'blend_forward': 4 * I + 44 * V + 8 * T + 20 * P,
+        'blend_backward': 4 * I + 44 * V + 32 * P + 36 * V,
+        'preprocess_backward': 4 * N + (80 + 4 * S) * V + (56 + 4 * S) * V + 16 * V + 236 * N,
+        'adam_step': 1652 * N,
+    }
+    st['iteration'] = 1940 * N + (408 + 12 * S) * V + 28 * I + 52 * P + 16 * T
+    return st
+
+
+def make_problem(device, n=N_GAUSSIANS, w=WIDTH, h=HEIGHT, views=N_VIEWS):
+    from fgs_b200 import synthetic as syn
+    sc = syn.make_scene(n, 0)
+    cams = [syn.make_camera(k, w, h, n_views=views) for k in range(views)]
+    targets = [syn.make_target(w, h, seed=k) for k in range(views)]
+    return sc, cams, targets
+
+
+def settings_tuple(cam, device, bg):
+    return (cam.w2c.to(device), cam.position.to(device), bg, SH_BASES, cam.width, cam.height, cam.focal_x,
+            cam.focal_y, cam.center_x, cam.center_y, cam.near_plane, cam.far_plane, False)
+
+
+def load_backend(impl):
+    if impl == 'reference':
+        from tests import util
+        ref = util.load_reference()
+        return ref
+    import fgs_b200
+    return fgs_b200
+
+
+def run_gpu(args, impl):
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group('nccl', device_id=dev)
+    be = load_backend(impl)
+    if be is None:
+        if rank == 0:
+            return run_cpu_port(args, reason='baseline/_ref not installed on this box')
+        return None
+
+    sc, cams, targets = make_problem(dev)
+    params = [p.to(dev).contiguous().requires_grad_(True) for p in sc]
+    opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
+    bg = torch.zeros(3, device=dev)
+    st_dev = [settings_tuple(c, dev, bg) for c in cams]
+    gt_dev = [t.to(dev) for t in targets]
+    gt_pin = [t.pin_memory() for t in targets]
+    w2c_pin = [c.w2c.pin_memory() for c in cams]
+    pos_pin = [c.position.pin_memory() for c in cams]
+    empty = torch.empty(0)
+
+    def view_of(it):  # rank r trains view (it * world + r) of the 8-view ring
+        return (it * world + rank) % N_VIEWS
+
+    def step_resident(it):
+        k = view_of(it)
+        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st_dev[k]))
+        loss = (img - gt_dev[k]).abs().mean()
+        loss.backward()
+        if dist is not None:
+            for p in params:
+                dist.all_reduce(p.grad)
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def step_e2e(it):  # host buffers in, loss out: H2D of the view's target + camera, D2H of the loss
+        k = view_of(it)
+        gt = gt_pin[k].to(dev, non_blocking=True)
+        w2c = w2c_pin[k].to(dev, non_blocking=True)
+        pos = pos_pin[k].to(dev, non_blocking=True)
+        st = (w2c, pos) + st_dev[k][2:]
+        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st))
+        loss = (img - gt).abs().mean()
+        loss.backward()
+        if dist is not None:
+            for p in params:
+                dist.all_reduce(p.grad)
+        opt.step()
+        opt.zero_grad()
+        return float(loss.item())
+
+    def timed(fn, steps, warmup, sampler=None):
+        for it in range(warmup):
+            fn(it)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for it in range(steps):
+            fn(warmup + it)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item()), clocks
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, clocks = timed(step_resident, steps, warmup, sampler)
+    ms_e2e, _ = timed(step_e2e, steps, 3)
+    ms_step = ms_total / steps
+    value = world * 1000.0 / ms_step
+    e2e_value = world * 1000.0 / (ms_e2e / steps)
+
+    out = {
+        'metric': METRIC, 'value': round(value, 3), 'unit': 'iters/s', 'n_gpus': world, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': round(ms_step, 4), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: fastergs_garden shape, 1M Gaussians, 1920x1080, 16 SH bases, '
+                               'fwd + L1 + bwd + FusedAdam.step per view',
+                   'n_gaussians': N_GAUSSIANS, 'width': WIDTH, 'height': HEIGHT, 'views_per_step': world,
+                   'parallelism': f'view-dp{world}' if world > 1 else 'single',
+                   'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
+        'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
+                'h2d_bytes_per_step': 3 * WIDTH * HEIGHT * 4 + 64 + 12, 'd2h_bytes_per_step': 4},
+        'clocks': clocks,
+    }
+    if impl == 'reference':
+        out['impl'] = 'reference'
+        out['cpu_baseline'] = None
+        out['config']['reference'] = 'unmodified FasterGSCudaBackend (baseline/_ref) CUDA path on the same GPU'
+    else:
+        out.update(profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank))
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline()
+    if dist is not None:
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank):
+    """Per-kernel CUDA-event timing of a few extra (untimed) iterations -> roofline of the dominant
+    kernel, launch count, scene statistics."""
+    from fgs_b200 import _capi
+    reps = 5
+    _capi.profile_enable(True)
+    per = {}
+    launches = 0
+    for it in range(reps):
+        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st_dev[it % N_VIEWS]))
+        loss = (img - gt_dev[it % N_VIEWS]).abs().mean()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        recs = _capi.profile_read()
+        launches = len(recs)
+        for name, ms in recs:
+            per.setdefault(name, []).append(ms)
+    _capi.profile_enable(False)
+    kern = {k: sum(v) / reps for k, v in per.items()}  # ms per iteration per kernel group
+    # scene statistics of view 0 (V, I) from the forward state
+    from fgs_b200 import _C
+    st = st_dev[0]
+    with torch.no_grad():
+        r = _C.forward(*[p.detach() for p in params], *st)
+    I = int(r[5])
+    from fgs_b200 import _capi as cap
+    V = None
+    try:
+        V = int(torch.frombuffer(bytearray(r[1][:8].cpu().numpy().tobytes()), dtype=torch.int32)[0])
+    except Exception:
+        pass
+    P, T = WIDTH * HEIGHT, math.ceil(WIDTH / 16) * math.ceil(HEIGHT / 12)
+    N = N_GAUSSIANS
+    alg = algorithmic_bytes(N, V or 0, I, P, T)
+    dom = max(kern, key=kern.get)
+    peak, peak_src = peak_hbm_gbs()
+    dom_bytes = alg.get(dom, 0)
+    dom_ms = kern[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    iter_achieved = alg['iteration'] / (ms_step * 1e-3) / 1e9
+    kernel_ms_sum = sum(kern.values())
+    return {
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
+                     'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                     'algorithmic_bytes_per_launch': dom_bytes, 'ms_per_launch': round(dom_ms, 4),
+                     'share_of_step': round(dom_ms / ms_step, 3),
+                     'note': 'blend kernels are FP32-issue bound, not HBM bound; see DESIGN.md'},
+        'roofline_iteration': {'algorithmic_bytes': alg['iteration'], 'achieved': round(iter_achieved, 2),
+                               'peak': peak, 'unit': 'GB/s', 'frac': round(iter_achieved / peak, 4)},
+        'kernels_ms': {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
+        'kernels_ms_sum': round(kernel_ms_sum, 4),
+        'scene': {'N': N, 'V': V, 'I': I, 'P': P, 'T': T},
+    }
+
+
+def cpu_baseline():
+    """Oracle port timed on the host cores on a bounded sample of the SAME workload: full-size
+    preprocess (1M Gaussians) and full-size Adam, blend forward+backward on a 128x96 pixel window
+    of the 1080p view scaled by the pixel ratio."""
+    from oracle import torch_oracle as O
+    from fgs_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = syn.make_scene(N_GAUSSIANS, 0)
+    cam = syn.make_camera(0, WIDTH, HEIGHT)
+    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), SH_BASES, WIDTH, HEIGHT, cam.focal_x, cam.focal_y,
+                   cam.center_x, cam.center_y, cam.near_plane, cam.far_plane, False)
+    win = (896, 492, 1024, 588)  # 8 x 8 tiles around the image centre
+    leaves = [p.clone().requires_grad_(True) for p in sc]
+    t0 = time.perf_counter()
+    out = O.render(*leaves, s, window=win)
+    t1 = time.perf_counter()
+    gt = syn.make_target(WIDTH, HEIGHT)[:, win[1]:win[3], win[0]:win[2]]
+    (out.image - gt).abs().mean().backward()
+    t2 = time.perf_counter()
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in leaves]
+    with torch.no_grad():
+        for p, (m, v), lr in zip(leaves, state, LRS):
+            O.adam_step(p, p.grad if p.grad is not None else torch.zeros_like(p), m, v, 1, lr)
+    t3 = time.perf_counter()
+    # split forward time into the full-size part (preprocess) and the window part (blend)
+    tp0 = time.perf_counter()
+    with torch.no_grad():
+        O.preprocess(*sc, s)
+    t_pre = time.perf_counter() - tp0
+    ratio = (WIDTH * HEIGHT) / ((win[2] - win[0]) * (win[3] - win[1]))
+    t_blend_fwd = max(t1 - t0 - t_pre, 0.0)
+    # backward of the full-size preprocess is inside (t2 - t1); attribute the same fraction as forward
+    t_bwd = t2 - t1
+    frac_pre = t_pre / max(t1 - t0, 1e-9)
+    est = t_pre + t_blend_fwd * ratio + t_bwd * frac_pre + t_bwd * (1 - frac_pre) * ratio + (t3 - t2)
+    return {'value': round(1.0 / est, 6), 'unit': 'iters/s', 'cores': cores, 'kind': 'port',
+            'sample': f'oracle/torch_oracle.py fp32: full 1M-Gaussian preprocess+Adam, blend fwd+bwd on the '
+                      f'{win[2]-win[0]}x{win[3]-win[1]} px centre window scaled x{ratio:.0f} to 1920x1080; '
+                      f'measured {t3 - t0 + t_pre:.1f} s of CPU work, estimated {est:.0f} s per full iteration'}
+
+
+def run_cpu_port(args, reason):
+    cb = cpu_baseline()
+    return {'metric': METRIC, 'value': cb['value'], 'unit': 'iters/s', 'n_gpus': 0, 'steps': 1, 'warmup': 0,
+            'ms_per_step': round(1000.0 / cb['value'], 1), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'configs[1] (bounded sample, see cpu_baseline.sample)', 'note': reason},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': 'iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='mine', choices=['mine', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        if args.impl == 'reference':
+            print(json.dumps(run_cpu_port(args, 'no CUDA device')))
+            return
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    out = run_gpu(args, args.impl)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const Blend
     WarpScratch& ws = sm.ws[warp];
     const float3 bg = make_float3(__ldg(cam.bg), __ldg(cam.bg + 1), __ldg(cam.bg + 2));
     const uint32_t n_pixels = (uint32_t)cam.img_w * (uint32_t)cam.img_h;
-    int cur_tile = -1;
+    int cur_tile = -2;  // distinct from the end-of-stream marker (-1): a CTA may receive no tile at all
     // per-pixel state (phase A)
     float sr = 0.f, sg = 0.f, sb = 0.f;  // colour still to come behind the current Gaussian ("colour after")
     float gr = 0.f, gg = 0.f, gb = 0.f;  // dL/dpixel colour

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
 
     // ================================== consumer warps ==================================
     const float3 bg = make_float3(__ldg(cam.bg), __ldg(cam.bg + 1), __ldg(cam.bg + 2));
-    int cur_tile = -1;
+    int cur_tile = -2;  // distinct from the end-of-stream marker (-1): a CTA may receive no tile at all
     bool tile_finished = false;  // all 192 pixels done -> ignore the rest of this tile's batches
     // per-pixel state
     float cr = 0.f, cg = 0.f, cb = 0.f, T = 1.f;

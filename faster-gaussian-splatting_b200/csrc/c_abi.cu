@@ -33,6 +33,46 @@ int fail_arg(const char* msg) {
         if (e_ != cudaSuccess) return fail(e_, where); \
     } while (0)
 
+// ---- optional per-kernel timing (CUDA events on the launching stream), used by bench.py -----------
+struct Profiler {
+    static constexpr int kMaxRecords = 512;
+    bool enabled = false;
+    int n = 0;
+    const char* names[kMaxRecords];
+    cudaEvent_t start[kMaxRecords];
+    cudaEvent_t stop[kMaxRecords];
+    int created = 0;
+};
+Profiler& prof() {
+    static Profiler p;
+    return p;
+}
+struct ProfScope {
+    int slot = -1;
+    cudaStream_t stream;
+    ProfScope(const char* name, cudaStream_t s) : stream(s) {
+        Profiler& p = prof();
+        if (!p.enabled || p.n >= Profiler::kMaxRecords) return;
+        if (p.n >= p.created) {
+            if (cudaEventCreate(&p.start[p.created]) != cudaSuccess || cudaEventCreate(&p.stop[p.created]) != cudaSuccess) return;
+            ++p.created;
+        }
+        slot = p.n++;
+        p.names[slot] = name;
+        cudaEventRecord(p.start[slot], stream);
+    }
+    ~ProfScope() {
+        if (slot >= 0) cudaEventRecord(prof().stop[slot], stream);
+    }
+};
+
+#define FGS_KERNEL(expr, where)                        \
+    do {                                               \
+        ProfScope ps_(where, stream);                  \
+        cudaError_t e_ = (expr);                       \
+        if (e_ != cudaSuccess) return fail(e_, where); \
+    } while (0)
+
 int bits_for(int max_value) {  // number of bits needed to represent max_value (>= 1)
     int b = 1;
     while ((max_value >> b) != 0 && b < 32) ++b;
@@ -170,15 +210,15 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
     InstanceLayout<KeyT> il(blob, n_instances, end_bit);
     if (n_instances > 0) {
-        FGS_TRY(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, il.keys[0], il.vals[0],
+        FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, il.keys[0], il.vals[0],
                                               pl.counters + kCtrVisible, n_visible, cam.grid_w, stream),
                 "create_instances");
         bool in_alt = false;
-        FGS_TRY(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
+        FGS_KERNEL(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
                                        n_instances, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
                                        &in_alt, stream),
                 "tile sort");
-        FGS_TRY(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
+        FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
                                                tl.ranges, n_instances, stream),
                 "ranges_and_gather");
     }
@@ -194,7 +234,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     a.training = training;
     a.to_chw = to_chw;
     a.clamp_output = clamp_output;
-    FGS_TRY(launch_blend_forward(a, cam, stream), "blend_forward");
+    FGS_KERNEL(launch_blend_forward(a, cam, stream), "blend_forward");
     return 0;
 }
 
@@ -226,7 +266,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
     FGS_TRY(cudaMemsetAsync(tl.tile_max_n, 0, sizeof(uint32_t) * n_tiles, stream), "memset tile_max_n");
 
-    FGS_TRY(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.keys[0],
+    FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.keys[0],
                               pl.idx[0], pl.counters, n, cam, !training, stream),
             "preprocess");
     Readback& rb = readback();
@@ -235,11 +275,11 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
 
     // depth order: bits [0, 32) of the positive float depth (sign bit is always 0 after the near cull)
     bool in_alt = false;
-    FGS_TRY(radix_sort_pairs<uint32_t>(pl.keys[0], pl.keys[1], pl.idx[0], pl.idx[1], pl.counters + kCtrVisible, n, 32,
+    FGS_KERNEL(radix_sort_pairs<uint32_t>(pl.keys[0], pl.keys[1], pl.idx[0], pl.idx[1], pl.counters + kCtrVisible, n, 32,
                                        pl.hist, pl.lookback, pl.counters + kCtrTicket0, &in_alt, stream),
             "depth sort");
     const uint32_t* sorted_idx = pl.idx[in_alt ? 1 : 0];
-    FGS_TRY(launch_offsets_scan(sorted_idx, pl.n_touched, pl.offsets, pl.counters + kCtrVisible, n, pl.scan_lookback,
+    FGS_KERNEL(launch_offsets_scan(sorted_idx, pl.n_touched, pl.offsets, pl.counters + kCtrVisible, n, pl.scan_lookback,
                                 pl.counters + kCtrTicket0 + 4, stream),
             "offsets scan");
 
@@ -292,7 +332,7 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
         ba.grad2d = grad2d;
         ba.queue = pl.counters + kCtrTileQueueBwd;
         ba.n_tiles = n_tiles;
-        FGS_TRY(launch_blend_backward(ba, cam, stream), "blend_backward");
+        FGS_KERNEL(launch_blend_backward(ba, cam, stream), "blend_backward");
     }
     pa.means = means;
     pa.scales = scales;
@@ -303,7 +343,7 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
     pa.grad2d = grad2d;
     pa.densification_info = densification_info;
     pa.n = n;
-    FGS_TRY(launch_preprocess_backward(pa, cam, stream), "preprocess_backward");
+    FGS_KERNEL(launch_preprocess_backward(pa, cam, stream), "preprocess_backward");
     return 0;
 }
 
@@ -392,10 +432,35 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
                   int32_t step_count, double learning_rate, double beta1, double beta2, double epsilon, void* stream) {
     const double bc1_rcp = 1.0 / (1.0 - std::pow(beta1, (double)step_count));
     const double bc2_sqrt_rcp = 1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step_count));
-    FGS_TRY(launch_adam(param_grad, param, exp_avg, exp_avg_sq, n_elements, (float)(learning_rate * bc1_rcp),
-                        (float)beta1, (float)beta2, (float)epsilon, (float)bc2_sqrt_rcp,
-                        reinterpret_cast<cudaStream_t>(stream)),
-            "adam_step");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {
+        ProfScope ps_("adam_step", st);
+        FGS_TRY(launch_adam(param_grad, param, exp_avg, exp_avg_sq, n_elements, (float)(learning_rate * bc1_rcp),
+                            (float)beta1, (float)beta2, (float)epsilon, (float)bc2_sqrt_rcp, st),
+                "adam_step");
+    }
+    return 0;
+}
+
+void fgs_profile_enable(int32_t on) {
+    prof().enabled = on != 0;
+    prof().n = 0;
+}
+
+int fgs_profile_read(char* out, size_t out_bytes) {
+    Profiler& p = prof();
+    if (!out || out_bytes == 0) return fail_arg("fgs_profile_read: NULL buffer");
+    size_t off = 0;
+    out[0] = 0;
+    for (int i = 0; i < p.n; ++i) {
+        FGS_TRY(cudaEventSynchronize(p.stop[i]), "profile sync");
+        float ms = 0.f;
+        FGS_TRY(cudaEventElapsedTime(&ms, p.start[i], p.stop[i]), "profile elapsed");
+        const int w = std::snprintf(out + off, out_bytes - off, "%s=%.6f\n", p.names[i], ms);
+        if (w < 0 || (size_t)w >= out_bytes - off) break;
+        off += (size_t)w;
+    }
+    p.n = 0;
     return 0;
 }
 

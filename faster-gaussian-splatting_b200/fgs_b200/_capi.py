@@ -64,6 +64,8 @@ SIGNATURES = {
                                                                       C.c_int32, _P]),
     'fgs_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_double,
                                  C.c_double, _P]),
+    'fgs_profile_enable': (None, [C.c_int32]),
+    'fgs_profile_read': (C.c_int, [C.c_char_p, C.c_size_t]),
     'fgs_sort_pairs_u32': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,
                                       C.POINTER(C.c_int32), _P]),
     'fgs_sort_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -100,3 +102,18 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().fgs_last_error().decode(errors='replace')
         raise RuntimeError(f'fgs_b200 {what} failed (status {status}): {msg}')
+
+
+def profile_enable(on: bool) -> None:
+    load().fgs_profile_enable(1 if on else 0)
+
+
+def profile_read() -> list[tuple[str, float]]:
+    """[(kernel name, milliseconds)] in launch order since the last read."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().fgs_profile_read(buf, len(buf)), 'profile_read')
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, _, ms = line.partition('=')
+        out.append((name, float(ms)))
+    return out

@@ -115,6 +115,12 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
                   size_t n_elements, int32_t step_count, double learning_rate, double beta1, double beta2,
                   double epsilon, void* stream);
 
+/* Optional per-kernel timing for bench.py: while enabled every kernel (group) launched by the entry
+ * points above is bracketed by CUDA events on the caller's stream.  fgs_profile_read waits for them
+ * and writes one "name=milliseconds\n" line per launch, in launch order, then clears the list. */
+void fgs_profile_enable(int32_t on);
+int fgs_profile_read(char* out, size_t out_bytes);
+
 /* Building blocks exported for the unit tests (each is one stage of fgs_forward). */
 int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                        const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,

@@ -266,11 +266,21 @@ class RenderOut(NamedTuple):
     order: torch.Tensor           # depth-sorted indices of the visible Gaussians
 
 
-def render(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, pixel_chunk: int = 16384) -> RenderOut:
+def render(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, pixel_chunk: int = 16384,
+           window=None) -> RenderOut:
     """Forward of diff_rasterize: preprocess + depth order + dense front-to-back blend
-    (kernels_forward.cuh:362-498, B1-B8 in SURVEY.md §8.1).  Differentiable."""
+    (kernels_forward.cuh:362-498, B1-B8 in SURVEY.md §8.1).  Differentiable.
+
+    `window=(x0, y0, x1, y1)` renders only that pixel rectangle (exactly: Gaussians whose
+    opacity-aware bounding box misses the window have alpha < 1/255 on all of its pixels); the
+    returned image is (3, y1-y0, x1-x0).  Used to time a bounded sample of a large workload."""
     proj = preprocess(means, scales, rotations, opacities, sh0, sh_rest, s)
-    vis = proj.visible.nonzero(as_tuple=True)[0]
+    vis_mask = proj.visible
+    if window is not None:
+        wx0, wy0, wx1, wy1 = window
+        b = proj.screen_bounds
+        vis_mask = vis_mask & (b[:, 0] < wx1) & (b[:, 1] > wx0) & (b[:, 2] < wy1) & (b[:, 3] > wy0)
+    vis = vis_mask.nonzero(as_tuple=True)[0]
     order = vis[torch.argsort(proj.depth.detach()[vis], stable=True)]
     dt = means.dtype
     H, Wd = s.height, s.width
@@ -279,7 +289,12 @@ def render(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, pixel
     con = proj.conic[order]
     op = proj.opacity[order]
     col = torch.clamp(proj.color[order], min=0.0)
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=dt), torch.arange(Wd, dtype=dt), indexing='ij')
+    if window is None:
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=dt), torch.arange(Wd, dtype=dt), indexing='ij')
+    else:
+        ys, xs = torch.meshgrid(torch.arange(window[1], window[3], dtype=dt),
+                                torch.arange(window[0], window[2], dtype=dt), indexing='ij')
+        H, Wd = ys.shape
     px = xs.reshape(-1) + 0.5
     py = ys.reshape(-1) + 0.5
     P = px.numel()

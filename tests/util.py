@@ -44,4 +44,6 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def cos_sim(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().flatten(), b.double().flatten()
+    if float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0:
+        return 1.0
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
