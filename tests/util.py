@@ -20,19 +20,28 @@ def settings_for(cam, active_sh_bases=16, bg=(0.0, 0.0, 0.0), aa=False, device='
 
 def load_reference():
     """The UNMODIFIED reference extension built into baseline/_ref (git-ignored, travels to the GPU
-    box).  Returns the module `FasterGSCudaBackend.torch_bindings` or None."""
-    so = list((REF_DIR / 'FasterGSCudaBackend').glob('_C*.so')) if REF_DIR.exists() else []
-    if not so:
+    box).  Returns the module `FasterGSCudaBackend.torch_bindings` of the REFERENCE or None.
+
+    The pip-installed reference has no FasterGSCudaBackend/__init__.py (namespace package), so a
+    plain import would lose against this repo's drop-in alias package of the same name; the package
+    object is therefore created by hand with __path__ pinned to baseline/_ref."""
+    ref_pkg = REF_DIR / 'FasterGSCudaBackend'
+    if not (ref_pkg.exists() and list(ref_pkg.glob('_C*.so'))):
         return None
+    import types
+    import torch  # noqa: F401  (libc10.so etc. must be loaded before the extension)
     mod = sys.modules.get('FasterGSCudaBackend')
-    if mod is not None and str(REF_DIR) not in str(getattr(mod, '__path__', [''])[0]):
+    if mod is None or [str(p) for p in getattr(mod, '__path__', [])] != [str(ref_pkg)]:
         for k in [k for k in sys.modules if k == 'FasterGSCudaBackend' or k.startswith('FasterGSCudaBackend.')]:
             del sys.modules[k]
-    sys.path.insert(0, str(REF_DIR))
-    try:
-        return importlib.import_module('FasterGSCudaBackend.torch_bindings')
-    finally:
-        sys.path.remove(str(REF_DIR))
+        pkg = types.ModuleType('FasterGSCudaBackend')
+        pkg.__path__ = [str(ref_pkg)]
+        sys.modules['FasterGSCudaBackend'] = pkg
+    tb = importlib.import_module('FasterGSCudaBackend.torch_bindings')
+    assert str(ref_pkg) in tb.__file__, tb.__file__
+    c_mod = sys.modules['FasterGSCudaBackend._C']
+    assert str(ref_pkg) in c_mod.__file__ and c_mod.__file__.endswith('.so'), c_mod.__file__
+    return tb
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
