@@ -37,13 +37,13 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     const uint32_t cand = active ? tw * (ty1 - ty0) : 0u;
     const float msx = q0.x - 0.5f, msy = q0.y - 0.5f;
     const float A = q0.z, B = q0.w, C = q1.x;
-    const float tau = __logf(q1.y * kMinAlphaRcp);
+    const float tau = __log2f(q1.y * kMinAlphaRcp);  // base-2 domain, same expression as preprocess
     uint32_t wr = active ? __ldg(offsets + i) : 0u;
 
     if (cand <= (uint32_t)kSeqTiles) {
         for (uint32_t c = 0; c < cand; ++c) {
             const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
-            if (tile_contributes(msx, msy, A, B, C, tx, ty, tau)) {
+            if (tile_contributes2(msx, msy, A, B, C, tx, ty, tau)) {
                 inst_keys[wr] = (KeyT)(ty * (uint32_t)grid_w + tx);
                 inst_vals[wr] = prim;
                 ++wr;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
         for (uint32_t c0 = 0; c0 < bcand; c0 += 32) {
             const uint32_t c = c0 + lane;
             const uint32_t tx = bx0 + c % btw, ty = by0 + c / btw;
-            const bool ok = c < bcand && tile_contributes(bmx, bmy, bA, bB, bC, tx, ty, btau);
+            const bool ok = c < bcand && tile_contributes2(bmx, bmy, bA, bB, bC, tx, ty, btau);
             const uint32_t m = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 const uint32_t pos = bwr + __popc(m & ((1u << lane) - 1u));

@@ -18,6 +18,8 @@
 //    through shared memory replaces nine warp reductions (or nine shuffles per pixel step) per Gaussian;
 //  * the nine sums leave as two 16-byte vector reductions + one scalar (REDG.E.ADD.F32x4) into a
 //    packed 48-byte per-Gaussian gradient record.
+// The stored conic is pre-scaled to the base-2 exponent domain (fgs_device.cuh); the gradients are
+// converted back to the reference's conic convention in phase B.
 #include "fgs_device.cuh"
 #include "fgs_host.h"
 
@@ -25,8 +27,8 @@ namespace fgs {
 
 namespace {
 
-constexpr int kBatch = 64;
-constexpr int kStages = 4;
+constexpr int kBatch = 32;
+constexpr int kStages = 6;
 constexpr int kConsumerThreads = kBlendWarps * 32;
 constexpr int kBwdThreads = kConsumerThreads + 32;
 
@@ -34,11 +36,70 @@ struct StageHdr {
     int tile, offset, count, pad;
 };
 
+constexpr int kSlots = 16;  // surviving Gaussians queued per warp before phase B runs
+
 struct WarpScratch {
-    float u[32][33];
-    float w[32][33];
-    float4 g[32];
+    float2 uw[kSlots][33];  // [slot][pixel] -> (u, w)
+    float4 g[32];           // per pixel: dL/d(colour)
+    Rec par[kSlots];        // per slot: the Gaussian's record
 };
+
+// Phase B: lanes k and k+16 own slot k and each reduce it over 16 of the warp's 32 pixels straight out
+// of shared memory; one shuffle step joins the halves, lane k emits the nine gradient components.
+__device__ __noinline__ void flush_slots(WarpScratch& ws, const int nslots, const int lane, const float fx0,
+                                         const float fy0, const bool proper_aa, Grad2D* __restrict__ grad2d) {
+    __syncwarp();
+    const int slot = lane & (kSlots - 1);
+    const int p0 = lane & kSlots;  // 0 or 16: first pixel of this half
+    const float4 q0 = ws.par[slot].q0;
+    const float4 q1 = ws.par[slot].q1;
+    const float mx = q0.x, my = q0.y, op = q1.y;
+    float dop = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
+    float mxx = 0.f, mxy = 0.f, myy = 0.f, mx1 = 0.f, my1 = 0.f;
+    if (slot < nslots) {
+#pragma unroll 8
+        for (int i = 0; i < 16; ++i) {
+            const int p = p0 + i;
+            const float2 uw = ws.uw[slot][p];
+            const float4 g4 = ws.g[p];
+            const float dx = mx - (fx0 + (float)(p & 7));
+            const float dy = my - (fy0 + (float)(p >> 3));
+            const float h = -op * uw.x;  // -alpha * dL/dalpha
+            dop += uw.x;
+            dcr = fmaf(uw.y, g4.x, dcr);
+            dcg = fmaf(uw.y, g4.y, dcg);
+            dcb = fmaf(uw.y, g4.z, dcb);
+            const float hx = h * dx, hy = h * dy;
+            mx1 += hx;
+            my1 += hy;
+            mxx = fmaf(hx, dx, mxx);
+            mxy = fmaf(hx, dy, mxy);
+            myy = fmaf(hy, dy, myy);
+        }
+    }
+    dop += __shfl_xor_sync(0xffffffffu, dop, 16);
+    dcr += __shfl_xor_sync(0xffffffffu, dcr, 16);
+    dcg += __shfl_xor_sync(0xffffffffu, dcg, 16);
+    dcb += __shfl_xor_sync(0xffffffffu, dcb, 16);
+    mx1 += __shfl_xor_sync(0xffffffffu, mx1, 16);
+    my1 += __shfl_xor_sync(0xffffffffu, my1, 16);
+    mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
+    mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
+    myy += __shfl_xor_sync(0xffffffffu, myy, 16);
+    if (lane < nslots) {
+        const float4 q2 = ws.par[slot].q2;
+        // back to the reference's conic: A = A2 / (-0.5 log2 e), B = B2 / (-log2 e), C = C2 / (-0.5 log2 e)
+        const float cA = q0.z * (-2.0f / kLog2e), cB = q0.w * (-1.0f / kLog2e), cC = q1.x * (-2.0f / kLog2e);
+        const float dmx = cA * mx1 + cB * my1;
+        const float dmy = cB * mx1 + cC * my1;
+        const float dopacity = proper_aa ? dop : op * (1.0f - op) * dop;
+        Grad2D* dst = grad2d + __float_as_uint(q2.w);
+        atomicAdd(&dst->g0, make_float4(dmx, dmy, 0.5f * mxx, 0.5f * mxy));
+        atomicAdd(&dst->g1, make_float4(0.5f * myy, dopacity, dcr * color_mask(q1.z), dcg * color_mask(q1.w)));
+        atomicAdd(&dst->g2.x, dcb * color_mask(q2.x));
+    }
+    __syncwarp();
+}
 
 struct __align__(128) BwdSmem {
     Rec recs[kStages][kBatch];
@@ -48,7 +109,7 @@ struct __align__(128) BwdSmem {
     WarpScratch ws[kBlendWarps];
 };
 
-__global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
+__global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -76,7 +137,7 @@ __global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const Blend
             if (n <= 0) continue;
             const int nb = (n + kBatch - 1) / kBatch;
             for (int b = 0; b < nb; ++b) {
-                mbar_wait(&sm.empty[stage], phase ^ 1u);
+                mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
                 const int cnt = min(kBatch, n - b * kBatch);
                 sm.hdr[stage].tile = tile;
                 sm.hdr[stage].offset = b * kBatch;
@@ -90,7 +151,7 @@ __global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const Blend
                 }
             }
         }
-        mbar_wait(&sm.empty[stage], phase ^ 1u);
+        mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
         sm.hdr[stage].tile = -1;
         sm.hdr[stage].offset = 0;
         sm.hdr[stage].count = 0;
@@ -111,53 +172,17 @@ __global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const Blend
     uint32_t n_proc = 0, warp_max = 0;
     float px = 0.f, py = 0.f;
     uint32_t sub_x0 = 0, sub_y0 = 0;
-    // per-slot state (phase B): lane k owns slot k
     int nslots = 0;
-    float s_mx = 0.f, s_my = 0.f, s_A = 0.f, s_B = 0.f, s_C = 0.f, s_o = 0.f;
-    float s_mr = 0.f, s_mg = 0.f, s_mb = 0.f;  // colour >= 0 masks
-    uint32_t s_prim = 0;
 
     auto flush = [&]() {
-        __syncwarp();
-        if (lane < nslots) {
-            float dop = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
-            float mxx = 0.f, mxy = 0.f, myy = 0.f, mx1 = 0.f, my1 = 0.f;
-            const float fx0 = (float)sub_x0 + 0.5f, fy0 = (float)sub_y0 + 0.5f;
-#pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const float u = ws.u[lane][p];
-                const float w = ws.w[lane][p];
-                const float4 g4 = ws.g[p];
-                const float dx = s_mx - (fx0 + (float)(p & 7));
-                const float dy = s_my - (fy0 + (float)(p >> 3));
-                const float h = -s_o * u;  // -alpha * dL/dalpha
-                dop += u;
-                dcr = fmaf(w, g4.x, dcr);
-                dcg = fmaf(w, g4.y, dcg);
-                dcb = fmaf(w, g4.z, dcb);
-                const float hx = h * dx, hy = h * dy;
-                mx1 += hx;
-                my1 += hy;
-                mxx = fmaf(hx, dx, mxx);
-                mxy = fmaf(hx, dy, mxy);
-                myy = fmaf(hy, dy, myy);
-            }
-            const float dmx = s_A * mx1 + s_B * my1;
-            const float dmy = s_B * mx1 + s_C * my1;
-            const float dopacity = cam.proper_aa ? dop : s_o * (1.0f - s_o) * dop;
-            Grad2D* dst = a.grad2d + s_prim;
-            atomicAdd(&dst->g0, make_float4(dmx, dmy, 0.5f * mxx, 0.5f * mxy));
-            atomicAdd(&dst->g1, make_float4(0.5f * myy, dopacity, dcr * s_mr, dcg * s_mg));
-            atomicAdd(&dst->g2.x, dcb * s_mb);
-        }
-        __syncwarp();
+        flush_slots(ws, nslots, lane, (float)sub_x0 + 0.5f, (float)sub_y0 + 0.5f, cam.proper_aa != 0, a.grad2d);
         nslots = 0;
     };
 
     int stage = 0;
     uint32_t phase = 0;
     for (;;) {
-        mbar_wait(&sm.full[stage], phase);
+        mbar_wait_sleep(&sm.full[stage], phase);
         const int tile = sm.hdr[stage].tile;
         const int offset = sm.hdr[stage].offset;
         const int count = sm.hdr[stage].count;
@@ -191,74 +216,69 @@ __global__ void __launch_bounds__(kBwdThreads) blend_backward_kernel(const Blend
                 galpha = Tf * -(gr * bg.x + gg * bg.y + gb * bg.z);
             }
             warp_max = __reduce_max_sync(0xffffffffu, n_proc);
-            __syncwarp();
             ws.g[lane] = make_float4(gr, gg, gb, 0.f);
             __syncwarp();
         }
         if ((uint32_t)offset < warp_max) {
             const Rec* recs = &sm.recs[stage][0];
-            for (int g0 = 0; g0 < count && (uint32_t)(offset + g0) < warp_max; g0 += 32) {
-                const int j = g0 + lane;
-                bool hit = false;
-                if (j < count) {
-                    const float4 q2 = recs[j].q2;
-                    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
-                    hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
-                          sub_y0 < (by >> 16);
-                    if (hit) {
-                        const float4 q0 = recs[j].q0;
-                        const float4 q1 = recs[j].q1;
-                        hit = rect_contributes(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, (float)sub_x0, (float)sub_y0,
-                                               (float)(kSubW - 1), (float)(kSubH - 1), __logf(q1.y * kMinAlphaRcp));
-                    }
+            const float fx0 = (float)sub_x0, fy0 = (float)sub_y0;
+            // one 32-record batch = one cull group
+            bool hit = false;
+            if (lane < count && (uint32_t)(offset + lane) < warp_max) {
+                const float4 q2 = recs[lane].q2;
+                const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+                hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
+                      sub_y0 < (by >> 16);
+                if (hit) {
+                    const float4 q0 = recs[lane].q0;
+                    const float4 q1 = recs[lane].q1;
+                    hit = rect_contributes2(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, fx0, fy0, (float)(kSubW - 1),
+                                            (float)(kSubH - 1), __log2f(q1.y * kMinAlphaRcp));
                 }
-                uint32_t pending = __ballot_sync(0xffffffffu, hit);
-                while (pending) {
-                    const int jj = g0 + __ffs((int)pending) - 1;
-                    pending &= pending - 1;
-                    const float4 q0 = recs[jj].q0;
-                    const float4 q1 = recs[jj].q1;
-                    const float4 q2 = recs[jj].q2;
-                    float u = 0.f, w = 0.f;
-                    bool contrib = false;
-                    if ((uint32_t)(offset + jj) < n_proc) {
-                        const float dx = q0.x - px, dy = q0.y - py;
-                        const float power = blend_power(q0.z, q0.w, q1.x, dx, dy);
-                        const float gauss = __expf(fminf(power, 0.0f));
-                        const float alpha = __fmul_rn(q1.y, gauss);
-                        if (alpha >= kMinAlpha) {
-                            contrib = true;
-                            w = __fmul_rn(T, alpha);
-                            const float c_r = fmaxf(q1.z, 0.0f), c_g = fmaxf(q1.w, 0.0f), c_b = fmaxf(q2.x, 0.0f);
-                            sr = fmaf(-w, c_r, sr);
-                            sg = fmaf(-w, c_g, sg);
-                            sb = fmaf(-w, c_b, sb);
-                            const float oma = __fsub_rn(1.0f, alpha);
-                            const float rcp = 1.0f / fmaxf(oma, kOneMinusAlphaEps);
-                            const float dlda = (T * c_r - sr * rcp) * gr + (T * c_g - sg * rcp) * gg +
-                                               (T * c_b - sb * rcp) * gb + galpha * rcp;
-                            u = gauss * dlda;
-                            T = __fmul_rn(T, oma);
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, contrib)) {
-                        ws.u[nslots][lane] = u;
-                        ws.w[nslots][lane] = w;
-                        if (lane == nslots) {
-                            s_mx = q0.x;
-                            s_my = q0.y;
-                            s_A = q0.z;
-                            s_B = q0.w;
-                            s_C = q1.x;
-                            s_o = q1.y;
-                            s_mr = q1.z >= 0.0f ? 1.0f : 0.0f;
-                            s_mg = q1.w >= 0.0f ? 1.0f : 0.0f;
-                            s_mb = q2.x >= 0.0f ? 1.0f : 0.0f;
-                            s_prim = __float_as_uint(q2.w);
-                        }
-                        if (++nslots == 32) flush();
-                    }
-                }
+            }
+            uint32_t pending = __ballot_sync(0xffffffffu, hit);
+            // two hits per iteration: the alpha evaluations are independent and overlap, only the
+            // transmittance / colour-after recurrences are sequential
+            while (pending) {
+                const int ja = __ffs((int)pending) - 1;
+                pending &= pending - 1;
+                const bool has_b = pending != 0u;
+                const int jb = has_b ? __ffs((int)pending) - 1 : ja;
+                pending &= pending - 1;
+                const float4 a0 = recs[ja].q0, a1 = recs[ja].q1;
+                const float4 b0 = recs[jb].q0, b1 = recs[jb].q1;
+                const float gauss_a = exp2f(fminf(blend_power2(a0.z, a0.w, a1.x, a0.x - px, a0.y - py), 0.0f));
+                const float gauss_b = exp2f(fminf(blend_power2(b0.z, b0.w, b1.x, b0.x - px, b0.y - py), 0.0f));
+                const float alpha_a = __fmul_rn(a1.y, gauss_a);
+                const float alpha_b = __fmul_rn(b1.y, gauss_b);
+                const bool contrib_a = alpha_a >= kMinAlpha && (uint32_t)(offset + ja) < n_proc;
+                const bool contrib_b = has_b && alpha_b >= kMinAlpha && (uint32_t)(offset + jb) < n_proc;
+#define FGS_PHASE_A(JJ, Q1, GAUSS, ALPHA, CONTRIB)                                                                  \
+    {                                                                                                                \
+        float u = 0.f, w = 0.f;                                                                                      \
+        if (CONTRIB) {                                                                                               \
+            const float c_b = recs[JJ].q2.x;                                                                         \
+            w = __fmul_rn(T, ALPHA);                                                                                 \
+            sr = fmaf(-w, Q1.z, sr);                                                                                 \
+            sg = fmaf(-w, Q1.w, sg);                                                                                 \
+            sb = fmaf(-w, c_b, sb);                                                                                  \
+            const float oma = __fsub_rn(1.0f, ALPHA);                                                                \
+            const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));                                       \
+            const float dlda = (T * Q1.z - sr * rcp) * gr + (T * Q1.w - sg * rcp) * gg + (T * c_b - sb * rcp) * gb + \
+                               galpha * rcp;                                                                         \
+            u = GAUSS * dlda;                                                                                        \
+            T = __fmul_rn(T, oma);                                                                                   \
+        }                                                                                                            \
+        if (__any_sync(0xffffffffu, CONTRIB)) {                                                                      \
+            ws.uw[nslots][lane] = make_float2(u, w);                                                                 \
+            if (lane < 3)                                                                                            \
+                reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[JJ])[lane]; \
+            if (++nslots == kSlots) flush();                                                                         \
+        }                                                                                                            \
+    }
+                FGS_PHASE_A(ja, a1, gauss_a, alpha_a, contrib_a)
+                if (has_b) FGS_PHASE_A(jb, b1, gauss_b, alpha_b, contrib_b)
+#undef FGS_PHASE_A
             }
         }
         __syncwarp();
@@ -278,6 +298,8 @@ cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStr
     const size_t smem = sizeof(BwdSmem);
     if (s_grid == 0) {
         cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);

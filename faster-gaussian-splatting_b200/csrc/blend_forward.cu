@@ -7,13 +7,18 @@
 //
 // New design:
 //  * persistent CTAs pull tiles from an atomic queue; a dedicated producer warp streams each tile's
-//    tile-contiguous 48-byte records into a 4-stage shared-memory ring with 1-D bulk async copies
+//    tile-contiguous 48-byte records into a shared-memory ring with 1-D bulk async copies
 //    (cp.async.bulk + mbarrier complete_tx, i.e. TMA; SASS UBLKCP), six consumer warps blend;
-//  * the per-stage header (tile id, offset, count) travels with the data, so the producer runs ahead
-//    across tile boundaries and the consumers never touch global memory for scheduling;
+//  * the per-stage header (tile id, sequence number, offset, count) travels with the data, so the
+//    producer runs ahead across tile boundaries, the consumers never touch global memory for
+//    scheduling and never meet at a CTA-wide barrier: each warp free-runs through the ring;
+//  * early termination is a 6-bit "sub-tile finished" mask per tile in shared memory (one atomicOr per
+//    warp and tile) instead of a __syncthreads_and every 192 Gaussians;
 //  * sub-tile culling is two-level: the reference's strict bounding-box overlap, then the exact
 //    "maximum of the Gaussian inside the rectangle" test on the 8x4 sub-tile (the same predicate the
 //    reference uses for 16x12 tiles); both only remove pairs whose alpha is below 1/255;
+//  * the exponent is evaluated in the base-2 domain on a pre-scaled conic (no log2(e) multiply, no
+//    -0.5 factor in the loop), colours arrive pre-clamped;
 //  * no bucket checkpoints are written: the backward pass recomputes transmittance front-to-back.
 #include "fgs_device.cuh"
 #include "fgs_host.h"
@@ -23,15 +28,17 @@ namespace fgs {
 namespace {
 
 constexpr int kBatch = 64;                                // records per bulk copy (3 KB)
-constexpr int kStages = 4;
+constexpr int kStages = 8;
+constexpr int kSeqRing = 16;                              // > kStages: tiles in flight per CTA
 constexpr int kConsumerThreads = kBlendWarps * 32;        // 192
 constexpr int kFwdThreads = kConsumerThreads + 32;        // + producer warp
+constexpr uint32_t kAllWarps = (1u << kBlendWarps) - 1u;
 
 struct StageHdr {
     int tile;      // -1: end of stream
+    int seq;       // per-CTA tile sequence number
     int offset;    // index of the first record of this batch inside the tile's list
     int count;     // records in this batch
-    int pad;
 };
 
 struct __align__(128) FwdSmem {
@@ -39,7 +46,7 @@ struct __align__(128) FwdSmem {
     StageHdr hdr[kStages];
     uint64_t full[kStages];
     uint64_t empty[kStages];
-    volatile int skip_tile;
+    uint32_t done_mask[kSeqRing];  // bit w set: warp w has finished all its pixels of that tile
 };
 
 template <bool kTraining>
@@ -52,9 +59,9 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], kBlendWarps);
         }
-        sm.skip_tile = -1;
         mbar_fence_init();
     }
+    if (tid < kSeqRing) sm.done_mask[tid] = 0;
     __syncthreads();
 
     if (warp == kBlendWarps) {
@@ -62,17 +69,23 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
         if (lane != 0) return;
         int stage = 0;
         uint32_t phase = 0;
+        int seq = 0;
         for (;;) {
             const int tile = (int)atomicAdd(a.queue, 1u);
             if (tile >= a.n_tiles) break;
             const uint2 range = a.tile_ranges[tile];
             const int n = (int)(range.y - range.x);
             const int nb = n > 0 ? (n + kBatch - 1) / kBatch : 1;
+            volatile uint32_t* dm = &sm.done_mask[seq & (kSeqRing - 1)];
             for (int b = 0; b < nb; ++b) {
-                if (b > 0 && sm.skip_tile == tile) break;
-                mbar_wait(&sm.empty[stage], phase ^ 1u);
+                mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
+                // the slot of sequence number seq was last used kSeqRing tiles ago; every consumer has
+                // released that tile's stages long before (the ring is only kStages deep)
+                if (b == 0) *dm = 0;
+                else if (*dm == kAllWarps) break;
                 const int cnt = min(kBatch, n - b * kBatch);
                 sm.hdr[stage].tile = tile;
+                sm.hdr[stage].seq = seq;
                 sm.hdr[stage].offset = b * kBatch;
                 sm.hdr[stage].count = cnt > 0 ? cnt : 0;
                 if (cnt > 0) {
@@ -87,9 +100,11 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
                     phase ^= 1u;
                 }
             }
+            ++seq;
         }
-        mbar_wait(&sm.empty[stage], phase ^ 1u);
+        mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
         sm.hdr[stage].tile = -1;
+        sm.hdr[stage].seq = seq;
         sm.hdr[stage].offset = 0;
         sm.hdr[stage].count = 0;
         mbar_arrive(&sm.full[stage]);
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
     // ================================== consumer warps ==================================
     const float3 bg = make_float3(__ldg(cam.bg), __ldg(cam.bg + 1), __ldg(cam.bg + 2));
     int cur_tile = -2;  // distinct from the end-of-stream marker (-1): a CTA may receive no tile at all
-    bool tile_finished = false;  // all 192 pixels done -> ignore the rest of this tile's batches
+    bool warp_done = false;  // every pixel of this warp's sub-tile is finished
     // per-pixel state
     float cr = 0.f, cg = 0.f, cb = 0.f, T = 1.f;
     uint32_t n_last = 0;
@@ -110,9 +125,9 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
 
     auto finalize = [&]() {
         if (inside) {
-            cr += T * bg.x;
-            cg += T * bg.y;
-            cb += T * bg.z;
+            cr = fmaf(T, bg.x, cr);
+            cg = fmaf(T, bg.y, cg);
+            cb = fmaf(T, bg.z, cb);
             const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
             if (kTraining) {
                 const uint32_t np = (uint32_t)cam.img_w * (uint32_t)cam.img_h;
@@ -148,7 +163,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
     int stage = 0;
     uint32_t phase = 0;
     for (;;) {
-        mbar_wait(&sm.full[stage], phase);
+        mbar_wait_sleep(&sm.full[stage], phase);
         const int tile = sm.hdr[stage].tile;
         const int offset = sm.hdr[stage].offset;
         const int count = sm.hdr[stage].count;
@@ -156,7 +171,6 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
             if (cur_tile >= 0) finalize();
             if (tile < 0) break;
             cur_tile = tile;
-            tile_finished = false;
             const uint32_t tile_x = (uint32_t)tile % (uint32_t)cam.grid_w, tile_y = (uint32_t)tile / (uint32_t)cam.grid_w;
             sub_x0 = tile_x * kTileW + (uint32_t)(warp & 1) * kSubW;
             sub_y0 = tile_y * kTileH + (uint32_t)(warp >> 1) * kSubH;
@@ -169,57 +183,53 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
             T = 1.f;
             n_last = 0;
             done = !inside;
+            warp_done = __all_sync(0xffffffffu, done);
+            if (warp_done && lane == 0) atomicOr(&sm.done_mask[sm.hdr[stage].seq & (kSeqRing - 1)], 1u << warp);
         }
-        if (!tile_finished && count > 0) {
+        if (!warp_done && count > 0) {
             const Rec* recs = &sm.recs[stage][0];
-            if (!__all_sync(0xffffffffu, done)) {
-                for (int g0 = 0; g0 < count; g0 += 32) {
-                    const int j = g0 + lane;
-                    bool hit = false;
-                    if (j < count) {
-                        const float4 q2 = recs[j].q2;
-                        const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
-                        // strict bounding-box / sub-tile overlap (kernels_forward.cuh:445-451)
-                        hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
-                              sub_y0 < (by >> 16);
-                        if (hit) {
-                            const float4 q0 = recs[j].q0;
-                            const float4 q1 = recs[j].q1;
-                            hit = rect_contributes(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, (float)sub_x0,
-                                                   (float)sub_y0, (float)(kSubW - 1), (float)(kSubH - 1),
-                                                   __logf(q1.y * kMinAlphaRcp));
-                        }
+            const float fx0 = (float)sub_x0, fy0 = (float)sub_y0;
+            for (int g0 = 0; g0 < count; g0 += 32) {
+                const int j = g0 + lane;
+                bool hit = false;
+                if (j < count) {
+                    const float4 q2 = recs[j].q2;
+                    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+                    // strict bounding-box / sub-tile overlap (kernels_forward.cuh:445-451)
+                    hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
+                          sub_y0 < (by >> 16);
+                    if (hit) {
+                        const float4 q0 = recs[j].q0;
+                        const float4 q1 = recs[j].q1;
+                        hit = rect_contributes2(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, fx0, fy0, (float)(kSubW - 1),
+                                                (float)(kSubH - 1), __log2f(q1.y * kMinAlphaRcp));
                     }
-                    uint32_t pending = __ballot_sync(0xffffffffu, hit);
-                    while (pending) {
-                        const int jj = g0 + __ffs((int)pending) - 1;
-                        pending &= pending - 1;
-                        const float4 q0 = recs[jj].q0;
-                        const float4 q1 = recs[jj].q1;
-                        const float colb = recs[jj].q2.x;
-                        if (!done) {
-                            const float dx = q0.x - px, dy = q0.y - py;
-                            const float power = blend_power(q0.z, q0.w, q1.x, dx, dy);
-                            const float gauss = __expf(fminf(power, 0.0f));
-                            const float alpha = __fmul_rn(q1.y, gauss);
-                            if (alpha >= kMinAlpha) {
-                                const float w = __fmul_rn(T, alpha);
-                                cr = fmaf(w, fmaxf(q1.z, 0.0f), cr);
-                                cg = fmaf(w, fmaxf(q1.w, 0.0f), cg);
-                                cb = fmaf(w, fmaxf(colb, 0.0f), cb);
-                                T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                                n_last = (uint32_t)(offset + jj + 1);
-                                if (T < kTransmittanceThreshold) done = true;
-                            }
-                        }
-                    }
-                    if (__all_sync(0xffffffffu, done)) break;
                 }
-            }
-            // tile-wide early termination vote (kernels_forward.cuh:420)
-            if (named_bar_and(1, kConsumerThreads, done)) {
-                tile_finished = true;
-                if (tid == 0) sm.skip_tile = cur_tile;
+                uint32_t pending = __ballot_sync(0xffffffffu, hit);
+                while (pending) {
+                    const int jj = g0 + __ffs((int)pending) - 1;
+                    pending &= pending - 1;
+                    const float4 q0 = recs[jj].q0;
+                    const float4 q1 = recs[jj].q1;
+                    const float dx = q0.x - px, dy = q0.y - py;
+                    const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, dx, dy), 0.0f));
+                    const float alpha = __fmul_rn(q1.y, gauss);
+                    if (alpha >= kMinAlpha && !done) {
+                        const float colb = recs[jj].q2.x;
+                        const float w = __fmul_rn(T, alpha);
+                        cr = fmaf(w, q1.z, cr);
+                        cg = fmaf(w, q1.w, cg);
+                        cb = fmaf(w, colb, cb);
+                        T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        n_last = (uint32_t)(offset + jj + 1);
+                        done = T < kTransmittanceThreshold;
+                    }
+                }
+                if (__all_sync(0xffffffffu, done)) {
+                    warp_done = true;
+                    if (lane == 0) atomicOr(&sm.done_mask[sm.hdr[stage].seq & (kSeqRing - 1)], 1u << warp);
+                    break;
+                }
             }
         }
         __syncwarp();

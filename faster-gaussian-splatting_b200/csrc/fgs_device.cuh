@@ -24,9 +24,15 @@ constexpr int kTilePixels = kTileW * kTileH;   // 192
 constexpr int kBlendWarps = kTilePixels / 32;  // 6
 
 // ---- per-Gaussian 2D record (48 B, three float4) ---------------------------------------------------
-// q0 = (mean2d.x, mean2d.y, conic.x, conic.y)
-// q1 = (conic.z, opacity, color.r, color.g)          colour is stored UNCLAMPED (kernels_forward.cuh:197)
+// q0 = (mean2d.x, mean2d.y, A2, B2)
+// q1 = (C2, opacity, color.r, color.g)
 // q2 = (color.b, bits(xmin | xmax << 16), bits(ymin | ymax << 16), bits(primitive index))
+// (A2, B2, C2) is the conic pre-scaled into the base-2 exponent domain,
+//      A2 = -0.5 log2(e) conic.x,  B2 = -log2(e) conic.y,  C2 = -0.5 log2(e) conic.z,
+// so that the blend evaluates  log2 G = A2 dx^2 + B2 dx dy + C2 dy^2  and feeds MUFU.EX2 directly.
+// Colours are stored clamped to >= 0 (what the blend consumes, kernels_forward.cuh:430); a colour
+// that was negative before the clamp is stored as -0.0f so the backward still knows the clamp mask
+// (kernels_backward.cuh:314-318) from the sign bit.
 struct __align__(16) Rec {
     float4 q0, q1, q2;
 };
@@ -93,6 +99,43 @@ __device__ __forceinline__ bool tile_contributes(float mx, float my, float A, fl
                             (float)(kTileW - 1), (float)(kTileH - 1), tau);
 }
 
+// Same predicate on the pre-scaled conic (A2, B2, C2) and tau2 = log2(255 * opacity):
+//   0.5 (A ex^2 + C ey^2) + B ex ey <= tau   <=>   -(A2 ex^2 + B2 ex ey + C2 ey^2) <= tau2,
+// and the closest-point parameters only involve ratios of conic entries.
+__device__ __forceinline__ bool rect_contributes2(float mx, float my, float A2, float B2, float C2, float rx0,
+                                                  float ry0, float ext_x, float ext_y, float tau2) {
+    const float rx1 = rx0 + ext_x, ry1 = ry0 + ext_y;
+    const float x_min_diff = rx0 - mx;
+    const bool x_left = x_min_diff >= 0.0f;
+    const bool x_out = x_left || mx > rx1;
+    const float y_min_diff = ry0 - my;
+    const bool y_above = y_min_diff >= 0.0f;
+    const bool y_out = y_above || my > ry1;
+    if (!x_out && !y_out) return true;
+    const float cx = x_left ? rx0 : rx1;
+    const float cy = y_above ? ry0 : ry1;
+    const float diff_x = mx - cx, diff_y = my - cy;
+    const float dx = copysignf(ext_x, x_min_diff);
+    const float dy = copysignf(ext_y, y_min_diff);
+    const float tx = y_out ? __saturatef((2.0f * A2 * diff_x + B2 * diff_y) / (2.0f * A2 * dx)) : 0.0f;
+    const float ty = x_out ? __saturatef((B2 * diff_x + 2.0f * C2 * diff_y) / (2.0f * C2 * dy)) : 0.0f;
+    const float ex = mx - (cx + tx * dx), ey = my - (cy + ty * dy);
+    const float neg_power2 = A2 * ex * ex + C2 * ey * ey + B2 * ex * ey;
+    return -neg_power2 <= tau2;
+}
+
+__device__ __forceinline__ bool tile_contributes2(float mx, float my, float A2, float B2, float C2, uint32_t tile_x,
+                                                  uint32_t tile_y, float tau2) {
+    return rect_contributes2(mx, my, A2, B2, C2, (float)(tile_x * kTileW), (float)(tile_y * kTileH),
+                             (float)(kTileW - 1), (float)(kTileH - 1), tau2);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// clamp to >= 0, remembering a negative input in the sign bit (-0.0f)
+__device__ __forceinline__ float pack_color(float c) { return c >= 0.0f ? c : -0.0f; }
+__device__ __forceinline__ float color_mask(float packed) { return (__float_as_uint(packed) >> 31) ? 0.0f : 1.0f; }
+
 // tile rectangle of a screen-space bounding box: kernel_utils.cuh:61-68
 __device__ __forceinline__ void tile_bounds_of(uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax,
                                                uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
@@ -154,12 +197,24 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 
-// q = -1/2 (A dx^2 + C dy^2) - B dx dy (kernels_forward.cuh:461).  The operation order is pinned
-// with explicit round-to-nearest intrinsics so that the forward and the backward kernel evaluate
-// bit-identical alphas (the backward replays the forward's skip/stop decisions).
-__device__ __forceinline__ float blend_power(float A, float B, float C, float dx, float dy) {
-    const float s = __fmaf_rn(C, __fmul_rn(dy, dy), __fmul_rn(A, __fmul_rn(dx, dx)));
-    return __fmaf_rn(-0.5f, s, -__fmul_rn(B, __fmul_rn(dx, dy)));
+// log2 G = A2 dx^2 + B2 dx dy + C2 dy^2 (kernels_forward.cuh:461 in the base-2 domain).  The operation
+// order is pinned with explicit round-to-nearest intrinsics so that the forward and the backward
+// kernel evaluate bit-identical alphas (the backward replays the forward's skip/stop decisions).
+__device__ __forceinline__ float blend_power2(float A2, float B2, float C2, float dx, float dy) {
+    const float u = __fmaf_rn(B2, dy, __fmul_rn(A2, dx));
+    return __fmaf_rn(__fmul_rn(C2, dy), dy, __fmul_rn(u, dx));
+}
+
+// mbarrier wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!ok);
 }
 
 }  // namespace fgs

@@ -191,9 +191,12 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float m2y = y * cam.focal_y + cam.center_y;
 
     // P6/P7: opacity-aware extent, bounds clamped to the padded tile grid
-    const float tau = __logf(opacity * kMinAlphaRcp);
+    const float tau2 = __log2f(opacity * kMinAlphaRcp);  // tau * log2(e)
+    const float tau = tau2 * 0.6931471805599453f;
     const float ext_x = fmaxf(sqrtf(cov_a * 2.0f * tau) - 0.5f, 0.0f);
     const float ext_y = fmaxf(sqrtf(cov_c * 2.0f * tau) - 0.5f, 0.0f);
+    // conic in the base-2 exponent domain (see fgs_device.cuh): everything downstream uses these
+    const float A2 = -0.5f * kLog2e * conic_a, B2 = -kLog2e * conic_b, C2 = -0.5f * kLog2e * conic_c;
     const int pw = cam.grid_w * kTileW, ph = cam.grid_h * kTileH;
     const uint32_t xmin = (uint32_t)min(pw, max(0, __float2int_rd(m2x - ext_x)));
     const uint32_t xmax = (uint32_t)min(pw, max(0, __float2int_ru(m2x + ext_x)));
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     if (active && cand <= (uint32_t)kSeqTiles) {
         for (uint32_t c = 0; c < cand; ++c) {
             const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
-            n_touched += tile_contributes(msx, msy, conic_a, conic_b, conic_c, tx, ty, tau) ? 1u : 0u;
+            n_touched += tile_contributes2(msx, msy, A2, B2, C2, tx, ty, tau2) ? 1u : 0u;
         }
     }
     uint32_t big = __ballot_sync(0xffffffffu, active && cand > (uint32_t)kSeqTiles);
@@ -219,13 +222,13 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
         const int src = __ffs((int)big) - 1;
         big &= big - 1;
         const float bmx = __shfl_sync(0xffffffffu, msx, src), bmy = __shfl_sync(0xffffffffu, msy, src);
-        const float bA = __shfl_sync(0xffffffffu, conic_a, src), bB = __shfl_sync(0xffffffffu, conic_b, src);
-        const float bC = __shfl_sync(0xffffffffu, conic_c, src), btau = __shfl_sync(0xffffffffu, tau, src);
+        const float bA = __shfl_sync(0xffffffffu, A2, src), bB = __shfl_sync(0xffffffffu, B2, src);
+        const float bC = __shfl_sync(0xffffffffu, C2, src), btau = __shfl_sync(0xffffffffu, tau2, src);
         const uint32_t bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
         const uint32_t btw = __shfl_sync(0xffffffffu, tw, src), bcand = __shfl_sync(0xffffffffu, cand, src);
         uint32_t cnt = 0;
         for (uint32_t c = lane; c < bcand; c += 32)
-            cnt += tile_contributes(bmx, bmy, bA, bB, bC, bx0 + c % btw, by0 + c / btw, btau) ? 1u : 0u;
+            cnt += tile_contributes2(bmx, bmy, bA, bB, bC, bx0 + c % btw, by0 + c / btw, btau) ? 1u : 0u;
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == src) n_touched = cnt;
     }
@@ -258,16 +261,12 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     dir.y *= inv_len;
     dir.z *= inv_len;
     float3 color = eval_sh(make_float3(s_sh0[3 * r], s_sh0[3 * r + 1], s_sh0[3 * r + 2]), rest_ptr, dir, active_bases);
-    if (kInference) {  // inference stores the colour already clamped (kernels_inference.cuh:200)
-        color.x = fmaxf(color.x, 0.0f);
-        color.y = fmaxf(color.y, 0.0f);
-        color.z = fmaxf(color.z, 0.0f);
-    }
-
+    // colours are stored clamped (what every blend consumes, kernels_forward.cuh:430 /
+    // kernels_inference.cuh:200); the clamp mask for the backward rides in the sign bit
     Rec rec;
-    rec.q0 = make_float4(m2x, m2y, conic_a, conic_b);
-    rec.q1 = make_float4(conic_c, opacity, color.x, color.y);
-    rec.q2 = make_float4(color.z, __uint_as_float(xmin | (xmax << 16)), __uint_as_float(ymin | (ymax << 16)),
+    rec.q0 = make_float4(m2x, m2y, A2, B2);
+    rec.q1 = make_float4(C2, opacity, pack_color(color.x), pack_color(color.y));
+    rec.q2 = make_float4(pack_color(color.z), __uint_as_float(xmin | (xmax << 16)), __uint_as_float(ymin | (ymax << 16)),
                          __uint_as_float((uint32_t)idx));
     recs[idx] = rec;
 
