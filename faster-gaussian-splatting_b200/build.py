@@ -44,7 +44,14 @@ def newest_mtime(paths) -> float:
     return max(p.stat().st_mtime for p in paths)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path | None = None) -> Path:
+    """`defines`/`out` build an experiment variant (e.g. -DFGS_UNROLL_BWD=1) next to the product library;
+    select it at run time with FGS_B200_LIB=<path>."""
+    global LIB, OBJ_DIR
+    if out is not None:
+        LIB = Path(out)
+        OBJ_DIR = HERE / 'build' / ('obj_' + LIB.stem)
+        force = True
     srcs = [CSRC / s for s in SOURCES]
     deps = srcs + [(CSRC / h).resolve() for h in HEADERS] + [Path(__file__)]
     if LIB.exists() and not force and LIB.stat().st_mtime >= newest_mtime(deps):
@@ -55,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> tuple[Path, str]:
         obj = OBJ_DIR / (src.stem + '.o')
-        cmd = [nvcc, *NVCC_FLAGS, '-c', str(src), '-o', str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f'-D{d}' for d in defines], '-c', str(src), '-o', str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f'nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}')
@@ -80,5 +87,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--force', action='store_true')
     ap.add_argument('--verbose', action='store_true')
+    ap.add_argument('-D', dest='defines', action='append', default=[])
+    ap.add_argument('--out', default=None)
     args = ap.parse_args()
-    print(build(force=args.force, verbose=args.verbose))
+    print(build(force=args.force, verbose=args.verbose, defines=tuple(args.defines), out=args.out))

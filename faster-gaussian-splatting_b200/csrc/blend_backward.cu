@@ -36,6 +36,13 @@ struct StageHdr {
     int tile, offset, count, pad;
 };
 
+#ifndef FGS_UNROLL_BWD
+#define FGS_UNROLL_BWD 1
+#endif
+#ifndef FGS_BWD_MAXREG
+#define FGS_BWD_MAXREG 80
+#endif
+constexpr int kUnroll = FGS_UNROLL_BWD;   // Gaussians evaluated per phase-A iteration
 constexpr int kSlots = 16;  // surviving Gaussians queued per warp before phase B runs
 
 struct WarpScratch {
@@ -109,7 +116,7 @@ struct __align__(128) BwdSmem {
     WarpScratch ws[kBlendWarps];
 };
 
-__global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
+__global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -128,16 +135,33 @@ __global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, cons
         if (lane != 0) return;
         int stage = 0;
         uint32_t phase = 0;
+        // two-deep software pipeline of the tile queue (see blend_forward.cu)
+        int t1 = (int)atomicAdd(a.queue, 1u);
+        uint2 r1 = make_uint2(0u, 0u);
+        uint32_t m1 = 0;
+        if (t1 < a.n_tiles) {
+            r1 = __ldg(a.tile_ranges + t1);
+            m1 = __ldg(a.tile_max_n + t1);
+        }
+        int t2 = (int)atomicAdd(a.queue, 1u);
         for (;;) {
-            const int tile = (int)atomicAdd(a.queue, 1u);
+            const int tile = t1;
             if (tile >= a.n_tiles) break;
-            const uint2 range = a.tile_ranges[tile];
+            const uint2 range = r1;
             // nothing past the tile's last contributor matters (kernels_backward.cuh:295)
-            const int n = min((int)(range.y - range.x), (int)a.tile_max_n[tile]);
+            const int n = min((int)(range.y - range.x), (int)m1);
+            t1 = t2;
+            if (t1 < a.n_tiles) {
+                r1 = __ldg(a.tile_ranges + t1);
+                m1 = __ldg(a.tile_max_n + t1);
+                t2 = (int)atomicAdd(a.queue, 1u);
+            } else {
+                t2 = a.n_tiles;
+            }
             if (n <= 0) continue;
             const int nb = (n + kBatch - 1) / kBatch;
             for (int b = 0; b < nb; ++b) {
-                mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
+                mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
                 const int cnt = min(kBatch, n - b * kBatch);
                 sm.hdr[stage].tile = tile;
                 sm.hdr[stage].offset = b * kBatch;
@@ -151,7 +175,7 @@ __global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, cons
                 }
             }
         }
-        mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
+        mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
         sm.hdr[stage].tile = -1;
         sm.hdr[stage].offset = 0;
         sm.hdr[stage].count = 0;
@@ -182,7 +206,7 @@ __global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, cons
     int stage = 0;
     uint32_t phase = 0;
     for (;;) {
-        mbar_wait_sleep(&sm.full[stage], phase);
+        mbar_wait_sleep<32>(&sm.full[stage], phase);
         const int tile = sm.hdr[stage].tile;
         const int offset = sm.hdr[stage].offset;
         const int count = sm.hdr[stage].count;
@@ -237,48 +261,55 @@ __global__ void __maxnreg__(80) blend_backward_kernel(const BlendBwdArgs a, cons
                 }
             }
             uint32_t pending = __ballot_sync(0xffffffffu, hit);
-            // two hits per iteration: the alpha evaluations are independent and overlap, only the
-            // transmittance / colour-after recurrences are sequential
+            // kUnroll hits per iteration, branch-free: the alpha evaluations and the dL/dalpha arithmetic of
+            // different Gaussians are independent; only T (one multiply) and the colour-after terms (one
+            // FMA per channel) chain from one Gaussian to the next
             while (pending) {
-                const int ja = __ffs((int)pending) - 1;
-                pending &= pending - 1;
-                const bool has_b = pending != 0u;
-                const int jb = has_b ? __ffs((int)pending) - 1 : ja;
-                pending &= pending - 1;
-                const float4 a0 = recs[ja].q0, a1 = recs[ja].q1;
-                const float4 b0 = recs[jb].q0, b1 = recs[jb].q1;
-                const float gauss_a = exp2f(fminf(blend_power2(a0.z, a0.w, a1.x, a0.x - px, a0.y - py), 0.0f));
-                const float gauss_b = exp2f(fminf(blend_power2(b0.z, b0.w, b1.x, b0.x - px, b0.y - py), 0.0f));
-                const float alpha_a = __fmul_rn(a1.y, gauss_a);
-                const float alpha_b = __fmul_rn(b1.y, gauss_b);
-                const bool contrib_a = alpha_a >= kMinAlpha && (uint32_t)(offset + ja) < n_proc;
-                const bool contrib_b = has_b && alpha_b >= kMinAlpha && (uint32_t)(offset + jb) < n_proc;
-#define FGS_PHASE_A(JJ, Q1, GAUSS, ALPHA, CONTRIB)                                                                  \
-    {                                                                                                                \
-        float u = 0.f, w = 0.f;                                                                                      \
-        if (CONTRIB) {                                                                                               \
-            const float c_b = recs[JJ].q2.x;                                                                         \
-            w = __fmul_rn(T, ALPHA);                                                                                 \
-            sr = fmaf(-w, Q1.z, sr);                                                                                 \
-            sg = fmaf(-w, Q1.w, sg);                                                                                 \
-            sb = fmaf(-w, c_b, sb);                                                                                  \
-            const float oma = __fsub_rn(1.0f, ALPHA);                                                                \
-            const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));                                       \
-            const float dlda = (T * Q1.z - sr * rcp) * gr + (T * Q1.w - sg * rcp) * gg + (T * c_b - sb * rcp) * gb + \
-                               galpha * rcp;                                                                         \
-            u = GAUSS * dlda;                                                                                        \
-            T = __fmul_rn(T, oma);                                                                                   \
-        }                                                                                                            \
-        if (__any_sync(0xffffffffu, CONTRIB)) {                                                                      \
-            ws.uw[nslots][lane] = make_float2(u, w);                                                                 \
-            if (lane < 3)                                                                                            \
-                reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[JJ])[lane]; \
-            if (++nslots == kSlots) flush();                                                                         \
-        }                                                                                                            \
-    }
-                FGS_PHASE_A(ja, a1, gauss_a, alpha_a, contrib_a)
-                if (has_b) FGS_PHASE_A(jb, b1, gauss_b, alpha_b, contrib_b)
-#undef FGS_PHASE_A
+                int jx[kUnroll];
+                bool vx[kUnroll];
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    vx[k] = pending != 0u;
+                    jx[k] = vx[k] ? __ffs((int)pending) - 1 : (k > 0 ? jx[k - 1] : 0);
+                    pending &= pending - 1;
+                }
+                float gauss[kUnroll], alpha[kUnroll], u[kUnroll], w[kUnroll];
+                bool cx[kUnroll];
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    const float4 q0 = recs[jx[k]].q0;
+                    const float c2 = recs[jx[k]].q1.x, op = recs[jx[k]].q1.y;
+                    gauss[k] = exp2f(fminf(blend_power2(q0.z, q0.w, c2, q0.x - px, q0.y - py), 0.0f));
+                    alpha[k] = __fmul_rn(op, gauss[k]);
+                    cx[k] = vx[k] && alpha[k] >= kMinAlpha && (uint32_t)(offset + jx[k]) < n_proc;
+                }
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    const float c_r = recs[jx[k]].q1.z, c_g = recs[jx[k]].q1.w, c_b = recs[jx[k]].q2.x;
+                    const float ae = cx[k] ? alpha[k] : 0.0f;  // alpha_eff = 0 leaves T and the colour-after terms untouched
+                    const float Tk = T;
+                    w[k] = __fmul_rn(Tk, ae);
+                    sr = fmaf(-w[k], c_r, sr);
+                    sg = fmaf(-w[k], c_g, sg);
+                    sb = fmaf(-w[k], c_b, sb);
+                    const float oma = __fsub_rn(1.0f, ae);
+                    T = __fmul_rn(Tk, oma);
+                    const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));
+                    const float dlda = fmaf(fmaf(-sr, rcp, Tk * c_r), gr,
+                                            fmaf(fmaf(-sg, rcp, Tk * c_g), gg,
+                                                 fmaf(fmaf(-sb, rcp, Tk * c_b), gb, galpha * rcp)));
+                    u[k] = cx[k] ? gauss[k] * dlda : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < kUnroll; ++k) {
+                    if (__any_sync(0xffffffffu, cx[k])) {
+                        ws.uw[nslots][lane] = make_float2(u[k], w[k]);
+                        if (lane < 3)
+                            reinterpret_cast<float4*>(&ws.par[nslots])[lane] =
+                                reinterpret_cast<const float4*>(&recs[jx[k]])[lane];
+                        if (++nslots == kSlots) flush();
+                    }
+                }
             }
         }
         __syncwarp();

@@ -29,6 +29,10 @@ namespace {
 
 constexpr int kBatch = 64;                                // records per bulk copy (3 KB)
 constexpr int kStages = 8;
+#ifndef FGS_UNROLL_FWD
+#define FGS_UNROLL_FWD 1
+#endif
+constexpr int kUnroll = FGS_UNROLL_FWD;                               // Gaussians evaluated per loop iteration
 constexpr int kSeqRing = 16;                              // > kStages: tiles in flight per CTA
 constexpr int kConsumerThreads = kBlendWarps * 32;        // 192
 constexpr int kFwdThreads = kConsumerThreads + 32;        // + producer warp
@@ -70,15 +74,23 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
         int stage = 0;
         uint32_t phase = 0;
         int seq = 0;
+        // the tile queue is software-pipelined two deep: the atomic for tile t+2 and the range load of
+        // tile t+1 are in flight while tile t streams, so their latency never stalls the ring
+        int t1 = (int)atomicAdd(a.queue, 1u);
+        uint2 r1 = t1 < a.n_tiles ? __ldg(a.tile_ranges + t1) : make_uint2(0u, 0u);
+        int t2 = (int)atomicAdd(a.queue, 1u);
         for (;;) {
-            const int tile = (int)atomicAdd(a.queue, 1u);
+            const int tile = t1;
             if (tile >= a.n_tiles) break;
-            const uint2 range = a.tile_ranges[tile];
+            const uint2 range = r1;
+            t1 = t2;
+            r1 = t1 < a.n_tiles ? __ldg(a.tile_ranges + t1) : make_uint2(0u, 0u);
+            t2 = t1 < a.n_tiles ? (int)atomicAdd(a.queue, 1u) : a.n_tiles;
             const int n = (int)(range.y - range.x);
             const int nb = n > 0 ? (n + kBatch - 1) / kBatch : 1;
             volatile uint32_t* dm = &sm.done_mask[seq & (kSeqRing - 1)];
             for (int b = 0; b < nb; ++b) {
-                mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
+                mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
                 // the slot of sequence number seq was last used kSeqRing tiles ago; every consumer has
                 // released that tile's stages long before (the ring is only kStages deep)
                 if (b == 0) *dm = 0;
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
             }
             ++seq;
         }
-        mbar_wait_sleep(&sm.empty[stage], phase ^ 1u);
+        mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
         sm.hdr[stage].tile = -1;
         sm.hdr[stage].seq = seq;
         sm.hdr[stage].offset = 0;
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
     int stage = 0;
     uint32_t phase = 0;
     for (;;) {
-        mbar_wait_sleep(&sm.full[stage], phase);
+        mbar_wait_sleep<32>(&sm.full[stage], phase);
         const int tile = sm.hdr[stage].tile;
         const int offset = sm.hdr[stage].offset;
         const int count = sm.hdr[stage].count;
@@ -206,23 +218,37 @@ __global__ void __launch_bounds__(kFwdThreads) blend_forward_kernel(const BlendF
                     }
                 }
                 uint32_t pending = __ballot_sync(0xffffffffu, hit);
+                // kUnroll hits per iteration, branch-free: the alpha evaluations are independent; T, the
+                // accumulated colour and the done flag chain from one Gaussian to the next
                 while (pending) {
-                    const int jj = g0 + __ffs((int)pending) - 1;
-                    pending &= pending - 1;
-                    const float4 q0 = recs[jj].q0;
-                    const float4 q1 = recs[jj].q1;
-                    const float dx = q0.x - px, dy = q0.y - py;
-                    const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, dx, dy), 0.0f));
-                    const float alpha = __fmul_rn(q1.y, gauss);
-                    if (alpha >= kMinAlpha && !done) {
-                        const float colb = recs[jj].q2.x;
-                        const float w = __fmul_rn(T, alpha);
-                        cr = fmaf(w, q1.z, cr);
-                        cg = fmaf(w, q1.w, cg);
-                        cb = fmaf(w, colb, cb);
-                        T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                        n_last = (uint32_t)(offset + jj + 1);
-                        done = T < kTransmittanceThreshold;
+                    int jx[kUnroll];
+                    bool vx[kUnroll];
+#pragma unroll
+                    for (int k = 0; k < kUnroll; ++k) {
+                        vx[k] = pending != 0u;
+                        jx[k] = vx[k] ? g0 + __ffs((int)pending) - 1 : (k > 0 ? jx[k - 1] : g0);
+                        pending &= pending - 1;
+                    }
+                    float alpha[kUnroll];
+#pragma unroll
+                    for (int k = 0; k < kUnroll; ++k) {
+                        const float4 q0 = recs[jx[k]].q0;
+                        const float c2 = recs[jx[k]].q1.x, op = recs[jx[k]].q1.y;
+                        const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, c2, q0.x - px, q0.y - py), 0.0f));
+                        alpha[k] = __fmul_rn(op, gauss);
+                        if (!(vx[k] && alpha[k] >= kMinAlpha)) alpha[k] = 0.0f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < kUnroll; ++k) {
+                        const bool c = alpha[k] > 0.0f && !done;
+                        const float ae = c ? alpha[k] : 0.0f;  // alpha_eff = 0 leaves the pixel untouched
+                        const float w = __fmul_rn(T, ae);
+                        cr = fmaf(w, recs[jx[k]].q1.z, cr);
+                        cg = fmaf(w, recs[jx[k]].q1.w, cg);
+                        cb = fmaf(w, recs[jx[k]].q2.x, cb);
+                        T = __fmul_rn(T, __fsub_rn(1.0f, ae));
+                        if (c) n_last = (uint32_t)(offset + jx[k] + 1);
+                        done = done || T < kTransmittanceThreshold;
                     }
                 }
                 if (__all_sync(0xffffffffu, done)) {

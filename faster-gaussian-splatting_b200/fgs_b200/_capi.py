@@ -79,15 +79,22 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() or os.environ.get('FGS_B200_REBUILD'):
+    override = os.environ.get('FGS_B200_LIB')  # experiment variants built with build.py --out
+    if override:
+        lib_path = Path(override)
+        if not lib_path.exists():
+            raise ImportError(f'fgs_b200: FGS_B200_LIB={override} does not exist')
+    elif not LIB_PATH.exists() or os.environ.get('FGS_B200_REBUILD'):
         import importlib.util
         spec = importlib.util.spec_from_file_location('fgs_b200_build', _PKG.parent / 'build.py')
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.build(force=bool(os.environ.get('FGS_B200_REBUILD')))
-    if not LIB_PATH.exists():
-        raise ImportError(f'fgs_b200: {LIB_PATH} is missing and could not be built; there is no fallback path')
-    lib = C.CDLL(str(LIB_PATH))
+    if not override:
+        lib_path = LIB_PATH
+    if not lib_path.exists():
+        raise ImportError(f'fgs_b200: {lib_path} is missing and could not be built; there is no fallback path')
+    lib = C.CDLL(str(lib_path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means the .so and the header disagree
         fn.restype = res
