@@ -9,13 +9,16 @@
 // raw logit.
 //
 // New design (no bucket checkpoints, no 223-step shuffle pipeline):
-//  * same persistent producer/consumer ring as the forward (tile-contiguous records via TMA bulk copies);
+//  * warp-autonomous persistent kernel, same (tile, sub-tile) item queue and per-warp TMA ring as the
+//    forward (blend_forward.cu); a warp only streams the prefix of its tile's list that its own 32
+//    pixels actually consumed in the forward;
 //  * phase A, pixel-parallel: every lane replays the forward for its pixel front-to-back (so the
 //    transmittance comes from registers, not from stored checkpoints) and emits two scalars per
 //    (Gaussian, pixel) pair into a per-warp shared-memory slot: u = G * dL/dalpha and w = T * alpha;
-//  * phase B, Gaussian-parallel: once 32 surviving Gaussians are queued, lane k owns slot k and sums its
-//    nine gradient components over the warp's 32 pixels straight out of shared memory -- a transpose
-//    through shared memory replaces nine warp reductions (or nine shuffles per pixel step) per Gaussian;
+//  * phase B, Gaussian-parallel: once 16 surviving Gaussians are queued, lanes k and k+16 own slot k
+//    and each sum its nine gradient components over 16 of the warp's 32 pixels straight out of shared
+//    memory; one shuffle step joins the halves -- a transpose through shared memory replaces nine
+//    warp reductions (or nine shuffles per pixel step) per Gaussian;
 //  * the nine sums leave as two 16-byte vector reductions + one scalar (REDG.E.ADD.F32x4) into a
 //    packed 48-byte per-Gaussian gradient record.
 // The stored conic is pre-scaled to the base-2 exponent domain (fgs_device.cuh); the gradients are
@@ -27,33 +30,26 @@ namespace fgs {
 
 namespace {
 
-constexpr int kBatch = 32;
-constexpr int kStages = 6;
-constexpr int kConsumerThreads = kBlendWarps * 32;
-constexpr int kBwdThreads = kConsumerThreads + 32;
-
-struct StageHdr {
-    int tile, offset, count, pad;
-};
-
-#ifndef FGS_UNROLL_BWD
-#define FGS_UNROLL_BWD 1
-#endif
 #ifndef FGS_BWD_MAXREG
 #define FGS_BWD_MAXREG 80
 #endif
-constexpr int kUnroll = FGS_UNROLL_BWD;   // Gaussians evaluated per phase-A iteration
-constexpr int kSlots = 16;  // surviving Gaussians queued per warp before phase B runs
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBatch = 32;   // records per bulk copy = one cull group
+constexpr int kRing = 2;     // ring slots per warp
+constexpr int kSlots = 16;   // surviving Gaussians queued per warp before phase B runs
 
-struct WarpScratch {
+struct __align__(128) WarpSmem {
+    Rec recs[kRing][kBatch];
     float2 uw[kSlots][33];  // [slot][pixel] -> (u, w)
     float4 g[32];           // per pixel: dL/d(colour)
     Rec par[kSlots];        // per slot: the Gaussian's record
+    uint64_t full[kRing];
 };
 
 // Phase B: lanes k and k+16 own slot k and each reduce it over 16 of the warp's 32 pixels straight out
 // of shared memory; one shuffle step joins the halves, lane k emits the nine gradient components.
-__device__ __noinline__ void flush_slots(WarpScratch& ws, const int nslots, const int lane, const float fx0,
+__device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const int lane, const float fx0,
                                          const float fy0, const bool proper_aa, Grad2D* __restrict__ grad2d) {
     __syncwarp();
     const int slot = lane & (kSlots - 1);
@@ -108,147 +104,104 @@ __device__ __noinline__ void flush_slots(WarpScratch& ws, const int nslots, cons
     __syncwarp();
 }
 
-struct __align__(128) BwdSmem {
-    Rec recs[kStages][kBatch];
-    StageHdr hdr[kStages];
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
-    WarpScratch ws[kBlendWarps];
-};
-
 __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kBlendWarps);
-        }
+    WarpSmem* all = reinterpret_cast<WarpSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& ws = all[warp];
+    if (lane == 0) {
+        for (int s = 0; s < kRing; ++s) mbar_init(&ws.full[s], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
 
-    if (warp == kBlendWarps) {
-        // ================================ producer warp ================================
-        if (lane != 0) return;
-        int stage = 0;
-        uint32_t phase = 0;
-        // two-deep software pipeline of the tile queue (see blend_forward.cu)
-        int t1 = (int)atomicAdd(a.queue, 1u);
-        uint2 r1 = make_uint2(0u, 0u);
-        uint32_t m1 = 0;
-        if (t1 < a.n_tiles) {
-            r1 = __ldg(a.tile_ranges + t1);
-            m1 = __ldg(a.tile_max_n + t1);
-        }
-        int t2 = (int)atomicAdd(a.queue, 1u);
-        for (;;) {
-            const int tile = t1;
-            if (tile >= a.n_tiles) break;
-            const uint2 range = r1;
-            // nothing past the tile's last contributor matters (kernels_backward.cuh:295)
-            const int n = min((int)(range.y - range.x), (int)m1);
-            t1 = t2;
-            if (t1 < a.n_tiles) {
-                r1 = __ldg(a.tile_ranges + t1);
-                m1 = __ldg(a.tile_max_n + t1);
-                t2 = (int)atomicAdd(a.queue, 1u);
-            } else {
-                t2 = a.n_tiles;
-            }
-            if (n <= 0) continue;
-            const int nb = (n + kBatch - 1) / kBatch;
-            for (int b = 0; b < nb; ++b) {
-                mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
-                const int cnt = min(kBatch, n - b * kBatch);
-                sm.hdr[stage].tile = tile;
-                sm.hdr[stage].offset = b * kBatch;
-                sm.hdr[stage].count = cnt;
-                mbar_arrive_expect_tx(&sm.full[stage], (uint32_t)cnt * (uint32_t)sizeof(Rec));
-                bulk_g2s(&sm.recs[stage][0], a.inst_recs + range.x + (uint32_t)(b * kBatch),
-                         (uint32_t)cnt * (uint32_t)sizeof(Rec), &sm.full[stage]);
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
-            }
-        }
-        mbar_wait_sleep<256>(&sm.empty[stage], phase ^ 1u);
-        sm.hdr[stage].tile = -1;
-        sm.hdr[stage].offset = 0;
-        sm.hdr[stage].count = 0;
-        mbar_arrive(&sm.full[stage]);
-        return;
-    }
-
-    // ================================== consumer warps ==================================
-    WarpScratch& ws = sm.ws[warp];
     const float3 bg = make_float3(__ldg(cam.bg), __ldg(cam.bg + 1), __ldg(cam.bg + 2));
     const uint32_t n_pixels = (uint32_t)cam.img_w * (uint32_t)cam.img_h;
-    int cur_tile = -2;  // distinct from the end-of-stream marker (-1): a CTA may receive no tile at all
-    // per-pixel state (phase A)
-    float sr = 0.f, sg = 0.f, sb = 0.f;  // colour still to come behind the current Gaussian ("colour after")
-    float gr = 0.f, gg = 0.f, gb = 0.f;  // dL/dpixel colour
-    float galpha = 0.f;                  // T_final * -(bg . g)
-    float T = 1.f;
-    uint32_t n_proc = 0, warp_max = 0;
-    float px = 0.f, py = 0.f;
-    uint32_t sub_x0 = 0, sub_y0 = 0;
-    int nslots = 0;
-
-    auto flush = [&]() {
-        flush_slots(ws, nslots, lane, (float)sub_x0 + 0.5f, (float)sub_y0 + 0.5f, cam.proper_aa != 0, a.grad2d);
-        nslots = 0;
+    const int n_items = a.n_tiles * kBlendWarps;
+    auto grab = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = (int)atomicAdd(a.queue, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
     };
+    // two-deep software pipeline of the item queue (see blend_forward.cu)
+    int i1 = grab();
+    uint2 r1 = make_uint2(0u, 0u);
+    uint32_t m1 = 0;
+    if (i1 < n_items) {
+        r1 = __ldg(a.tile_ranges + i1 / kBlendWarps);
+        m1 = __ldg(a.tile_max_n + i1);
+    }
+    int i2 = grab();
+    uint32_t k = 0;
 
-    int stage = 0;
-    uint32_t phase = 0;
     for (;;) {
-        mbar_wait_sleep<32>(&sm.full[stage], phase);
-        const int tile = sm.hdr[stage].tile;
-        const int offset = sm.hdr[stage].offset;
-        const int count = sm.hdr[stage].count;
-        if (tile != cur_tile) {
-            if (nslots > 0) flush();
-            if (tile < 0) break;
-            cur_tile = tile;
-            const uint32_t tile_x = (uint32_t)tile % (uint32_t)cam.grid_w, tile_y = (uint32_t)tile / (uint32_t)cam.grid_w;
-            sub_x0 = tile_x * kTileW + (uint32_t)(warp & 1) * kSubW;
-            sub_y0 = tile_y * kTileH + (uint32_t)(warp >> 1) * kSubH;
-            const uint32_t pix_x = sub_x0 + (uint32_t)(lane & 7);
-            const uint32_t pix_y = sub_y0 + (uint32_t)(lane >> 3);
-            const bool inside = pix_x < (uint32_t)cam.img_w && pix_y < (uint32_t)cam.img_h;
-            px = (float)pix_x + 0.5f;
-            py = (float)pix_y + 0.5f;
-            T = 1.f;
-            n_proc = 0;
-            gr = gg = gb = 0.f;
-            sr = sg = sb = 0.f;
-            galpha = 0.f;
-            if (inside) {
-                const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
-                n_proc = a.n_processed[pidx];
-                const float Tf = a.final_T[pidx];
-                gr = a.grad_image[pidx];
-                gg = a.grad_image[n_pixels + pidx];
-                gb = a.grad_image[2 * n_pixels + pidx];
-                sr = a.image[pidx] - Tf * bg.x;
-                sg = a.image[n_pixels + pidx] - Tf * bg.y;
-                sb = a.image[2 * n_pixels + pidx] - Tf * bg.z;
-                galpha = Tf * -(gr * bg.x + gg * bg.y + gb * bg.z);
-            }
-            warp_max = __reduce_max_sync(0xffffffffu, n_proc);
-            ws.g[lane] = make_float4(gr, gg, gb, 0.f);
-            __syncwarp();
+        const int item = i1;
+        if (item >= n_items) break;
+        const uint2 range = r1;
+        // nothing past this sub-tile's last contributor matters (kernels_backward.cuh:295)
+        const int n = min((int)(range.y - range.x), (int)m1);
+        i1 = i2;
+        if (i1 < n_items) {
+            r1 = __ldg(a.tile_ranges + i1 / kBlendWarps);
+            m1 = __ldg(a.tile_max_n + i1);
+            i2 = grab();
+        } else {
+            i2 = n_items;
         }
-        if ((uint32_t)offset < warp_max) {
-            const Rec* recs = &sm.recs[stage][0];
-            const float fx0 = (float)sub_x0, fy0 = (float)sub_y0;
-            // one 32-record batch = one cull group
+        if (n <= 0) continue;
+
+        const int tile = item / kBlendWarps, sub = item - tile * kBlendWarps;
+        const uint32_t tile_x = (uint32_t)tile % (uint32_t)cam.grid_w, tile_y = (uint32_t)tile / (uint32_t)cam.grid_w;
+        const uint32_t sub_x0 = tile_x * kTileW + (uint32_t)(sub & 1) * kSubW;
+        const uint32_t sub_y0 = tile_y * kTileH + (uint32_t)(sub >> 1) * kSubH;
+        const uint32_t pix_x = sub_x0 + (uint32_t)(lane & 7), pix_y = sub_y0 + (uint32_t)(lane >> 3);
+        const bool inside = pix_x < (uint32_t)cam.img_w && pix_y < (uint32_t)cam.img_h;
+        const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
+        const float fx0 = (float)sub_x0, fy0 = (float)sub_y0;
+
+        const int nb = (n + kBatch - 1) / kBatch;
+        const Rec* src = a.inst_recs + range.x;
+        int issued = 0;
+        auto issue = [&]() {
+            if (lane == 0) {
+                const uint32_t slot = (k + (uint32_t)issued) % kRing;
+                const uint32_t bytes = (uint32_t)min(kBatch, n - issued * kBatch) * (uint32_t)sizeof(Rec);
+                mbar_arrive_expect_tx(&ws.full[slot], bytes);
+                bulk_g2s(&ws.recs[slot][0], src + issued * kBatch, bytes, &ws.full[slot]);
+            }
+            ++issued;
+        };
+        while (issued < nb && issued < kRing) issue();
+
+        // per-pixel state: colour still to come behind the current Gaussian ("colour after"),
+        // dL/d(pixel colour), T_final * -(bg . g), running transmittance
+        float sr = 0.f, sg = 0.f, sb = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, galpha = 0.f, T = 1.f;
+        uint32_t n_proc = 0;
+        if (inside) {
+            const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
+            n_proc = a.n_processed[pidx];
+            const float Tf = a.final_T[pidx];
+            gr = a.grad_image[pidx];
+            gg = a.grad_image[n_pixels + pidx];
+            gb = a.grad_image[2 * n_pixels + pidx];
+            sr = a.image[pidx] - Tf * bg.x;
+            sg = a.image[n_pixels + pidx] - Tf * bg.y;
+            sb = a.image[2 * n_pixels + pidx] - Tf * bg.z;
+            galpha = Tf * -(gr * bg.x + gg * bg.y + gb * bg.z);
+        }
+        ws.g[lane] = make_float4(gr, gg, gb, 0.f);
+        __syncwarp();
+        int nslots = 0;
+
+        for (int b = 0; b < nb; ++b) {
+            const uint32_t kb = k + (uint32_t)b;
+            const uint32_t slot = kb % kRing;
+            mbar_wait(&ws.full[slot], (kb / kRing) & 1u);
+            const Rec* recs = &ws.recs[slot][0];
+            const int count = min(kBatch, n - b * kBatch);
+            const int offset = b * kBatch;
             bool hit = false;
-            if (lane < count && (uint32_t)(offset + lane) < warp_max) {
+            if (lane < count) {
                 const float4 q2 = recs[lane].q2;
                 const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
                 hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
@@ -261,63 +214,43 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 }
             }
             uint32_t pending = __ballot_sync(0xffffffffu, hit);
-            // kUnroll hits per iteration, branch-free: the alpha evaluations and the dL/dalpha arithmetic of
-            // different Gaussians are independent; only T (one multiply) and the colour-after terms (one
-            // FMA per channel) chain from one Gaussian to the next
+            // branch-free body: alpha_eff = 0 leaves T and the colour-after terms untouched
             while (pending) {
-                int jx[kUnroll];
-                bool vx[kUnroll];
-#pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
-                    vx[k] = pending != 0u;
-                    jx[k] = vx[k] ? __ffs((int)pending) - 1 : (k > 0 ? jx[k - 1] : 0);
-                    pending &= pending - 1;
-                }
-                float gauss[kUnroll], alpha[kUnroll], u[kUnroll], w[kUnroll];
-                bool cx[kUnroll];
-#pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
-                    const float4 q0 = recs[jx[k]].q0;
-                    const float c2 = recs[jx[k]].q1.x, op = recs[jx[k]].q1.y;
-                    gauss[k] = exp2f(fminf(blend_power2(q0.z, q0.w, c2, q0.x - px, q0.y - py), 0.0f));
-                    alpha[k] = __fmul_rn(op, gauss[k]);
-                    cx[k] = vx[k] && alpha[k] >= kMinAlpha && (uint32_t)(offset + jx[k]) < n_proc;
-                }
-#pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
-                    const float c_r = recs[jx[k]].q1.z, c_g = recs[jx[k]].q1.w, c_b = recs[jx[k]].q2.x;
-                    const float ae = cx[k] ? alpha[k] : 0.0f;  // alpha_eff = 0 leaves T and the colour-after terms untouched
-                    const float Tk = T;
-                    w[k] = __fmul_rn(Tk, ae);
-                    sr = fmaf(-w[k], c_r, sr);
-                    sg = fmaf(-w[k], c_g, sg);
-                    sb = fmaf(-w[k], c_b, sb);
-                    const float oma = __fsub_rn(1.0f, ae);
-                    T = __fmul_rn(Tk, oma);
-                    const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));
-                    const float dlda = fmaf(fmaf(-sr, rcp, Tk * c_r), gr,
-                                            fmaf(fmaf(-sg, rcp, Tk * c_g), gg,
-                                                 fmaf(fmaf(-sb, rcp, Tk * c_b), gb, galpha * rcp)));
-                    u[k] = cx[k] ? gauss[k] * dlda : 0.0f;
-                }
-#pragma unroll
-                for (int k = 0; k < kUnroll; ++k) {
-                    if (__any_sync(0xffffffffu, cx[k])) {
-                        ws.uw[nslots][lane] = make_float2(u[k], w[k]);
-                        if (lane < 3)
-                            reinterpret_cast<float4*>(&ws.par[nslots])[lane] =
-                                reinterpret_cast<const float4*>(&recs[jx[k]])[lane];
-                        if (++nslots == kSlots) flush();
+                const int jj = __ffs((int)pending) - 1;
+                pending &= pending - 1;
+                const float4 q0 = recs[jj].q0;
+                const float4 q1 = recs[jj].q1;
+                const float c_b = recs[jj].q2.x;
+                const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, q0.x - px, q0.y - py), 0.0f));
+                const float alpha = __fmul_rn(q1.y, gauss);
+                const bool c = alpha >= kMinAlpha && (uint32_t)(offset + jj) < n_proc;
+                const float ae = c ? alpha : 0.0f;
+                const float Tk = T;
+                const float w = __fmul_rn(Tk, ae);
+                sr = fmaf(-w, q1.z, sr);
+                sg = fmaf(-w, q1.w, sg);
+                sb = fmaf(-w, c_b, sb);
+                const float oma = __fsub_rn(1.0f, ae);
+                T = __fmul_rn(Tk, oma);
+                const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));
+                const float dlda = fmaf(fmaf(-sr, rcp, Tk * q1.z), gr,
+                                        fmaf(fmaf(-sg, rcp, Tk * q1.w), gg, fmaf(fmaf(-sb, rcp, Tk * c_b), gb, galpha * rcp)));
+                const float u = c ? gauss * dlda : 0.0f;
+                if (__any_sync(0xffffffffu, c)) {
+                    ws.uw[nslots][lane] = make_float2(u, w);
+                    if (lane < 3)
+                        reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[jj])[lane];
+                    if (++nslots == kSlots) {
+                        flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
+                        nslots = 0;
                     }
                 }
             }
+            __syncwarp();
+            if (issued < nb) issue();  // refill the slot just consumed
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
-        if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-        }
+        k += (uint32_t)nb;
+        if (nslots > 0) flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
     }
 }
 
@@ -326,7 +259,7 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
 cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream) {
     if (a.n_tiles <= 0) return cudaSuccess;
     static int s_grid = 0;
-    const size_t smem = sizeof(BwdSmem);
+    const size_t smem = sizeof(WarpSmem) * kWarps;
     if (s_grid == 0) {
         cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -335,12 +268,13 @@ cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStr
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_backward_kernel, kBwdThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_backward_kernel, kThreads, smem);
         if (occ < 1) occ = 1;
         s_grid = sms * occ;
     }
-    const int g = s_grid < a.n_tiles ? s_grid : a.n_tiles;
-    blend_backward_kernel<<<g, kBwdThreads, smem, stream>>>(a, cam);
+    const int items = a.n_tiles * kBlendWarps;
+    const int g = s_grid < (items + kWarps - 1) / kWarps ? s_grid : (items + kWarps - 1) / kWarps;
+    blend_backward_kernel<<<g, kThreads, smem, stream>>>(a, cam);
     return cudaGetLastError();
 }
 

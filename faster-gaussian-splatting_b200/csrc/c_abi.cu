@@ -132,7 +132,7 @@ struct TileLayout {
     TileLayout(char* blob, int n_tiles, int n_pixels, bool training) {
         Carver c(blob);
         ranges = c.take<uint2>((size_t)n_tiles);
-        tile_max_n = c.take<uint32_t>((size_t)n_tiles);
+        tile_max_n = c.take<uint32_t>((size_t)n_tiles * kBlendWarps);  // last contributor per (tile, sub-tile) item
         final_T = training ? c.take<float>((size_t)n_pixels) : nullptr;
         n_processed = training ? c.take<uint32_t>((size_t)n_pixels) : nullptr;
         bytes = c.bytes();
@@ -262,9 +262,8 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     PrimitiveLayout pl(prim_blob, n);
 
     FGS_TRY(cudaMemsetAsync(pl.counters, 0, sizeof(uint32_t) * kCtrCount, stream), "memset counters");
-    // ranges and tile_max_n are adjacent in the layout only up to alignment: clear both explicitly
+    // empty tiles keep the range (0, 0); tile_max_n is written for every item by the blend forward
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
-    FGS_TRY(cudaMemsetAsync(tl.tile_max_n, 0, sizeof(uint32_t) * n_tiles, stream), "memset tile_max_n");
 
     FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.keys[0],
                               pl.idx[0], pl.counters, n, cam, !training, stream),
