@@ -76,32 +76,54 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     }
 }
 
-// one thread per 16-byte third of an instance record; the first third also emits the tile range
-// boundaries (kernels_forward.cuh:330-348)
+// One thread per instance: gathers the Gaussian's 48-byte record into instance order, replaces the
+// bounding box (only needed up to here) by the 6-bit mask of the tile's 8x4 sub-tiles the Gaussian
+// actually reaches -- strict bounding-box overlap (kernels_forward.cuh:445-451) and the exact
+// maximum-inside-the-rectangle test, evaluated once here instead of once per warp and batch in both
+// blend kernels -- and emits the tile range boundaries (kernels_forward.cuh:330-348).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restrict__ keys,
                                                             const uint32_t* __restrict__ vals,
                                                             const Rec* __restrict__ recs, Rec* __restrict__ inst_recs,
-                                                            uint2* __restrict__ ranges, const uint32_t n_inst) {
-    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t inst = t / 3u, part = t - inst * 3u;
+                                                            uint2* __restrict__ ranges, const uint32_t n_inst,
+                                                            const uint32_t grid_w) {
+    const uint32_t inst = blockIdx.x * 256u + threadIdx.x;
     if (inst >= n_inst) return;
     const uint32_t prim = __ldg(vals + inst);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(recs + prim) + part);
-    reinterpret_cast<float4*>(inst_recs)[t] = v;
-    if (part == 0) {
-        const uint32_t key = (uint32_t)keys[inst];
-        if (inst == 0) {
-            ranges[key].x = 0;
-        } else {
-            const uint32_t prev = (uint32_t)keys[inst - 1];
-            if (prev != key) {
-                ranges[prev].y = inst;
-                ranges[key].x = inst;
-            }
-        }
-        if (inst == n_inst - 1) ranges[key].y = n_inst;
+    const uint32_t key = (uint32_t)keys[inst];
+    const float4 q0 = __ldg(&recs[prim].q0);
+    const float4 q1 = __ldg(&recs[prim].q1);
+    float4 q2 = __ldg(&recs[prim].q2);
+    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+    const uint32_t xmin = bx & 0xffffu, xmax = bx >> 16, ymin = by & 0xffffu, ymax = by >> 16;
+    const uint32_t tx0 = (key % grid_w) * kTileW, ty0 = (key / grid_w) * kTileH;
+    const float tau2 = __log2f(q1.y * kMinAlphaRcp);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int sub = 0; sub < kBlendWarps; ++sub) {
+        const uint32_t sx = tx0 + (uint32_t)(sub & 1) * kSubW, sy = ty0 + (uint32_t)(sub >> 1) * kSubH;
+        bool hit = xmin < sx + kSubW && sx < xmax && ymin < sy + kSubH && sy < ymax;
+        if (hit)
+            hit = rect_contributes2(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, (float)sx, (float)sy, (float)(kSubW - 1),
+                                    (float)(kSubH - 1), tau2);
+        mask |= (hit ? 1u : 0u) << sub;
     }
+    q2.y = __uint_as_float(mask);
+    q2.z = 0.0f;
+    Rec* dst = inst_recs + inst;
+    dst->q0 = q0;
+    dst->q1 = q1;
+    dst->q2 = q2;
+    if (inst == 0) {
+        ranges[key].x = 0;
+    } else {
+        const uint32_t prev = (uint32_t)keys[inst - 1];
+        if (prev != key) {
+            ranges[prev].y = inst;
+            ranges[key].x = inst;
+        }
+    }
+    if (inst == n_inst - 1) ranges[key].y = n_inst;
 }
 
 }  // namespace
@@ -122,16 +144,16 @@ template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const ui
 
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
-                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, cudaStream_t stream) {
+                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, int grid_w,
+                                     cudaStream_t stream) {
     if (n_instances <= 0) return cudaSuccess;
-    const long long threads = 3ll * n_instances;
-    ranges_gather_kernel<KeyT><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, (uint32_t)n_instances);
+    ranges_gather_kernel<KeyT><<<(unsigned)((n_instances + 255) / 256), 256, 0, stream>>>(
+        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, (uint32_t)n_instances, (uint32_t)grid_w);
     return cudaGetLastError();
 }
 template cudaError_t launch_ranges_and_gather<uint16_t>(const uint16_t*, const uint32_t*, const Rec*, Rec*, uint2*, int,
-                                                        cudaStream_t);
+                                                        int, cudaStream_t);
 template cudaError_t launch_ranges_and_gather<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, Rec*, uint2*, int,
-                                                        cudaStream_t);
+                                                        int, cudaStream_t);
 
 }  // namespace fgs

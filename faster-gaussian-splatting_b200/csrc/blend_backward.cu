@@ -41,65 +41,84 @@ constexpr int kSlots = 16;   // surviving Gaussians queued per warp before phase
 
 struct __align__(128) WarpSmem {
     Rec recs[kRing][kBatch];
-    float2 uw[kSlots][33];  // [slot][pixel] -> (u, w)
-    float4 g[32];           // per pixel: dL/d(colour)
+    float u[kSlots][34];    // [slot][pixel] -> u = G * dL/dalpha   (row stride 34: 8-byte aligned pixel pairs,
+    float w[kSlots][34];    // [slot][pixel] -> w = T * alpha         conflict-free 64-bit reads in phase B)
+    float g[3][32];         // per pixel: dL/d(colour), one plane per channel
     Rec par[kSlots];        // per slot: the Gaussian's record
     uint64_t full[kRing];
 };
 
 // Phase B: lanes k and k+16 own slot k and each reduce it over 16 of the warp's 32 pixels straight out
-// of shared memory; one shuffle step joins the halves, lane k emits the nine gradient components.
+// of shared memory, two horizontally adjacent pixels per step with packed FP32x2 arithmetic (FFMA2 /
+// FMUL2 / FADD2: half the issue slots of the scalar form); one shuffle step joins the halves, lane k
+// emits the nine gradient components.
 __device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const int lane, const float fx0,
                                          const float fy0, const bool proper_aa, Grad2D* __restrict__ grad2d) {
     __syncwarp();
     const int slot = lane & (kSlots - 1);
-    const int p0 = lane & kSlots;  // 0 or 16: first pixel of this half
+    const int p0 = lane & kSlots;  // 0 or 16: first pixel of this half (two rows of eight pixels)
     const float4 q0 = ws.par[slot].q0;
     const float4 q1 = ws.par[slot].q1;
-    const float mx = q0.x, my = q0.y, op = q1.y;
-    float dop = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
-    float mxx = 0.f, mxy = 0.f, myy = 0.f, mx1 = 0.f, my1 = 0.f;
+    const float op = q1.y;
+    float2 dop = make_float2(0.f, 0.f), dcr = dop, dcg = dop, dcb = dop;
+    float2 mxx = dop, mxy = dop, myy = dop, mx1 = dop, my1 = dop;
     if (slot < nslots) {
-#pragma unroll 8
-        for (int i = 0; i < 16; ++i) {
-            const int p = p0 + i;
-            const float2 uw = ws.uw[slot][p];
-            const float4 g4 = ws.g[p];
-            const float dx = mx - (fx0 + (float)(p & 7));
-            const float dy = my - (fy0 + (float)(p >> 3));
-            const float h = -op * uw.x;  // -alpha * dL/dalpha
-            dop += uw.x;
-            dcr = fmaf(uw.y, g4.x, dcr);
-            dcg = fmaf(uw.y, g4.y, dcg);
-            dcb = fmaf(uw.y, g4.z, dcb);
-            const float hx = h * dx, hy = h * dy;
-            mx1 += hx;
-            my1 += hy;
-            mxx = fmaf(hx, dx, mxx);
-            mxy = fmaf(hx, dy, mxy);
-            myy = fmaf(hy, dy, myy);
+        const float2 nop2 = make_float2(-op, -op);
+        const float2 step = make_float2(-2.0f, -2.0f);
+        const float* urow = &ws.u[slot][p0];
+        const float* wrow = &ws.w[slot][p0];
+        float dy = q0.y - (fy0 + (float)(p0 >> 3));
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            float2 dx = make_float2(q0.x - fx0, q0.x - fx0 - 1.0f);
+            const float2 dy2 = make_float2(dy, dy);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = row * 8 + c * 2;
+                const float2 u2 = *reinterpret_cast<const float2*>(urow + i);
+                const float2 w2 = *reinterpret_cast<const float2*>(wrow + i);
+                const float2 gr2 = *reinterpret_cast<const float2*>(&ws.g[0][p0 + i]);
+                const float2 gg2 = *reinterpret_cast<const float2*>(&ws.g[1][p0 + i]);
+                const float2 gb2 = *reinterpret_cast<const float2*>(&ws.g[2][p0 + i]);
+                const float2 h2 = __fmul2_rn(nop2, u2);  // -alpha * dL/dalpha
+                dop = __fadd2_rn(dop, u2);
+                dcr = __ffma2_rn(w2, gr2, dcr);
+                dcg = __ffma2_rn(w2, gg2, dcg);
+                dcb = __ffma2_rn(w2, gb2, dcb);
+                const float2 hx = __fmul2_rn(h2, dx), hy = __fmul2_rn(h2, dy2);
+                mx1 = __fadd2_rn(mx1, hx);
+                my1 = __fadd2_rn(my1, hy);
+                mxx = __ffma2_rn(hx, dx, mxx);
+                mxy = __ffma2_rn(hx, dy2, mxy);
+                myy = __ffma2_rn(hy, dy2, myy);
+                dx = __fadd2_rn(dx, step);
+            }
+            dy -= 1.0f;
         }
     }
-    dop += __shfl_xor_sync(0xffffffffu, dop, 16);
-    dcr += __shfl_xor_sync(0xffffffffu, dcr, 16);
-    dcg += __shfl_xor_sync(0xffffffffu, dcg, 16);
-    dcb += __shfl_xor_sync(0xffffffffu, dcb, 16);
-    mx1 += __shfl_xor_sync(0xffffffffu, mx1, 16);
-    my1 += __shfl_xor_sync(0xffffffffu, my1, 16);
-    mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
-    mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
-    myy += __shfl_xor_sync(0xffffffffu, myy, 16);
+    float s_dop = dop.x + dop.y, s_dcr = dcr.x + dcr.y, s_dcg = dcg.x + dcg.y, s_dcb = dcb.x + dcb.y;
+    float s_mx1 = mx1.x + mx1.y, s_my1 = my1.x + my1.y, s_mxx = mxx.x + mxx.y, s_mxy = mxy.x + mxy.y,
+          s_myy = myy.x + myy.y;
+    s_dop += __shfl_xor_sync(0xffffffffu, s_dop, 16);
+    s_dcr += __shfl_xor_sync(0xffffffffu, s_dcr, 16);
+    s_dcg += __shfl_xor_sync(0xffffffffu, s_dcg, 16);
+    s_dcb += __shfl_xor_sync(0xffffffffu, s_dcb, 16);
+    s_mx1 += __shfl_xor_sync(0xffffffffu, s_mx1, 16);
+    s_my1 += __shfl_xor_sync(0xffffffffu, s_my1, 16);
+    s_mxx += __shfl_xor_sync(0xffffffffu, s_mxx, 16);
+    s_mxy += __shfl_xor_sync(0xffffffffu, s_mxy, 16);
+    s_myy += __shfl_xor_sync(0xffffffffu, s_myy, 16);
     if (lane < nslots) {
         const float4 q2 = ws.par[slot].q2;
         // back to the reference's conic: A = A2 / (-0.5 log2 e), B = B2 / (-log2 e), C = C2 / (-0.5 log2 e)
         const float cA = q0.z * (-2.0f / kLog2e), cB = q0.w * (-1.0f / kLog2e), cC = q1.x * (-2.0f / kLog2e);
-        const float dmx = cA * mx1 + cB * my1;
-        const float dmy = cB * mx1 + cC * my1;
-        const float dopacity = proper_aa ? dop : op * (1.0f - op) * dop;
+        const float dmx = cA * s_mx1 + cB * s_my1;
+        const float dmy = cB * s_mx1 + cC * s_my1;
+        const float dopacity = proper_aa ? s_dop : op * (1.0f - op) * s_dop;
         Grad2D* dst = grad2d + __float_as_uint(q2.w);
-        atomicAdd(&dst->g0, make_float4(dmx, dmy, 0.5f * mxx, 0.5f * mxy));
-        atomicAdd(&dst->g1, make_float4(0.5f * myy, dopacity, dcr * color_mask(q1.z), dcg * color_mask(q1.w)));
-        atomicAdd(&dst->g2.x, dcb * color_mask(q2.x));
+        atomicAdd(&dst->g0, make_float4(dmx, dmy, 0.5f * s_mxx, 0.5f * s_mxy));
+        atomicAdd(&dst->g1, make_float4(0.5f * s_myy, dopacity, s_dcr * color_mask(q1.z), s_dcg * color_mask(q1.w)));
+        atomicAdd(&dst->g2.x, s_dcb * color_mask(q2.x));
     }
     __syncwarp();
 }
@@ -189,7 +208,9 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
             sb = a.image[2 * n_pixels + pidx] - Tf * bg.z;
             galpha = Tf * -(gr * bg.x + gg * bg.y + gb * bg.z);
         }
-        ws.g[lane] = make_float4(gr, gg, gb, 0.f);
+        ws.g[0][lane] = gr;
+        ws.g[1][lane] = gg;
+        ws.g[2][lane] = gb;
         __syncwarp();
         int nslots = 0;
 
@@ -200,19 +221,8 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
             const Rec* recs = &ws.recs[slot][0];
             const int count = min(kBatch, n - b * kBatch);
             const int offset = b * kBatch;
-            bool hit = false;
-            if (lane < count) {
-                const float4 q2 = recs[lane].q2;
-                const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
-                hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
-                      sub_y0 < (by >> 16);
-                if (hit) {
-                    const float4 q0 = recs[lane].q0;
-                    const float4 q1 = recs[lane].q1;
-                    hit = rect_contributes2(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, fx0, fy0, (float)(kSubW - 1),
-                                            (float)(kSubH - 1), __log2f(q1.y * kMinAlphaRcp));
-                }
-            }
+            // sub-tile culling was done once at gather time (binning.cu): bit `sub` of the record's mask
+            const bool hit = lane < count && ((__float_as_uint(recs[lane].q2.y) >> sub) & 1u) != 0u;
             uint32_t pending = __ballot_sync(0xffffffffu, hit);
             // branch-free body: alpha_eff = 0 leaves T and the colour-after terms untouched
             while (pending) {
@@ -237,7 +247,8 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                                         fmaf(fmaf(-sg, rcp, Tk * q1.w), gg, fmaf(fmaf(-sb, rcp, Tk * c_b), gb, galpha * rcp)));
                 const float u = c ? gauss * dlda : 0.0f;
                 if (__any_sync(0xffffffffu, c)) {
-                    ws.uw[nslots][lane] = make_float2(u, w);
+                    ws.u[nslots][lane] = u;
+                    ws.w[nslots][lane] = w;
                     if (lane < 3)
                         reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[jj])[lane];
                     if (++nslots == kSlots) {

@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
         const uint32_t pix_x = sub_x0 + (uint32_t)(lane & 7), pix_y = sub_y0 + (uint32_t)(lane >> 3);
         const bool inside = pix_x < (uint32_t)cam.img_w && pix_y < (uint32_t)cam.img_h;
         const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
-        const float fx0 = (float)sub_x0, fy0 = (float)sub_y0;
         float cr = 0.f, cg = 0.f, cb = 0.f, T = 1.f;
         uint32_t n_last = 0;
         bool done = !inside;
@@ -108,20 +107,8 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                 const Rec* recs = &R.recs[slot][0];
                 const int count = min(kBatch, n - b * kBatch);
                 const int offset = b * kBatch;
-                bool hit = false;
-                if (lane < count) {
-                    const float4 q2 = recs[lane].q2;
-                    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
-                    // strict bounding-box / sub-tile overlap (kernels_forward.cuh:445-451)
-                    hit = (bx & 0xffffu) < sub_x0 + kSubW && sub_x0 < (bx >> 16) && (by & 0xffffu) < sub_y0 + kSubH &&
-                          sub_y0 < (by >> 16);
-                    if (hit) {
-                        const float4 q0 = recs[lane].q0;
-                        const float4 q1 = recs[lane].q1;
-                        hit = rect_contributes2(q0.x - 0.5f, q0.y - 0.5f, q0.z, q0.w, q1.x, fx0, fy0, (float)(kSubW - 1),
-                                                (float)(kSubH - 1), __log2f(q1.y * kMinAlphaRcp));
-                    }
-                }
+                // sub-tile culling was done once at gather time (binning.cu): bit `sub` of the record's mask
+                const bool hit = lane < count && ((__float_as_uint(recs[lane].q2.y) >> sub) & 1u) != 0u;
                 uint32_t pending = __ballot_sync(0xffffffffu, hit);
                 while (pending) {
                     const int jj = __ffs((int)pending) - 1;

@@ -219,7 +219,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
                                        &in_alt, stream),
                 "tile sort");
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
-                                               tl.ranges, n_instances, stream),
+                                               tl.ranges, n_instances, cam.grid_w, stream),
                 "ranges_and_gather");
     }
     BlendFwdArgs a{};

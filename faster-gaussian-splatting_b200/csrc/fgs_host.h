@@ -59,7 +59,8 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
 // instance order (tile-contiguous, so the blend kernels can bulk-copy them)
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
-                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, cudaStream_t stream);
+                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, int grid_w,
+                                     cudaStream_t stream);
 
 struct BlendFwdArgs {
     const Rec* inst_recs;
