@@ -104,6 +104,7 @@ def algorithmic_bytes(N, V, I, P, T, S=45):
         'adam_step': 1652 * N,
     }
     st['iteration'] = 1940 * N + (408 + 12 * S) * V + 28 * I + 52 * P + 16 * T
+    st['iteration_fused'] = 1468 * N + (352 + 8 * S) * V + 28 * I + 52 * P + 16 * T
     return st
 
 
@@ -160,10 +161,15 @@ def run_gpu(args, impl):
     def view_of(it):  # rank r trains view (it * world + r) of the 8-view ring
         return (it * world + rank) % N_VIEWS
 
-    def step_resident(it):
-        k = view_of(it)
-        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st_dev[k]))
-        loss = (img - gt_dev[k]).abs().mean()
+    use_fused = (impl == 'mine') and dist is None and not args.unfused
+
+    def train_view(st, gt, fused):
+        rs = be.RasterizerSettings(*st)
+        if fused:  # backward applies the Adam update in the same kernel; opt.step() is then a no-op
+            img = be.diff_rasterize_fused(*params, empty, rs, opt)
+        else:
+            img = be.diff_rasterize(*params, empty, rs)
+        loss = (img - gt).abs().mean()
         loss.backward()
         if dist is not None:
             for p in params:
@@ -172,20 +178,42 @@ def run_gpu(args, impl):
         opt.zero_grad()
         return loss
 
-    def step_e2e(it):  # host buffers in, loss out: H2D of the view's target + camera, D2H of the loss
+    def step_resident(it, fused=None):
         k = view_of(it)
-        gt = gt_pin[k].to(dev, non_blocking=True)
-        w2c = w2c_pin[k].to(dev, non_blocking=True)
-        pos = pos_pin[k].to(dev, non_blocking=True)
-        st = (w2c, pos) + st_dev[k][2:]
-        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st))
-        loss = (img - gt).abs().mean()
-        loss.backward()
-        if dist is not None:
-            for p in params:
-                dist.all_reduce(p.grad)
-        opt.step()
-        opt.zero_grad()
+        return train_view(st_dev[k], gt_dev[k], use_fused if fused is None else fused)
+
+    # end to end: host buffers in, loss out.  The view's target image and camera are copied from pinned
+    # host memory every step (double-buffered on a copy stream so the transfer overlaps the previous
+    # step's kernels -- an input pipeline, as in any trainer), the loss is read back every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [{'gt': torch.empty_like(gt_dev[0]), 'w2c': torch.empty(4, 4, device=dev), 'pos': torch.empty(3, device=dev),
+             'ready': torch.cuda.Event(), 'free': torch.cuda.Event()} for _ in range(2)]
+
+    def prefetch(it):
+        b = bufs[it % 2]
+        k = view_of(it)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b['free'])
+            b['gt'].copy_(gt_pin[k], non_blocking=True)
+            b['w2c'].copy_(w2c_pin[k], non_blocking=True)
+            b['pos'].copy_(pos_pin[k], non_blocking=True)
+            b['ready'].record(copy_stream)
+
+    e2e_state = {'primed': -1}
+
+    def step_e2e(it, fused=None):
+        if e2e_state['primed'] < it:
+            for b in bufs:
+                b['free'].record(torch.cuda.current_stream())
+            prefetch(it)
+        prefetch(it + 1)
+        e2e_state['primed'] = it + 1
+        b = bufs[it % 2]
+        k = view_of(it)
+        torch.cuda.current_stream().wait_event(b['ready'])
+        st = (b['w2c'], b['pos']) + st_dev[k][2:]
+        loss = train_view(st, b['gt'], use_fused if fused is None else fused)
+        b['free'].record(torch.cuda.current_stream())
         return float(loss.item())
 
     def timed(fn, steps, warmup, sampler=None):
@@ -214,6 +242,14 @@ def run_gpu(args, impl):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, clocks = timed(step_resident, steps, warmup, sampler)
     ms_e2e, _ = timed(step_e2e, steps, 3)
+    extra = {}
+    if use_fused:  # also report the strict drop-in path: diff_rasterize backward + separate FusedAdam.step
+        ms_u, _ = timed(lambda it: step_resident(it, fused=False), steps, 3)
+        e2e_state['primed'] = -1
+        ms_ue, _ = timed(lambda it: step_e2e(it, fused=False), steps, 3)
+        extra['dropin_unfused'] = {'value': round(world * 1000.0 * steps / ms_u, 3), 'ms_per_step': round(ms_u / steps, 4),
+                                   'e2e': round(world * 1000.0 * steps / ms_ue, 3), 'unit': 'iters/s',
+                                   'note': 'diff_rasterize + FusedAdam.step, the API the reference Trainer.py calls'}
     ms_step = ms_total / steps
     value = world * 1000.0 / ms_step
     e2e_value = world * 1000.0 / (ms_e2e / steps)
@@ -226,17 +262,20 @@ def run_gpu(args, impl):
                                'fwd + L1 + bwd + FusedAdam.step per view',
                    'n_gaussians': N_GAUSSIANS, 'width': WIDTH, 'height': HEIGHT, 'views_per_step': world,
                    'parallelism': f'view-dp{world}' if world > 1 else 'single',
+                   'optimizer_path': ('fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' if use_fused
+                                      else 'backward, then FusedAdam.step'),
                    'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
         'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
                 'h2d_bytes_per_step': 3 * WIDTH * HEIGHT * 4 + 64 + 12, 'd2h_bytes_per_step': 4},
         'clocks': clocks,
     }
+    out.update(extra)
     if impl == 'reference':
         out['impl'] = 'reference'
         out['cpu_baseline'] = None
         out['config']['reference'] = 'unmodified FasterGSCudaBackend (baseline/_ref) CUDA path on the same GPU'
     else:
-        out.update(profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank))
+        out.update(profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use_fused))
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline()
     if dist is not None:
@@ -244,7 +283,7 @@ def run_gpu(args, impl):
     return out if rank == 0 else None
 
 
-def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank):
+def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use_fused=False):
     """Per-kernel CUDA-event timing of a few extra (untimed) iterations -> roofline of the dominant
     kernel, launch count, scene statistics."""
     from fgs_b200 import _capi
@@ -253,7 +292,8 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank):
     per = {}
     launches = 0
     for it in range(reps):
-        img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st_dev[it % N_VIEWS]))
+        rs = be.RasterizerSettings(*st_dev[it % N_VIEWS])
+        img = be.diff_rasterize_fused(*params, empty, rs, opt) if use_fused else be.diff_rasterize(*params, empty, rs)
         loss = (img - gt_dev[it % N_VIEWS]).abs().mean()
         loss.backward()
         opt.step()
@@ -284,7 +324,8 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank):
     dom_bytes = alg.get(dom, 0)
     dom_ms = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    iter_achieved = alg['iteration'] / (ms_step * 1e-3) / 1e9
+    iter_bytes = alg['iteration_fused'] if use_fused else alg['iteration']
+    iter_achieved = iter_bytes / (ms_step * 1e-3) / 1e9
     kernel_ms_sum = sum(kern.values())
     return {
         'gpu_launches': launches,
@@ -293,7 +334,7 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank):
                      'algorithmic_bytes_per_launch': dom_bytes, 'ms_per_launch': round(dom_ms, 4),
                      'share_of_step': round(dom_ms / ms_step, 3),
                      'note': 'blend kernels are FP32-issue bound, not HBM bound; see DESIGN.md'},
-        'roofline_iteration': {'algorithmic_bytes': alg['iteration'], 'achieved': round(iter_achieved, 2),
+        'roofline_iteration': {'algorithmic_bytes': iter_bytes, 'achieved': round(iter_achieved, 2),
                                'peak': peak, 'unit': 'GB/s', 'frac': round(iter_achieved / peak, 4)},
         'kernels_ms': {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
         'kernels_ms_sum': round(kernel_ms_sum, 4),
@@ -360,6 +401,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='mine', choices=['mine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--unfused', action='store_true', help='headline on the drop-in path (backward, then FusedAdam.step)')
     args = ap.parse_args()
     if not torch.cuda.is_available():
         if args.impl == 'reference':

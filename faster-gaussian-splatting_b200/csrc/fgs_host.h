@@ -19,7 +19,10 @@ enum : int {
 };
 
 constexpr int kSortBlock = 256;
-constexpr int kSortItems = 16;
+#ifndef FGS_SORT_ITEMS
+#define FGS_SORT_ITEMS 8
+#endif
+constexpr int kSortItems = FGS_SORT_ITEMS;
 constexpr int kSortTile = kSortBlock * kSortItems;  // keys per block per pass
 constexpr int kRadixMax = 256;
 
