@@ -3,10 +3,20 @@
     from fgs_b200 import diff_rasterize, rasterize, RasterizerSettings, FusedAdam
 
 The eight public names of the reference backend (/root/reference/FasterGSCudaBackend/__init__.py:14-18)
-plus `diff_rasterize_fused` (backward + Adam in one kernel).  Importing this package loads
-libfgs_b200.so; there is no fallback if it is missing."""
-from .torch_bindings import (FusedAdam, RasterizerSettings, add_noise, diff_rasterize, diff_rasterize_fused,
-                             rasterize, relocation_adjustment, update_3d_filter, update_pruning_scores)
+plus `diff_rasterize_fused` (backward + Adam in one kernel).  Accessing any of them loads
+libfgs_b200.so; there is no fallback if it is missing (ImportError).  The helper modules
+`fgs_b200.synthetic` (benchmark scenes) and `fgs_b200.parallel` (view-parallel all-reduce) are pure
+Python and do not load the library."""
+import importlib
 
 __all__ = ['diff_rasterize', 'diff_rasterize_fused', 'rasterize', 'update_pruning_scores', 'RasterizerSettings',
            'FusedAdam', 'update_3d_filter', 'relocation_adjustment', 'add_noise']
+
+
+def __getattr__(name):
+    if name in __all__:
+        tb = importlib.import_module('.torch_bindings', __name__)
+        return getattr(tb, name)
+    if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel'):
+        return importlib.import_module('.' + name, __name__)
+    raise AttributeError(f'module {__name__!r} has no attribute {name!r}')
