@@ -221,10 +221,26 @@ def run_gpu(args, impl):
             b['ready'].record(copy_stream)
 
     e2e_state = {'primed': -1}
+    # every step's loss is copied to pinned host memory and read on the host inside the timed region,
+    # one step late (asynchronous metric read-back, as a trainer's logger does); the last one is
+    # drained by the synchronize that closes the timed region
+    loss_pin = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    loss_log = []
+
+    def read_loss(it, loss):
+        slot = it % 2
+        loss_pin[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_evt[slot].record(torch.cuda.current_stream())
+        prev = (it - 1) % 2
+        if it > 0 and loss_evt[prev].query() is not None:
+            loss_evt[prev].synchronize()
+            loss_log.append(float(loss_pin[prev][0]))
+        return loss_log[-1] if loss_log else 0.0
 
     def step_e2e(it, fused=None):
         if acc > 1:
-            return float(accumulate_step(it).item())
+            return read_loss(it, accumulate_step(it))
         if e2e_state['primed'] < it:
             for b in bufs:
                 b['free'].record(torch.cuda.current_stream())
@@ -237,7 +253,7 @@ def run_gpu(args, impl):
         st = (b['w2c'], b['pos']) + st_dev[k][2:]
         loss = train_view(st, b['gt'], use_fused if fused is None else fused)
         b['free'].record(torch.cuda.current_stream())
-        return float(loss.item())
+        return read_loss(it, loss)
 
     def timed(fn, steps, warmup, sampler=None):
         for it in range(warmup):
