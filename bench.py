@@ -382,45 +382,54 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use
 
 
 def cpu_baseline():
-    """Oracle port timed on the host cores on a bounded sample of the SAME workload: full-size
-    preprocess (1M Gaussians) and full-size Adam, blend forward+backward on a 128x96 pixel window
-    of the 1080p view scaled by the pixel ratio."""
+    """Oracle port timed on the host cores on a BOUNDED, shape-preserving sample of the workload.
+
+    The benchmark scene scales Gaussian size with sqrt(1e6 / N) (fgs_b200/synthetic.py), so
+    N/16 Gaussians rendered at 480x270 (1/16 of the pixels) have the same footprint in pixels, the
+    same instances per Gaussian and the same depth complexity per pixel as the full 1M / 1080p
+    workload: per-Gaussian work and per-pixel work are both 1/16.  Measured: preprocess (+SH) forward
+    and backward on the 62.5k Gaussians, blend forward+backward on a 96x72 window of the 480x270 image,
+    Adam on the full 59 M parameters.  Estimate = 16 * preprocess + 16 * (480*270)/(96*72) * blend + Adam."""
     from oracle import torch_oracle as O
     from fgs_b200 import synthetic as syn
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sc = syn.make_scene(N_GAUSSIANS, 0)
-    cam = syn.make_camera(0, WIDTH, HEIGHT)
-    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), SH_BASES, WIDTH, HEIGHT, cam.focal_x, cam.focal_y,
+    shrink = 16
+    n, w, h = N_GAUSSIANS // shrink, WIDTH // 4, HEIGHT // 4
+    sc = syn.make_scene(n, 0)
+    cam = syn.make_camera(0, w, h)
+    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), SH_BASES, w, h, cam.focal_x, cam.focal_y,
                    cam.center_x, cam.center_y, cam.near_plane, cam.far_plane, False)
-    win = (896, 492, 1024, 588)  # 8 x 8 tiles around the image centre
+    win = (w // 2 - 48, h // 2 - 36, w // 2 + 48, h // 2 + 36)
+    t_start = time.perf_counter()
+    # (a) preprocess forward + backward alone
     leaves = [p.clone().requires_grad_(True) for p in sc]
     t0 = time.perf_counter()
+    pr = O.preprocess(*leaves, s)
+    (pr.mean2d.sum() + pr.conic.sum() + pr.opacity.sum() + pr.color.sum()).backward()
+    t_pre = time.perf_counter() - t0
+    # (b) windowed render forward + backward (contains one more preprocess pass)
+    leaves = [p.clone().requires_grad_(True) for p in sc]
+    gt = syn.make_target(w, h)[:, win[1]:win[3], win[0]:win[2]]
+    t0 = time.perf_counter()
     out = O.render(*leaves, s, window=win)
-    t1 = time.perf_counter()
-    gt = syn.make_target(WIDTH, HEIGHT)[:, win[1]:win[3], win[0]:win[2]]
     (out.image - gt).abs().mean().backward()
-    t2 = time.perf_counter()
-    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in leaves]
+    t_all = time.perf_counter() - t0
+    t_blend = max(t_all - t_pre, 0.0)
+    # (c) Adam on the full-size parameter set
+    full = [torch.zeros(N_GAUSSIANS, k) for k in (3, 3, 4, 1, 3, 45)]
+    t0 = time.perf_counter()
     with torch.no_grad():
-        for p, (m, v), lr in zip(leaves, state, LRS):
-            O.adam_step(p, p.grad if p.grad is not None else torch.zeros_like(p), m, v, 1, lr)
-    t3 = time.perf_counter()
-    # split forward time into the full-size part (preprocess) and the window part (blend)
-    tp0 = time.perf_counter()
-    with torch.no_grad():
-        O.preprocess(*sc, s)
-    t_pre = time.perf_counter() - tp0
-    ratio = (WIDTH * HEIGHT) / ((win[2] - win[0]) * (win[3] - win[1]))
-    t_blend_fwd = max(t1 - t0 - t_pre, 0.0)
-    # backward of the full-size preprocess is inside (t2 - t1); attribute the same fraction as forward
-    t_bwd = t2 - t1
-    frac_pre = t_pre / max(t1 - t0, 1e-9)
-    est = t_pre + t_blend_fwd * ratio + t_bwd * frac_pre + t_bwd * (1 - frac_pre) * ratio + (t3 - t2)
+        for p, lr in zip(full, LRS):
+            O.adam_step(p, torch.ones_like(p), torch.zeros_like(p), torch.zeros_like(p), 1, lr)
+    t_adam = time.perf_counter() - t0
+    ratio = (w * h) / ((win[2] - win[0]) * (win[3] - win[1]))
+    est = shrink * t_pre + shrink * ratio * t_blend + t_adam
     return {'value': round(1.0 / est, 6), 'unit': 'iters/s', 'cores': cores, 'kind': 'port',
-            'sample': f'oracle/torch_oracle.py fp32: full 1M-Gaussian preprocess+Adam, blend fwd+bwd on the '
-                      f'{win[2]-win[0]}x{win[3]-win[1]} px centre window scaled x{ratio:.0f} to 1920x1080; '
-                      f'measured {t3 - t0 + t_pre:.1f} s of CPU work, estimated {est:.0f} s per full iteration'}
+            'sample': f'oracle/torch_oracle.py fp32, shape-preserving 1/{shrink} sample: {n} Gaussians at {w}x{h}; '
+                      f'preprocess fwd+bwd {t_pre:.1f} s (x{shrink}), blend fwd+bwd on a 96x72 window {t_blend:.1f} s '
+                      f'(x{shrink * ratio:.0f}), Adam on 59M params {t_adam:.1f} s; measured '
+                      f'{time.perf_counter() - t_start:.0f} s of CPU work, estimated {est:.0f} s per full iteration'}
 
 
 def run_cpu_port(args, reason):

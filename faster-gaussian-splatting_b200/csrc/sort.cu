@@ -19,6 +19,10 @@ constexpr uint32_t kFlagLocal = 1u << 30;
 constexpr uint32_t kFlagIncl = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
 constexpr int kSortWarps = kSortBlock / 32;
+#ifndef FGS_SORT_WINDOW
+#define FGS_SORT_WINDOW 8
+#endif
+constexpr int kLookWindow = FGS_SORT_WINDOW;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
@@ -96,8 +100,11 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const KeyT* __re
     }
 }
 
+#ifndef FGS_SORT_MINBLOCKS
+#define FGS_SORT_MINBLOCKS 3
+#endif
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortBlock) onesweep_kernel(
+__global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ hist,
     uint32_t* lookback, uint32_t* ticket, const int shift, const int nbits) {
@@ -107,11 +114,13 @@ __global__ void __launch_bounds__(kSortBlock) onesweep_kernel(
     __shared__ uint32_t s_base[kRadixMax];
     __shared__ uint32_t s_lstart[kRadixMax];
     __shared__ uint32_t s_tmp[kSortWarps + 1];
+    __shared__ uint32_t s_cnt[kRadixMax];
     __shared__ uint32_t s_bid;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
     for (int i = tid; i < kSortWarps * kRadixMax; i += kSortBlock) (&s_warp_hist[0][0])[i] = 0;
+    s_cnt[tid] = 0;
     __syncthreads();
     const uint32_t bid = s_bid;
     const uint32_t n = *n_dev;
@@ -130,6 +139,15 @@ __global__ void __launch_bounds__(kSortBlock) onesweep_kernel(
         const uint32_t idx = warp_base + i * 32u + lane;
         key[i] = idx < n ? (uint32_t)keys_in[idx] : 0xffffffffu;
     }
+    // Early publication: a cheap shared-memory histogram of the block's digits goes out before the
+    // (much longer) ranking, so that by the time successors look back the chain of partial counts is
+    // already complete and only the inclusive wave has to propagate.
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i)
+        if (warp_base + i * 32u + lane < n) atomicAdd(&s_cnt[(key[i] >> shift) & dmask], 1u);
+    __syncthreads();
+    if ((uint32_t)tid < radix)
+        st_volatile_u32(lookback + (size_t)bid * kRadixMax + tid, s_cnt[tid] | (bid == 0 ? kFlagIncl : kFlagLocal));
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const bool valid = warp_base + i * 32u + lane < n;
@@ -154,24 +172,32 @@ __global__ void __launch_bounds__(kSortBlock) onesweep_kernel(
             cnt += t;
         }
     }
+    // Windowed decoupled look-back: kLookWindow predecessors are read with independent loads per
+    // step (one L2 latency per window instead of one per predecessor), then consumed in order until
+    // the first inclusive entry; an entry that is not published yet restarts the window there.
     uint32_t prefix = 0;
-    if (d < radix) {
-        uint32_t* mine = lookback + (size_t)bid * kRadixMax + d;
-        if (bid == 0) {
-            st_volatile_u32(mine, cnt | kFlagIncl);
-        } else {
-            st_volatile_u32(mine, cnt | kFlagLocal);
-            for (int j = (int)bid - 1; j >= 0; --j) {
-                const uint32_t* theirs = lookback + (size_t)j * kRadixMax + d;
-                uint32_t v;
-                do {
-                    v = ld_volatile_u32(theirs);
-                } while ((v >> 30) == 0u);
-                prefix += v & kValueMask;
-                if (v & kFlagIncl) break;
+    if (d < radix && bid > 0) {
+        int j = (int)bid - 1;
+        bool found = false;
+        while (!found) {
+            uint32_t v[kLookWindow];
+#pragma unroll
+            for (int w = 0; w < kLookWindow; ++w)
+                v[w] = j - w >= 0 ? ld_volatile_u32(lookback + (size_t)(j - w) * kRadixMax + d) : kFlagIncl;
+            int used = 0;
+#pragma unroll
+            for (int w = 0; w < kLookWindow; ++w) {
+                if (!found && used == w) {
+                    if ((v[w] >> 30) != 0u) {
+                        prefix += v[w] & kValueMask;
+                        found = (v[w] & kFlagIncl) != 0u;
+                        used = w + 1;
+                    }
+                }
             }
-            st_volatile_u32(mine, ((prefix + cnt) & kValueMask) | kFlagIncl);
+            j -= used;
         }
+        st_volatile_u32(lookback + (size_t)bid * kRadixMax + d, ((prefix + cnt) & kValueMask) | kFlagIncl);
     }
     const uint32_t g = d < radix ? hist[d] : 0u;
     const uint32_t gex = block_excl_scan_256(g, s_tmp, nullptr);
