@@ -280,7 +280,7 @@ def run_gpu(args, impl):
     steps, warmup = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, clocks = timed(step_resident, steps, warmup, sampler)
-    ms_e2e, _ = timed(step_e2e, steps, 3)
+    ms_e2e, _ = timed(step_e2e, steps, max(warmup, 10))
     extra = {}
     if use_fused:  # also report the strict drop-in path: diff_rasterize backward + separate FusedAdam.step
         ms_u, _ = timed(lambda it: step_resident(it, fused=False), steps, 3)

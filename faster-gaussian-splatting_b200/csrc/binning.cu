@@ -14,12 +14,11 @@ namespace fgs {
 namespace {
 
 constexpr int kInstBlock = 256;
-constexpr int kSeqTiles = 16;
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     const uint32_t* __restrict__ sorted_idx, const uint32_t* __restrict__ offsets, const Rec* __restrict__ recs,
-    KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const uint32_t* __restrict__ n_vis_dev,
+    const uint32_t* __restrict__ tile_mask, KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const uint32_t* __restrict__ n_vis_dev,
     const int grid_w) {
     const uint32_t n_vis = *n_vis_dev;
     const uint32_t i = blockIdx.x * kInstBlock + threadIdx.x;
@@ -40,17 +39,19 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     const float tau = __log2f(q1.y * kMinAlphaRcp);  // base-2 domain, same expression as preprocess
     uint32_t wr = active ? __ldg(offsets + i) : 0u;
 
-    if (cand <= (uint32_t)kSeqTiles) {
-        for (uint32_t c = 0; c < cand; ++c) {
+    if (cand > 0 && cand <= 32u) {
+        // rectangles of up to 32 tiles: preprocess kept the result of the exact tile test as a bit mask
+        uint32_t m = __ldg(tile_mask + prim);
+        while (m) {
+            const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
             const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
-            if (tile_contributes2(msx, msy, A, B, C, tx, ty, tau)) {
-                inst_keys[wr] = (KeyT)(ty * (uint32_t)grid_w + tx);
-                inst_vals[wr] = prim;
-                ++wr;
-            }
+            inst_keys[wr] = (KeyT)(ty * (uint32_t)grid_w + tx);
+            inst_vals[wr] = prim;
+            ++wr;
         }
     }
-    uint32_t big = __ballot_sync(0xffffffffu, cand > (uint32_t)kSeqTiles);
+    uint32_t big = __ballot_sync(0xffffffffu, cand > 32u);
     while (big) {
         const int src = __ffs((int)big) - 1;
         big &= big - 1;
@@ -130,16 +131,16 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
 
 template <typename KeyT>
 cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
-                                    KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
+                                    const uint32_t* tile_mask, KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
                                     int grid_w, cudaStream_t stream) {
     if (n_max <= 0) return cudaSuccess;
     create_instances_kernel<KeyT><<<div_up(n_max, kInstBlock), kInstBlock, 0, stream>>>(
-        sorted_idx, offsets, recs, inst_keys, inst_vals, n_vis_dev, grid_w);
+        sorted_idx, offsets, recs, tile_mask, inst_keys, inst_vals, n_vis_dev, grid_w);
     return cudaGetLastError();
 }
-template cudaError_t launch_create_instances<uint16_t>(const uint32_t*, const uint32_t*, const Rec*, uint16_t*,
+template cudaError_t launch_create_instances<uint16_t>(const uint32_t*, const uint32_t*, const Rec*, const uint32_t*, uint16_t*,
                                                        uint32_t*, const uint32_t*, int, int, cudaStream_t);
-template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, uint32_t*,
+template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, const uint32_t*, uint32_t*,
                                                        uint32_t*, const uint32_t*, int, int, cudaStream_t);
 
 template <typename KeyT>

@@ -98,6 +98,7 @@ struct PrimitiveLayout {
     uint32_t* counters;
     Rec* recs;
     uint32_t* n_touched;
+    uint32_t* tile_mask;
     uint32_t* keys[2];
     uint32_t* idx[2];
     uint32_t* offsets;
@@ -111,6 +112,7 @@ struct PrimitiveLayout {
         counters = c.take<uint32_t>(kCtrCount);
         recs = c.take<Rec>(nn);
         n_touched = c.take<uint32_t>(nn);
+        tile_mask = c.take<uint32_t>(nn);
         keys[0] = c.take<uint32_t>(nn);
         keys[1] = c.take<uint32_t>(nn);
         idx[0] = c.take<uint32_t>(nn);
@@ -210,7 +212,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
     InstanceLayout<KeyT> il(blob, n_instances, end_bit);
     if (n_instances > 0) {
-        FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, il.keys[0], il.vals[0],
+        FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, pl.tile_mask, il.keys[0], il.vals[0],
                                               pl.counters + kCtrVisible, n_visible, cam.grid_w, stream),
                 "create_instances");
         bool in_alt = false;
@@ -265,7 +267,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // empty tiles keep the range (0, 0); tile_max_n is written for every item by the blend forward
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
 
-    FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.keys[0],
+    FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_mask, pl.keys[0],
                               pl.idx[0], pl.counters, n, cam, !training, stream),
             "preprocess");
     Readback& rb = readback();

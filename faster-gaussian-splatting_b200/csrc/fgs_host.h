@@ -32,7 +32,8 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 // ---- launchers ---------------------------------------------------------------------------------------
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
-                              uint32_t* n_touched, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
+                              uint32_t* n_touched, uint32_t* tile_mask, uint32_t* depth_keys, uint32_t* vis_indices,
+                              uint32_t* counters,
                               int n, const Cam& cam, bool inference, cudaStream_t stream);
 
 // LSD radix sort of (key, value) pairs, onesweep style (one read + one write of the data per pass).
@@ -55,6 +56,7 @@ size_t offsets_scan_lookback_words(int n_max);
 
 template <typename KeyT>
 cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
+                                    const uint32_t* tile_mask,
                                     KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
                                     int grid_w, cudaStream_t stream);
 

@@ -79,7 +79,8 @@ template <bool kInference>
 __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ sh0, const float* __restrict__ sh_rest,
-    Rec* __restrict__ recs, uint32_t* __restrict__ n_touched_out, uint32_t* __restrict__ depth_keys,
+    Rec* __restrict__ recs, uint32_t* __restrict__ n_touched_out, uint32_t* __restrict__ tile_mask_out,
+    uint32_t* __restrict__ depth_keys,
     uint32_t* __restrict__ vis_indices, uint32_t* __restrict__ counters, const int n, const Cam cam) {
     __shared__ __align__(16) float s_means[kPreBlock * 3];
     __shared__ __align__(16) float s_scales[kPreBlock * 3];
@@ -211,11 +212,13 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     // P8: exact number of touched tiles
     const float msx = m2x - 0.5f, msy = m2y - 0.5f;
     uint32_t n_touched = 0;
+    uint32_t tile_mask = 0;  // bit c: candidate tile c of the rectangle is touched (kept for rectangles of <= 32 tiles)
     if (active && cand <= (uint32_t)kSeqTiles) {
         for (uint32_t c = 0; c < cand; ++c) {
             const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
-            n_touched += tile_contributes2(msx, msy, A2, B2, C2, tx, ty, tau2) ? 1u : 0u;
+            tile_mask |= (tile_contributes2(msx, msy, A2, B2, C2, tx, ty, tau2) ? 1u : 0u) << c;
         }
+        n_touched = __popc(tile_mask);
     }
     uint32_t big = __ballot_sync(0xffffffffu, active && cand > (uint32_t)kSeqTiles);
     while (big) {
@@ -226,14 +229,22 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
         const float bC = __shfl_sync(0xffffffffu, C2, src), btau = __shfl_sync(0xffffffffu, tau2, src);
         const uint32_t bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
         const uint32_t btw = __shfl_sync(0xffffffffu, tw, src), bcand = __shfl_sync(0xffffffffu, cand, src);
-        uint32_t cnt = 0;
-        for (uint32_t c = lane; c < bcand; c += 32)
-            cnt += tile_contributes2(bmx, bmy, bA, bB, bC, bx0 + c % btw, by0 + c / btw, btau) ? 1u : 0u;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == src) n_touched = cnt;
+        uint32_t cnt = 0, first_chunk = 0;
+        for (uint32_t c0 = 0; c0 < bcand; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool ok = c < bcand && tile_contributes2(bmx, bmy, bA, bB, bC, bx0 + c % btw, by0 + c / btw, btau);
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (c0 == 0) first_chunk = m;
+            cnt += __popc(m);
+        }
+        if (lane == src) {
+            n_touched = cnt;
+            tile_mask = first_chunk;
+        }
     }
     const bool visible = active && n_touched > 0;
     if (idx < n) n_touched_out[idx] = visible ? n_touched : 0u;
+    if (visible) tile_mask_out[idx] = tile_mask;
 
     // P9: SH -> RGB for visible Gaussians; the 180-byte rest rows are staged per warp
     const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
@@ -286,18 +297,18 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
 
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
-                              uint32_t* n_touched, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
+                              uint32_t* n_touched, uint32_t* tile_mask, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
                               int n, const Cam& cam, bool inference, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + kPreBlock - 1) / kPreBlock;
     const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
     if (inference)
         preprocess_kernel<true><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
-                                                                     recs, n_touched, depth_keys, vis_indices,
+                                                                     recs, n_touched, tile_mask, depth_keys, vis_indices,
                                                                      counters, n, cam);
     else
         preprocess_kernel<false><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
-                                                                      recs, n_touched, depth_keys, vis_indices,
+                                                                      recs, n_touched, tile_mask, depth_keys, vis_indices,
                                                                       counters, n, cam);
     return cudaGetLastError();
 }

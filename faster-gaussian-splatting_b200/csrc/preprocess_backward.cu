@@ -70,18 +70,35 @@ __device__ __forceinline__ void emit_span(const float* __restrict__ stage, float
     float* mm = m + first_elem;
     float* vv = v + first_elem;
     if (vec && ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(mm) | reinterpret_cast<uintptr_t>(vv)) & 15u) == 0) {
-        for (int i = lane; i < (n_floats >> 2); i += 32) {
-            const float4 g4 = reinterpret_cast<const float4*>(stage)[i];
-            float4 p4 = reinterpret_cast<float4*>(pp)[i];
-            float4 m4 = reinterpret_cast<float4*>(mm)[i];
-            float4 v4 = reinterpret_cast<float4*>(vv)[i];
-            adam_update(g4.x, p4.x, m4.x, v4.x, step_size, beta1, beta2, eps, b2);
-            adam_update(g4.y, p4.y, m4.y, v4.y, step_size, beta1, beta2, eps, b2);
-            adam_update(g4.z, p4.z, m4.z, v4.z, step_size, beta1, beta2, eps, b2);
-            adam_update(g4.w, p4.w, m4.w, v4.w, step_size, beta1, beta2, eps, b2);
-            reinterpret_cast<float4*>(pp)[i] = p4;
-            reinterpret_cast<float4*>(mm)[i] = m4;
-            reinterpret_cast<float4*>(vv)[i] = v4;
+        // kU independent 16-byte loads of p, m and v per lane are issued before any of them is consumed:
+        // the kernel is a pure HBM stream (24 B in, 12 B out per float), latency is hidden by bytes in flight
+        constexpr int kU = 4;
+        const int n4 = n_floats >> 2;
+        for (int i0 = lane; i0 < n4; i0 += 32 * kU) {
+            float4 p4[kU], m4[kU], v4[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < n4) {
+                    p4[u] = reinterpret_cast<const float4*>(pp)[i];
+                    m4[u] = reinterpret_cast<const float4*>(mm)[i];
+                    v4[u] = reinterpret_cast<const float4*>(vv)[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + 32 * u;
+                if (i < n4) {
+                    const float4 g4 = reinterpret_cast<const float4*>(stage)[i];
+                    adam_update(g4.x, p4[u].x, m4[u].x, v4[u].x, step_size, beta1, beta2, eps, b2);
+                    adam_update(g4.y, p4[u].y, m4[u].y, v4[u].y, step_size, beta1, beta2, eps, b2);
+                    adam_update(g4.z, p4[u].z, m4[u].z, v4[u].z, step_size, beta1, beta2, eps, b2);
+                    adam_update(g4.w, p4[u].w, m4[u].w, v4[u].w, step_size, beta1, beta2, eps, b2);
+                    reinterpret_cast<float4*>(pp)[i] = p4[u];
+                    reinterpret_cast<float4*>(mm)[i] = m4[u];
+                    reinterpret_cast<float4*>(vv)[i] = v4[u];
+                }
+            }
         }
     } else {
         for (int i = lane; i < n_floats; i += 32) {
