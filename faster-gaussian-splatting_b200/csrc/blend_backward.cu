@@ -192,21 +192,22 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
         };
         while (issued < nb && issued < kRing) issue();
 
-        // per-pixel state: colour still to come behind the current Gaussian ("colour after"),
-        // dL/d(pixel colour), T_final * -(bg . g), running transmittance
-        float sr = 0.f, sg = 0.f, sb = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, galpha = 0.f, T = 1.f;
-        uint32_t n_proc = 0;
+        // per-pixel state: dL/d(pixel colour) g, T_final * -(bg . g), the running transmittance T, and
+        // sigma = (colour still to come behind the current Gaussian) . g.  The reference carries the
+        // "colour after" vector and dots it with g for every Gaussian (kernels_backward.cuh:429-436); the
+        // dot product is linear, so the scalar is carried instead: sigma -= w * (c . g).
+        float gr = 0.f, gg = 0.f, gb = 0.f, galpha = 0.f, sigma = 0.f, T = 1.f;
+        int n_rel = 0;  // this pixel's last contributor, relative to the current batch
         if (inside) {
             const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
-            n_proc = a.n_processed[pidx];
+            n_rel = (int)a.n_processed[pidx];
             const float Tf = a.final_T[pidx];
             gr = a.grad_image[pidx];
             gg = a.grad_image[n_pixels + pidx];
             gb = a.grad_image[2 * n_pixels + pidx];
-            sr = a.image[pidx] - Tf * bg.x;
-            sg = a.image[n_pixels + pidx] - Tf * bg.y;
-            sb = a.image[2 * n_pixels + pidx] - Tf * bg.z;
-            galpha = Tf * -(gr * bg.x + gg * bg.y + gb * bg.z);
+            const float gbg = gr * bg.x + gg * bg.y + gb * bg.z;
+            sigma = a.image[pidx] * gr + a.image[n_pixels + pidx] * gg + a.image[2 * n_pixels + pidx] * gb - Tf * gbg;
+            galpha = -Tf * gbg;
         }
         ws.g[0][lane] = gr;
         ws.g[1][lane] = gg;
@@ -233,18 +234,16 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 const float c_b = recs[jj].q2.x;
                 const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, q0.x - px, q0.y - py), 0.0f));
                 const float alpha = __fmul_rn(q1.y, gauss);
-                const bool c = alpha >= kMinAlpha && (uint32_t)(offset + jj) < n_proc;
+                const bool c = alpha >= kMinAlpha && jj < n_rel;
                 const float ae = c ? alpha : 0.0f;
-                const float Tk = T;
-                const float w = __fmul_rn(Tk, ae);
-                sr = fmaf(-w, q1.z, sr);
-                sg = fmaf(-w, q1.w, sg);
-                sb = fmaf(-w, c_b, sb);
+                const float w = __fmul_rn(T, ae);
+                const float cg = fmaf(c_b, gb, fmaf(q1.w, gg, q1.z * gr));  // c . g
+                sigma = fmaf(-w, cg, sigma);
                 const float oma = __fsub_rn(1.0f, ae);
-                T = __fmul_rn(Tk, oma);
                 const float rcp = __fdividef(1.0f, fmaxf(oma, kOneMinusAlphaEps));
-                const float dlda = fmaf(fmaf(-sr, rcp, Tk * q1.z), gr,
-                                        fmaf(fmaf(-sg, rcp, Tk * q1.w), gg, fmaf(fmaf(-sb, rcp, Tk * c_b), gb, galpha * rcp)));
+                // dL/dalpha = (T c - C_after / (1 - alpha)) . g + galpha / (1 - alpha)
+                const float dlda = fmaf(T, cg, rcp * (galpha - sigma));
+                T = __fmul_rn(T, oma);
                 const float u = c ? gauss * dlda : 0.0f;
                 if (__any_sync(0xffffffffu, c)) {
                     ws.u[nslots][lane] = u;
@@ -258,6 +257,7 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 }
             }
             __syncwarp();
+            n_rel -= kBatch;
             if (issued < nb) issue();  // refill the slot just consumed
         }
         k += (uint32_t)nb;
