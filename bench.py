@@ -37,6 +37,7 @@ sys.path.insert(0, str(ROOT))
 N_GAUSSIANS, WIDTH, HEIGHT, SH_BASES, N_VIEWS = 1_000_000, 1920, 1080, 16, 8
 LRS = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]  # means, scales, rotations, opacities, sh0, sh_rest (Trainer.py:56-66)
 METRIC = 'train_iters_per_sec_1M_gaussians_1080p'
+T_TILES = math.ceil(WIDTH / 16) * math.ceil(HEIGHT / 12)
 
 
 def peak_hbm_gbs():
@@ -338,7 +339,9 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use
         opt.step()
         opt.zero_grad()
         recs = _capi.profile_read()
-        launches = len(recs)
+        # kernels per profiled group: a sort = 1 histogram kernel + one onesweep kernel per 8-bit digit place
+        per_group = {'depth sort': 1 + 4, 'tile sort': 1 + math.ceil(math.ceil(math.log2(max(T_TILES, 2))) / 8)}
+        launches = sum(per_group.get(name, 1) for name, _ in recs)
         for name, ms in recs:
             per.setdefault(name, []).append(ms)
     _capi.profile_enable(False)

@@ -105,11 +105,16 @@ struct PrimitiveLayout {
     uint32_t* hist;
     uint32_t* lookback;
     uint32_t* scan_lookback;
+    size_t zero_bytes;  // counters .. scan_lookback are contiguous: one memset clears them all
     size_t bytes;
     PrimitiveLayout(char* blob, int n) {
         Carver c(blob);
         const size_t nn = (size_t)(n > 0 ? n : 1);
         counters = c.take<uint32_t>(kCtrCount);
+        hist = c.take<uint32_t>(4 * kRadixMax);
+        lookback = c.take<uint32_t>(radix_sort_lookback_words(n, 32));
+        scan_lookback = c.take<uint32_t>(offsets_scan_lookback_words(n));
+        zero_bytes = c.bytes();
         recs = c.take<Rec>(nn);
         n_touched = c.take<uint32_t>(nn);
         tile_mask = c.take<uint32_t>(nn);
@@ -118,9 +123,6 @@ struct PrimitiveLayout {
         idx[0] = c.take<uint32_t>(nn);
         idx[1] = c.take<uint32_t>(nn);
         offsets = c.take<uint32_t>(nn);
-        hist = c.take<uint32_t>(4 * kRadixMax);
-        lookback = c.take<uint32_t>(radix_sort_lookback_words(n, 32));
-        scan_lookback = c.take<uint32_t>(offsets_scan_lookback_words(n));
         bytes = c.bytes();
     }
 };
@@ -218,7 +220,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
         bool in_alt = false;
         FGS_KERNEL(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
                                        n_instances, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
-                                       &in_alt, stream),
+                                       &in_alt, /*zero_scratch=*/true, stream),
                 "tile sort");
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
                                                tl.ranges, n_instances, cam.grid_w, stream),
@@ -263,7 +265,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     if (!prim_blob) return fail_arg("primitive buffer resize callback returned NULL");
     PrimitiveLayout pl(prim_blob, n);
 
-    FGS_TRY(cudaMemsetAsync(pl.counters, 0, sizeof(uint32_t) * kCtrCount, stream), "memset counters");
+    FGS_TRY(cudaMemsetAsync(pl.counters, 0, pl.zero_bytes, stream), "memset counters + sort scratch");
     // empty tiles keep the range (0, 0); tile_max_n is written for every item by the blend forward
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
 
@@ -277,11 +279,12 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // depth order: bits [0, 32) of the positive float depth (sign bit is always 0 after the near cull)
     bool in_alt = false;
     FGS_KERNEL(radix_sort_pairs<uint32_t>(pl.keys[0], pl.keys[1], pl.idx[0], pl.idx[1], pl.counters + kCtrVisible, n, 32,
-                                       pl.hist, pl.lookback, pl.counters + kCtrTicket0, &in_alt, stream),
+                                       pl.hist, pl.lookback, pl.counters + kCtrTicket0, &in_alt, /*zero_scratch=*/false,
+                                       stream),
             "depth sort");
     const uint32_t* sorted_idx = pl.idx[in_alt ? 1 : 0];
     FGS_KERNEL(launch_offsets_scan(sorted_idx, pl.n_touched, pl.offsets, pl.counters + kCtrVisible, n, pl.scan_lookback,
-                                pl.counters + kCtrTicket0 + 4, stream),
+                                pl.counters + kCtrTicket0 + 4, /*zero_scratch=*/false, stream),
             "offsets scan");
 
     FGS_TRY(cudaEventSynchronize(rb.event), "count read-back wait");
@@ -481,7 +484,7 @@ int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint3
     FGS_TRY(cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), st), "memset tickets");
     bool in_alt = false;
     FGS_TRY(radix_sort_pairs<uint32_t>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, hist, lookback, tickets,
-                                       &in_alt, st),
+                                       &in_alt, /*zero_scratch=*/true, st),
             "radix_sort_pairs");
     if (result_in_alt) *result_in_alt = in_alt ? 1 : 0;
     return 0;

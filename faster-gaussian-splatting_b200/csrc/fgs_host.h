@@ -40,18 +40,18 @@ cudaError_t launch_preprocess(const float* means, const float* scales, const flo
 // `n_dev` points at the element count on the device, `n_max` bounds it on the host (grid sizing).
 // Keys are KeyT in {uint16_t, uint32_t}; bits [0, end_bit) are sorted.  `hist` needs
 // passes * 256 uint32, `lookback` needs passes * div_up(n_max, kSortTile) * 256 uint32; both are
-// zeroed inside.  Returns in *result_in_alt whether the sorted data ended in the *_alt buffers.
+// zeroed inside when `zero_scratch` (they must be adjacent: hist first) or by the caller.  Returns in *result_in_alt whether the sorted data ended in the *_alt buffers.
 template <typename KeyT>
 cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
                              int n_max, int end_bit, uint32_t* hist, uint32_t* lookback, uint32_t* tickets,
-                             bool* result_in_alt, cudaStream_t stream);
+                             bool* result_in_alt, bool zero_scratch, cudaStream_t stream);
 size_t radix_sort_lookback_words(int n_max, int end_bit);
 int radix_sort_passes(int end_bit);
 
 // offsets[i] = exclusive prefix sum over i of n_touched[sorted_idx[i]], i < *n_dev
 cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_touched, uint32_t* offsets,
                                 const uint32_t* n_dev, int n_max, uint32_t* lookback, uint32_t* ticket,
-                                cudaStream_t stream);
+                                bool zero_scratch, cudaStream_t stream);
 size_t offsets_scan_lookback_words(int n_max);
 
 template <typename KeyT>

@@ -295,15 +295,22 @@ size_t radix_sort_lookback_words(int n_max, int end_bit) {
 template <typename KeyT>
 cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
                              int n_max, int end_bit, uint32_t* hist, uint32_t* lookback, uint32_t* tickets,
-                             bool* result_in_alt, cudaStream_t stream) {
+                             bool* result_in_alt, bool zero_scratch, cudaStream_t stream) {
     *result_in_alt = false;
     if (n_max <= 0) return cudaSuccess;
     const PassPlan plan = make_plan(end_bit);
     const int nblocks = div_up(n_max, kSortTile);
-    cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * plan.passes * kRadixMax, stream);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * radix_sort_lookback_words(n_max, end_bit), stream);
-    if (e != cudaSuccess) return e;
+    if (zero_scratch) {
+        cudaError_t e;
+        if (lookback == hist + 4 * kRadixMax) {  // adjacent: one memset
+            e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (4 * kRadixMax + radix_sort_lookback_words(n_max, end_bit)), stream);
+        } else {
+            e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * plan.passes * kRadixMax, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * radix_sort_lookback_words(n_max, end_bit), stream);
+        }
+        if (e != cudaSuccess) return e;
+    }
     const int hist_grid = nblocks < 148 * 8 ? nblocks : 148 * 8;
     radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan);
     KeyT* kin = keys;
@@ -326,18 +333,20 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
 }
 
 template cudaError_t radix_sort_pairs<uint16_t>(uint16_t*, uint16_t*, uint32_t*, uint32_t*, const uint32_t*, int, int,
-                                                uint32_t*, uint32_t*, uint32_t*, bool*, cudaStream_t);
+                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, cudaStream_t);
 template cudaError_t radix_sort_pairs<uint32_t>(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, int, int,
-                                                uint32_t*, uint32_t*, uint32_t*, bool*, cudaStream_t);
+                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, cudaStream_t);
 
 size_t offsets_scan_lookback_words(int n_max) { return (size_t)div_up(n_max > 0 ? n_max : 1, kScanTile); }
 
 cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_touched, uint32_t* offsets,
                                 const uint32_t* n_dev, int n_max, uint32_t* lookback, uint32_t* ticket,
-                                cudaStream_t stream) {
+                                bool zero_scratch, cudaStream_t stream) {
     if (n_max <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * offsets_scan_lookback_words(n_max), stream);
-    if (e != cudaSuccess) return e;
+    if (zero_scratch) {
+        cudaError_t e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * offsets_scan_lookback_words(n_max), stream);
+        if (e != cudaSuccess) return e;
+    }
     offsets_scan_kernel<<<div_up(n_max, kScanTile), kSortBlock, 0, stream>>>(sorted_idx, n_touched, offsets, n_dev,
                                                                            lookback, ticket);
     return cudaGetLastError();
