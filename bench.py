@@ -395,7 +395,9 @@ def cpu_baseline():
     Adam on the full 59 M parameters.  Estimate = 16 * preprocess + 16 * (480*270)/(96*72) * blend + Adam."""
     from oracle import torch_oracle as O
     from fgs_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
+    # the oracle is many small vectorised torch ops: beyond ~16 threads the fork/join overhead dominates
+    # (measured: 128 threads are 100x slower than 8 on this workload), so at most 16 host threads are used
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     shrink = 16
     n, w, h = N_GAUSSIANS // shrink, WIDTH // 4, HEIGHT // 4

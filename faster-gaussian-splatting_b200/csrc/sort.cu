@@ -148,15 +148,22 @@ __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kerne
     __syncthreads();
     if ((uint32_t)tid < radix)
         st_volatile_u32(lookback + (size_t)bid * kRadixMax + tid, s_cnt[tid] | (bid == 0 ? kFlagIncl : kFlagLocal));
+    // all MATCH.ANY operations first: they do not depend on the shared-memory counters, so their (long)
+    // latencies overlap instead of serialising with the counter updates below
+    uint32_t peers[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+        const bool valid = warp_base + i * 32u + lane < n;
+        peers[i] = __match_any_sync(0xffffffffu, valid ? (key[i] >> shift) & dmask : 0xffffffffu);
+    }
 #pragma unroll
     for (int i = 0; i < kSortItems; ++i) {
         const bool valid = warp_base + i * 32u + lane < n;
         const uint32_t d = (key[i] >> shift) & dmask;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
         const uint32_t prior = valid ? s_warp_hist[warp][d] : 0u;
-        rank[i] = prior + __popc(peers & lt_mask);
+        rank[i] = prior + __popc(peers[i] & lt_mask);
         __syncwarp();
-        if (valid && lane == __ffs((int)peers) - 1) s_warp_hist[warp][d] = prior + __popc(peers);
+        if (valid && lane == __ffs((int)peers[i]) - 1) s_warp_hist[warp][d] = prior + __popc(peers[i]);
         __syncwarp();
     }
     __syncthreads();

@@ -173,6 +173,30 @@ def test_empty_and_degenerate_inputs(cuda_device):
     assert img3.shape == (3, 29, 37) and torch.isfinite(img3).all()
 
 
+def test_more_than_65536_tiles_uses_32bit_tile_keys(cuda_device):
+    """> 65536 tiles switches the instance keys from ushort to uint (forward.cu:152-153).  Checked against
+    the same scene rendered at a size that still uses 16-bit keys, on the shared pixel region."""
+    import fgs_b200
+    from fgs_b200 import synthetic as syn
+    sc = syn.make_scene(3000, 4).to('cuda')
+    w, h = 4224, 3204  # 264 x 267 = 70488 tiles
+    cam = syn.make_camera(4, w, h)
+    rs = fgs_b200.RasterizerSettings(*util.settings_for(cam, device='cuda'))
+    params = [p.clone().requires_grad_(True) for p in sc]
+    img = fgs_b200.diff_rasterize(*params, torch.empty(0), rs)
+    assert img.shape == (3, h, w) and torch.isfinite(img).all()
+    img.mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in params) and float(params[0].grad.abs().sum()) > 0
+    # the oracle renders a pixel window of the same view exactly (oracle/torch_oracle.py: render(window=...))
+    from oracle import torch_oracle as O
+    win = (2040, 1560, 2168, 1656)
+    s = O.Settings(*[t.cpu().double() if torch.is_tensor(t) else t for t in util.settings_for(cam)])
+    with torch.no_grad():
+        ref = O.render(*[p.cpu().double() for p in sc], s, window=win).image
+    got = img.detach()[:, win[1]:win[3], win[0]:win[2]].cpu().double()
+    assert (got - ref).abs().mean().item() <= 1e-4
+
+
 def test_adam_step_matches_torch_adam(cuda_device):
     import fgs_b200
     g = torch.Generator(device='cpu').manual_seed(3)
