@@ -458,9 +458,10 @@ int fgs_profile_read(char* out, size_t out_bytes) {
     out[0] = 0;
     for (int i = 0; i < p.n; ++i) {
         FGS_TRY(cudaEventSynchronize(p.stop[i]), "profile sync");
-        float ms = 0.f;
+        float ms = 0.f, t0 = 0.f;
         FGS_TRY(cudaEventElapsedTime(&ms, p.start[i], p.stop[i]), "profile elapsed");
-        const int w = std::snprintf(out + off, out_bytes - off, "%s=%.6f\n", p.names[i], ms);
+        FGS_TRY(cudaEventElapsedTime(&t0, p.start[0], p.start[i]), "profile elapsed");
+        const int w = std::snprintf(out + off, out_bytes - off, "%s=%.6f@%.6f\n", p.names[i], ms, t0);
         if (w < 0 || (size_t)w >= out_bytes - off) break;
         off += (size_t)w;
     }

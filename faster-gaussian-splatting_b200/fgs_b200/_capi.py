@@ -117,10 +117,16 @@ def profile_enable(on: bool) -> None:
 
 def profile_read() -> list[tuple[str, float]]:
     """[(kernel name, milliseconds)] in launch order since the last read."""
+    _last_starts.clear()
     buf = C.create_string_buffer(1 << 16)
     check(load().fgs_profile_read(buf, len(buf)), 'profile_read')
     out = []
     for line in buf.value.decode().splitlines():
-        name, _, ms = line.partition('=')
+        name, _, rest = line.partition('=')
+        ms, _, t0 = rest.partition('@')
         out.append((name, float(ms)))
+        _last_starts.append((name, float(t0 or 0.0), float(ms)))
     return out
+
+
+_last_starts: list = []  # (name, start offset in ms since the first profiled launch, duration) of the last reads

@@ -117,7 +117,7 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
 
 /* Optional per-kernel timing for bench.py: while enabled every kernel (group) launched by the entry
  * points above is bracketed by CUDA events on the caller's stream.  fgs_profile_read waits for them
- * and writes one "name=milliseconds\n" line per launch, in launch order, then clears the list. */
+ * and writes one "name=milliseconds@start_offset_ms\n" line per launch, in launch order, then clears the list. */
 void fgs_profile_enable(int32_t on);
 int fgs_profile_read(char* out, size_t out_bytes);
 
