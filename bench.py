@@ -386,6 +386,11 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use
     dom = max(kern, key=kern.get)
     peak, peak_src = peak_hbm_gbs()
     dom_bytes = alg.get(dom, 0)
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/)
+        traffic = json.loads((ROOT / 'profiles' / 'r1_traffic.json').read_text())['bytes_per_launch'].get(dom)
+    except Exception:
+        pass
     dom_ms = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_bytes = alg['iteration_fused'] if use_fused else alg['iteration']
@@ -394,7 +399,7 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use
     return {
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
-                     'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                     'frac': round(achieved / peak, 4), 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': dom_bytes, 'ms_per_launch': round(dom_ms, 4),
                      'share_of_step': round(dom_ms / ms_step, 3),
                      'note': 'blend kernels are FP32-issue bound, not HBM bound; see DESIGN.md'},
