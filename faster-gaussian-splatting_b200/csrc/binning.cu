@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     const uint32_t cand = active ? tw * (ty1 - ty0) : 0u;
     const float msx = q0.x - 0.5f, msy = q0.y - 0.5f;
     const float A = q0.z, B = q0.w, C = q1.x;
-    const float tau = __log2f(q1.y * kMinAlphaRcp);  // base-2 domain, same expression as preprocess
+    const float tau = q1.y + kLog2_255;  // base-2 domain, same expression as preprocess
     uint32_t wr = active ? __ldg(offsets + i) : 0u;
 
     if (cand > 0 && cand <= 32u) {
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
     const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
     const uint32_t xmin = bx & 0xffffu, xmax = bx >> 16, ymin = by & 0xffffu, ymax = by >> 16;
     const uint32_t tx0 = (key % grid_w) * kTileW, ty0 = (key / grid_w) * kTileH;
-    const float tau2 = __log2f(q1.y * kMinAlphaRcp);
+    const float tau2 = q1.y + kLog2_255;
     uint32_t mask = 0;
 #pragma unroll
     for (int sub = 0; sub < kBlendWarps; ++sub) {

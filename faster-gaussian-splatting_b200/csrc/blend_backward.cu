@@ -41,7 +41,7 @@ constexpr int kSlots = 16;   // surviving Gaussians queued per warp before phase
 
 struct __align__(128) WarpSmem {
     Rec recs[kRing][kBatch];
-    float u[kSlots][34];    // [slot][pixel] -> u = G * dL/dalpha   (row stride 34: 8-byte aligned pixel pairs,
+    float u[kSlots][34];    // [slot][pixel] -> u = alpha * dL/dalpha (row stride 34: 8-byte aligned pixel pairs,
     float w[kSlots][34];    // [slot][pixel] -> w = T * alpha         conflict-free 64-bit reads in phase B)
     float g[3][32];         // per pixel: dL/d(colour), one plane per channel
     Rec par[kSlots];        // per slot: the Gaussian's record
@@ -59,11 +59,10 @@ __device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const i
     const int p0 = lane & kSlots;  // 0 or 16: first pixel of this half (two rows of eight pixels)
     const float4 q0 = ws.par[slot].q0;
     const float4 q1 = ws.par[slot].q1;
-    const float op = q1.y;
+    const float op = exp2f(q1.y);  // the record carries log2(opacity)
     float2 dop = make_float2(0.f, 0.f), dcr = dop, dcg = dop, dcb = dop;
     float2 mxx = dop, mxy = dop, myy = dop, mx1 = dop, my1 = dop;
     if (slot < nslots) {
-        const float2 nop2 = make_float2(-op, -op);
         const float2 step = make_float2(-2.0f, -2.0f);
         const float* urow = &ws.u[slot][p0];
         const float* wrow = &ws.w[slot][p0];
@@ -80,7 +79,7 @@ __device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const i
                 const float2 gr2 = *reinterpret_cast<const float2*>(&ws.g[0][p0 + i]);
                 const float2 gg2 = *reinterpret_cast<const float2*>(&ws.g[1][p0 + i]);
                 const float2 gb2 = *reinterpret_cast<const float2*>(&ws.g[2][p0 + i]);
-                const float2 h2 = __fmul2_rn(nop2, u2);  // -alpha * dL/dalpha
+                const float2 h2 = make_float2(-u2.x, -u2.y);  // -alpha * dL/dalpha
                 dop = __fadd2_rn(dop, u2);
                 dcr = __ffma2_rn(w2, gr2, dcr);
                 dcg = __ffma2_rn(w2, gg2, dcg);
@@ -114,7 +113,8 @@ __device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const i
         const float cA = q0.z * (-2.0f / kLog2e), cB = q0.w * (-1.0f / kLog2e), cC = q1.x * (-2.0f / kLog2e);
         const float dmx = cA * s_mx1 + cB * s_my1;
         const float dmy = cB * s_mx1 + cC * s_my1;
-        const float dopacity = proper_aa ? s_dop : op * (1.0f - op) * s_dop;
+        // sum of G dL/dalpha = s_dop / o; without anti-aliasing the gradient is w.r.t. the raw logit: x o (1 - o)
+        const float dopacity = proper_aa ? __fdividef(s_dop, op) : (1.0f - op) * s_dop;
         Grad2D* dst = grad2d + __float_as_uint(q2.w);
         atomicAdd(&dst->g0, make_float4(dmx, dmy, 0.5f * s_mxx, 0.5f * s_mxy));
         atomicAdd(&dst->g1, make_float4(0.5f * s_myy, dopacity, s_dcr * color_mask(q1.z), s_dcg * color_mask(q1.w)));
@@ -232,8 +232,7 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 const float4 q0 = recs[jj].q0;
                 const float4 q1 = recs[jj].q1;
                 const float c_b = recs[jj].q2.x;
-                const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, q0.x - px, q0.y - py), 0.0f));
-                const float alpha = __fmul_rn(q1.y, gauss);
+                const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                 const bool c = alpha >= kMinAlpha && jj < n_rel;
                 const float ae = c ? alpha : 0.0f;
                 const float w = __fmul_rn(T, ae);
@@ -244,7 +243,7 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 // dL/dalpha = (T c - C_after / (1 - alpha)) . g + galpha / (1 - alpha)
                 const float dlda = fmaf(T, cg, rcp * (galpha - sigma));
                 T = __fmul_rn(T, oma);
-                const float u = c ? gauss * dlda : 0.0f;
+                const float u = ae * dlda;  // alpha * dL/dalpha (0 when the pair does not contribute)
                 if (__any_sync(0xffffffffu, c)) {
                     ws.u[nslots][lane] = u;
                     ws.w[nslots][lane] = w;

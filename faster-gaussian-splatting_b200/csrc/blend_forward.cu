@@ -116,8 +116,7 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                     const float4 q0 = recs[jj].q0;
                     const float4 q1 = recs[jj].q1;
                     const float colb = recs[jj].q2.x;
-                    const float gauss = exp2f(fminf(blend_power2(q0.z, q0.w, q1.x, q0.x - px, q0.y - py), 0.0f));
-                    const float alpha = __fmul_rn(q1.y, gauss);
+                    const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                     const bool c = alpha >= kMinAlpha && !done;
                     const float ae = c ? alpha : 0.0f;  // alpha_eff = 0 leaves the pixel untouched
                     const float w = __fmul_rn(T, ae);

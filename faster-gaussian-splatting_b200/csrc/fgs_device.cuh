@@ -25,7 +25,7 @@ constexpr int kBlendWarps = kTilePixels / 32;  // 6
 
 // ---- per-Gaussian 2D record (48 B, three float4) ---------------------------------------------------
 // q0 = (mean2d.x, mean2d.y, A2, B2)
-// q1 = (C2, opacity, color.r, color.g)
+// q1 = (C2, log2(opacity), color.r, color.g)
 // q2 = (color.b, bits(xmin | xmax << 16), bits(ymin | ymax << 16), bits(primitive index))
 // (A2, B2, C2) is the conic pre-scaled into the base-2 exponent domain,
 //      A2 = -0.5 log2(e) conic.x,  B2 = -log2(e) conic.y,  C2 = -0.5 log2(e) conic.z,
@@ -131,6 +131,7 @@ __device__ __forceinline__ bool tile_contributes2(float mx, float my, float A2, 
 }
 
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2_255 = 7.994353436858858f;  // tau2 = log2(255 * opacity) = log2(opacity) + log2(255)
 
 // clamp to >= 0, remembering a negative input in the sign bit (-0.0f)
 __device__ __forceinline__ float pack_color(float c) { return c >= 0.0f ? c : -0.0f; }
@@ -203,6 +204,14 @@ __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ float blend_power2(float A2, float B2, float C2, float dx, float dy) {
     const float u = __fmaf_rn(B2, dy, __fmul_rn(A2, dx));
     return __fmaf_rn(__fmul_rn(C2, dy), dy, __fmul_rn(u, dx));
+}
+
+// log2(alpha) = log2(opacity) + A2 dx^2 + B2 dx dy + C2 dy^2: the opacity rides in the exponent (one FMA
+// instead of FMUL + FMUL); alpha = exp2(min(log2 alpha, log2 opacity)) equals o * exp(min(q, 0)).
+__device__ __forceinline__ float blend_alpha(float A2, float B2, float C2, float lop, float dx, float dy) {
+    const float u = __fmaf_rn(B2, dy, __fmul_rn(A2, dx));
+    const float la = __fmaf_rn(__fmul_rn(C2, dy), dy, __fmaf_rn(u, dx, lop));
+    return exp2f(fminf(la, lop));
 }
 
 // mbarrier wait with explicit back-off: a warp that finds the phase incomplete sleeps instead of

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float m2y = y * cam.focal_y + cam.center_y;
 
     // P6/P7: opacity-aware extent, bounds clamped to the padded tile grid
-    const float tau2 = __log2f(opacity * kMinAlphaRcp);  // tau * log2(e)
+    const float lop = __log2f(opacity);
+    const float tau2 = lop + kLog2_255;  // log2(255 * opacity) = tau * log2(e)
     const float tau = tau2 * 0.6931471805599453f;
     const float ext_x = fmaxf(sqrtf(cov_a * 2.0f * tau) - 0.5f, 0.0f);
     const float ext_y = fmaxf(sqrtf(cov_c * 2.0f * tau) - 0.5f, 0.0f);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     // kernels_inference.cuh:200); the clamp mask for the backward rides in the sign bit
     Rec rec;
     rec.q0 = make_float4(m2x, m2y, A2, B2);
-    rec.q1 = make_float4(C2, opacity, pack_color(color.x), pack_color(color.y));
+    rec.q1 = make_float4(C2, lop, pack_color(color.x), pack_color(color.y));
     rec.q2 = make_float4(pack_color(color.z), __uint_as_float(xmin | (xmax << 16)), __uint_as_float(ymin | (ymax << 16)),
                          __uint_as_float((uint32_t)idx));
     recs[idx] = rec;
