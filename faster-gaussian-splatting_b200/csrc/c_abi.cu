@@ -446,6 +446,32 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
     return 0;
 }
 
+int fgs_update_3d_filter(const float* positions, const float* w2c, float* filter_3d, uint8_t* visibility_mask,
+                         int32_t n_points, int32_t width, int32_t height, float focal_x, float focal_y, float center_x,
+                         float center_y, float near_plane, float clipping_tolerance, float distance2filter, void* stream) {
+    FGS_TRY(launch_update_3d_filter(positions, w2c, filter_3d, visibility_mask, n_points, width, height, focal_x, focal_y,
+                                    center_x, center_y, near_plane, clipping_tolerance, distance2filter,
+                                    reinterpret_cast<cudaStream_t>(stream)),
+            "update_3d_filter");
+    return 0;
+}
+
+int fgs_relocation_adjustment(const float* old_opacities, const float* old_scales, const int64_t* n_samples_per_primitive,
+                              float* new_opacities, float* new_scales, int32_t n_primitives, void* stream) {
+    FGS_TRY(launch_relocation(old_opacities, old_scales, reinterpret_cast<const long long*>(n_samples_per_primitive),
+                              new_opacities, new_scales, n_primitives, reinterpret_cast<cudaStream_t>(stream)),
+            "relocation_adjustment");
+    return 0;
+}
+
+int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
+                  const float* random_samples, float* means, int32_t n_primitives, float current_lr, void* stream) {
+    FGS_TRY(launch_add_noise(raw_scales, raw_rotations, raw_opacities, random_samples, means, n_primitives, current_lr,
+                             reinterpret_cast<cudaStream_t>(stream)),
+            "add_noise");
+    return 0;
+}
+
 void fgs_profile_enable(int32_t on) {
     prof().enabled = on != 0;
     prof().n = 0;

@@ -130,4 +130,14 @@ cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cuda
 cudaError_t launch_adam(const float* grad, float* param, float* exp_avg, float* exp_avg_sq, size_t n, float step_size,
                         float beta1, float beta2, float eps, float bias2_sqrt_rcp, cudaStream_t stream);
 
+// small per-Gaussian operators around the rasterizer (aux_ops.cu)
+cudaError_t launch_update_3d_filter(const float* positions, const float* w2c, float* filter_3d, unsigned char* visibility,
+                                    int n, int width, int height, float focal_x, float focal_y, float center_x,
+                                    float center_y, float near_plane, float clipping_tolerance, float distance2filter,
+                                    cudaStream_t stream);
+cudaError_t launch_relocation(const float* old_opacities, const float* old_scales, const long long* n_samples,
+                              float* new_opacities, float* new_scales, int n, cudaStream_t stream);
+cudaError_t launch_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
+                             const float* noise, float* means, int n, float lr, cudaStream_t stream);
+
 }  // namespace fgs

@@ -194,15 +194,50 @@ def adam_step(param_grad, param, exp_avg, exp_avg_sq, step_count, learning_rate,
         _capi.check(rc, 'adam_step')
 
 
-def _not_on_hot_path(name):
-    def fn(*_args, **_kwargs):
-        raise NotImplementedError(
-            f'fgs_b200._C.{name}: outside the accelerated hot path of this round (SURVEY.md §8f "next" rows)')
-    fn.__name__ = name
-    return fn
+def update_3d_filter(positions, w2c, filter_3d, visibility_mask, width, height, focal_x, focal_y, center_x, center_y,
+                     near_plane, clipping_tolerance, distance2filter) -> None:
+    """filter3d/include/filter3d.h:7-20; filter_3d and visibility_mask (bool) are updated in place."""
+    _check_param(positions, 'positions')
+    _check_param(filter_3d, 'filter_3d')
+    if not (visibility_mask.is_cuda and visibility_mask.dtype == torch.bool and visibility_mask.is_contiguous()):
+        raise RuntimeError("'visibility_mask' must be a contiguous CUDA bool tensor.")
+    dev = positions.device
+    with torch.cuda.device(dev):
+        w2c_c = _aux(w2c, dev)
+        rc = _lib.fgs_update_3d_filter(_ptr(positions), _ptr(w2c_c), _ptr(filter_3d), _ptr(visibility_mask),
+                                       positions.shape[0], int(width), int(height), float(focal_x), float(focal_y),
+                                       float(center_x), float(center_y), float(near_plane), float(clipping_tolerance),
+                                       float(distance2filter), _stream())
+        _capi.check(rc, 'update_3d_filter')
 
 
-pruning_scores = _not_on_hot_path('pruning_scores')
-update_3d_filter = _not_on_hot_path('update_3d_filter')
-relocation_adjustment = _not_on_hot_path('relocation_adjustment')
-add_noise = _not_on_hot_path('add_noise')
+def relocation_adjustment(old_opacities, old_scales, n_samples_per_primitive):
+    """densification_api.h:8-13.  Returns (new_opacities (n,1), new_scales (n,3))."""
+    dev = old_opacities.device
+    with torch.cuda.device(dev):
+        n = old_opacities.shape[0]
+        o = old_opacities.to(torch.float32).contiguous()
+        sc = old_scales.to(torch.float32).contiguous()
+        ns = n_samples_per_primitive.to(device=dev, dtype=torch.int64).contiguous()
+        new_o = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        new_s = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        rc = _lib.fgs_relocation_adjustment(_ptr(o), _ptr(sc), _ptr(ns), _ptr(new_o), _ptr(new_s), n, _stream())
+        _capi.check(rc, 'relocation_adjustment')
+    return new_o, new_s
+
+
+def add_noise(raw_scales, raw_rotations, raw_opacities, random_samples, means, current_lr) -> None:
+    """densification_api.h:15-21; `means` is updated in place."""
+    for t, name in ((raw_scales, 'raw_scales'), (raw_rotations, 'raw_rotations'), (raw_opacities, 'raw_opacities'),
+                    (random_samples, 'random_samples'), (means, 'means')):
+        _check_param(t, name)
+    with torch.cuda.device(means.device):
+        rc = _lib.fgs_add_noise(_ptr(raw_scales), _ptr(raw_rotations), _ptr(raw_opacities), _ptr(random_samples),
+                                _ptr(means), raw_scales.shape[0], float(current_lr), _stream())
+        _capi.check(rc, 'add_noise')
+
+
+def pruning_scores(*_args, **_kwargs):
+    raise NotImplementedError(
+        'fgs_b200._C.pruning_scores: Speedy-Splat pruning scores are outside the accelerated hot path of this round '
+        '(SURVEY.md §8f; SPEEDYSPLAT_PRUNING.USE is false in the benchmarked configuration)')

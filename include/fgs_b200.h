@@ -115,6 +115,22 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
                   size_t n_elements, int32_t step_count, double learning_rate, double beta1, double beta2,
                   double epsilon, void* stream);
 
+/* filter3d/include/filter3d.h:7-20 -- Mip-Splatting 3D filter: running minimum over views of
+ * distance2filter * depth for points inside the frustum dilated by `clipping_tolerance`;
+ * visibility_mask is a byte (bool) tensor set to 1 for updated points. */
+int fgs_update_3d_filter(const float* positions, const float* w2c, float* filter_3d, uint8_t* visibility_mask,
+                         int32_t n_points, int32_t width, int32_t height, float focal_x, float focal_y,
+                         float center_x, float center_y, float near_plane, float clipping_tolerance,
+                         float distance2filter, void* stream);
+
+/* densification/include/densification_api.h:8-21 -- 3DGS-MCMC helpers: opacity / scale of relocated
+ * Gaussians (Eq. 9, at most 50 samples) and the covariance-shaped exploration noise on the means. */
+int fgs_relocation_adjustment(const float* old_opacities, const float* old_scales,
+                              const int64_t* n_samples_per_primitive, float* new_opacities, float* new_scales,
+                              int32_t n_primitives, void* stream);
+int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
+                  const float* random_samples, float* means, int32_t n_primitives, float current_lr, void* stream);
+
 /* Optional per-kernel timing for bench.py: while enabled every kernel (group) launched by the entry
  * points above is bracketed by CUDA events on the caller's stream.  fgs_profile_read waits for them
  * and writes one "name=milliseconds@start_offset_ms\n" line per launch, in launch order, then clears the list. */

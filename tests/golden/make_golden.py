@@ -58,5 +58,36 @@ def main():
         print(name, 'image mean', float(img.mean()), 'grad means L1', float(grads[0].abs().sum()))
 
 
+def aux_inputs(device='cpu'):
+    """Seeded inputs of the three small operators (shared by the golden dump and the tests)."""
+    g = torch.Generator().manual_seed(11)
+    n = 4096
+    sc = syn.make_scene(n, 11)
+    cam = syn.make_camera(3, 640, 360)
+    d = dict(positions=sc.means, w2c=cam.w2c, filter_3d=torch.rand(n, 1, generator=g) * 0.02 + 1e-3,
+             old_opacities=torch.rand(n, 1, generator=g) * 0.98 + 0.01, old_scales=torch.rand(n, 3, generator=g) * 0.1,
+             n_samples=torch.randint(0, 60, (n,), generator=g), raw_scales=sc.scales, raw_rotations=sc.rotations.clone(),
+             raw_opacities=sc.opacities, noise=torch.randn(n, 3, generator=g), means=sc.means.clone())
+    d['raw_rotations'][::97] = 0.0
+    filt = dict(width=640, height=360, focal_x=cam.focal_x, focal_y=cam.focal_y, center_x=cam.center_x,
+                center_y=cam.center_y, near_plane=0.2, clipping_tolerance=0.15, distance2filter=0.0011)
+    return {k: v.to(device) for k, v in d.items()}, filt
+
+
+def dump_aux(ref, out_dir):
+    d, filt = aux_inputs('cuda')
+    f3 = d['filter_3d'].clone()
+    vis = torch.zeros(f3.shape[0], 1, dtype=torch.bool, device='cuda')
+    ref.update_3d_filter(d['positions'], d['w2c'], f3, vis, **filt)
+    new_o, new_s = ref.relocation_adjustment(d['old_opacities'], d['old_scales'], d['n_samples'])
+    means = d['means'].clone()
+    from FasterGSCudaBackend import _C as ref_C  # add_noise with a fixed noise tensor (the binding draws its own)
+    ref_C.add_noise(d['raw_scales'], d['raw_rotations'], d['raw_opacities'], d['noise'], means, 0.8)
+    np.savez_compressed(out_dir / 'aux_ops.npz', filter_3d=f3.cpu().numpy(), visibility=vis.cpu().numpy(),
+                        new_opacities=new_o.cpu().numpy(), new_scales=new_s.cpu().numpy(), means=means.cpu().numpy())
+    print('aux_ops', float(f3.mean()), int(vis.sum()), float(new_o.mean()), float(means.abs().mean()))
+
+
 if __name__ == '__main__':
     main()
+    dump_aux(util.load_reference(), ROOT / 'gpurun_out' / 'golden')
