@@ -123,6 +123,25 @@ __device__ __noinline__ void flush_slots(WarpSmem& ws, const int nslots, const i
     __syncwarp();
 }
 
+// Pruning-score variant of phase B (kernels_pruning_scores.cuh:495-500): slot k holds (o dL/dalpha)^2 per pixel,
+// the score of a Gaussian is the sum over its pixels.
+__device__ __noinline__ void flush_scores(WarpSmem& ws, const int nslots, const int lane, float* __restrict__ scores) {
+    __syncwarp();
+    const int slot = lane & (kSlots - 1);
+    const int p0 = lane & kSlots;
+    float acc = 0.f;
+    if (slot < nslots) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc += ws.u[slot][p0 + i];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane < nslots) atomicAdd(scores + __float_as_uint(ws.par[slot].q2.w), acc);
+    __syncwarp();
+}
+
+// kScores = false: gradients of the blend (training backward).  kScores = true: Speedy-Splat pruning scores
+// with dL/d(pixel colour) == 1 (kernels_pruning_scores.cuh:440-506); same traversal, different phase A payload.
+template <bool kScores>
 __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpSmem* all = reinterpret_cast<WarpSmem*>(smem_raw);
@@ -202,9 +221,13 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
             const uint32_t pidx = (uint32_t)cam.img_w * pix_y + pix_x;
             n_rel = (int)a.n_processed[pidx];
             const float Tf = a.final_T[pidx];
-            gr = a.grad_image[pidx];
-            gg = a.grad_image[n_pixels + pidx];
-            gb = a.grad_image[2 * n_pixels + pidx];
+            if (kScores) {
+                gr = gg = gb = 1.0f;
+            } else {
+                gr = a.grad_image[pidx];
+                gg = a.grad_image[n_pixels + pidx];
+                gb = a.grad_image[2 * n_pixels + pidx];
+            }
             const float gbg = gr * bg.x + gg * bg.y + gb * bg.z;
             sigma = a.image[pidx] * gr + a.image[n_pixels + pidx] * gg + a.image[2 * n_pixels + pidx] * gb - Tf * gbg;
             galpha = -Tf * gbg;
@@ -243,14 +266,19 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 // dL/dalpha = (T c - C_after / (1 - alpha)) . g + galpha / (1 - alpha)
                 const float dlda = fmaf(T, cg, rcp * (galpha - sigma));
                 T = __fmul_rn(T, oma);
-                const float u = ae * dlda;  // alpha * dL/dalpha (0 when the pair does not contribute)
+                float u = ae * dlda;  // alpha * dL/dalpha (0 when the pair does not contribute)
+                if (kScores) {        // (opacity * dL/dalpha)^2 (kernels_pruning_scores.cuh:496-497)
+                    const float od = exp2f(q1.y) * dlda;
+                    u = c ? od * od : 0.0f;
+                }
                 if (__any_sync(0xffffffffu, c)) {
                     ws.u[nslots][lane] = u;
                     ws.w[nslots][lane] = w;
                     if (lane < 3)
                         reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[jj])[lane];
                     if (++nslots == kSlots) {
-                        flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
+                        if (kScores) flush_scores(ws, nslots, lane, a.scores);
+                        else flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
                         nslots = 0;
                     }
                 }
@@ -260,32 +288,40 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
             if (issued < nb) issue();  // refill the slot just consumed
         }
         k += (uint32_t)nb;
-        if (nslots > 0) flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
+        if (nslots > 0) {
+            if (kScores) flush_scores(ws, nslots, lane, a.scores);
+            else flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
+        }
     }
 }
 
 }  // namespace
 
-cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream) {
-    if (a.n_tiles <= 0) return cudaSuccess;
+template <bool kScores>
+static cudaError_t launch_blend_backward_t(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream) {
     static int s_grid = 0;
     const size_t smem = sizeof(WarpSmem) * kWarps;
     if (s_grid == 0) {
-        cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<kScores>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(blend_backward_kernel<kScores>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_backward_kernel, kThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blend_backward_kernel<kScores>, kThreads, smem);
         if (occ < 1) occ = 1;
         s_grid = sms * occ;
     }
     const int items = a.n_tiles * kBlendWarps;
     const int g = s_grid < (items + kWarps - 1) / kWarps ? s_grid : (items + kWarps - 1) / kWarps;
-    blend_backward_kernel<<<g, kThreads, smem, stream>>>(a, cam);
+    blend_backward_kernel<kScores><<<g, kThreads, smem, stream>>>(a, cam);
     return cudaGetLastError();
+}
+
+cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream) {
+    if (a.n_tiles <= 0) return cudaSuccess;
+    return a.scores ? launch_blend_backward_t<true>(a, cam, stream) : launch_blend_backward_t<false>(a, cam, stream);
 }
 
 }  // namespace fgs

@@ -446,6 +446,52 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
     return 0;
 }
 
+int fgs_pruning_scores(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance,
+                       const float* means, const float* scales, const float* rotations, const float* opacities,
+                       const float* sh_coefficients_0, const float* sh_coefficients_rest, const float* w2c,
+                       const float* cam_position, const float* bg_color, float* image_scratch, float* scores,
+                       int32_t n_primitives, const fgs_settings* settings, void* stream) {
+    // forward with the per-pixel bookkeeping of the training path, then the score variant of the blend backward
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    fgs_forward_state state{};
+    const int rc = forward_impl(resize, user_primitive, user_tile, user_instance, means, scales, rotations, opacities,
+                                sh_coefficients_0, sh_coefficients_rest, w2c, cam_position, bg_color, image_scratch,
+                                n_primitives, settings, true, true, false, st, &state);
+    if (rc != 0 || state.n_instances <= 0) return rc;
+    const Cam cam = make_cam(*settings, w2c, cam_position, bg_color);
+    const int n_tiles = cam.grid_w * cam.grid_h;
+    const int end_bit = bits_for(n_tiles - 1);
+    // the blobs were just (re)allocated by the callbacks: ask for them again with the same sizes
+    PrimitiveLayout psz(nullptr, n_primitives);
+    PrimitiveLayout pl(resize(user_primitive, 0), n_primitives);
+    TileLayout tl(resize(user_tile, 0), n_tiles, settings->width * settings->height, true);
+    char* inst_blob = resize(user_instance, 0);
+    if (!pl.counters || !tl.ranges || !inst_blob) return fail_arg("fgs_pruning_scores: resize(user, 0) must return the current buffer");
+    const Rec* inst_recs = end_bit <= 16 ? InstanceLayout<uint16_t>(inst_blob, state.n_instances, end_bit).inst_recs
+                                         : InstanceLayout<uint32_t>(inst_blob, state.n_instances, end_bit).inst_recs;
+    FGS_TRY(cudaMemsetAsync(pl.counters + kCtrTileQueueBwd, 0, sizeof(uint32_t), st), "memset queue");
+    BlendBwdArgs ba{};
+    ba.inst_recs = inst_recs;
+    ba.tile_ranges = tl.ranges;
+    ba.image = image_scratch;
+    ba.grad_image = nullptr;
+    ba.final_T = tl.final_T;
+    ba.n_processed = tl.n_processed;
+    ba.tile_max_n = tl.tile_max_n;
+    ba.grad2d = nullptr;
+    ba.scores = scores;
+    ba.queue = pl.counters + kCtrTileQueueBwd;
+    ba.n_tiles = n_tiles;
+    {
+        cudaStream_t stream_ = st;
+        (void)stream_;
+        ProfScope ps_("pruning_scores", st);
+        FGS_TRY(launch_blend_backward(ba, cam, st), "pruning_scores");
+    }
+    (void)psz;
+    return 0;
+}
+
 int fgs_update_3d_filter(const float* positions, const float* w2c, float* filter_3d, uint8_t* visibility_mask,
                          int32_t n_points, int32_t width, int32_t height, float focal_x, float focal_y, float center_x,
                          float center_y, float near_plane, float clipping_tolerance, float distance2filter, void* stream) {

@@ -91,6 +91,7 @@ struct BlendBwdArgs {
     const uint32_t* n_processed;
     const uint32_t* tile_max_n;
     Grad2D* grad2d;           // indexed by primitive index, zeroed by the caller
+    float* scores;            // non-null: accumulate Speedy-Splat pruning scores instead of gradients
     uint32_t* queue;
     int n_tiles;
 };

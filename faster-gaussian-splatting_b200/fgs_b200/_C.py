@@ -24,6 +24,8 @@ _current_device = None
 
 
 def _resize(user, nbytes):
+    if int(nbytes) == 0 and int(user) in _current:  # query: the buffer handed out for this user last time
+        return _current[int(user)].data_ptr()
     t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_current_device)
     _current[int(user)] = t
     return t.data_ptr()
@@ -237,7 +239,28 @@ def add_noise(raw_scales, raw_rotations, raw_opacities, random_samples, means, c
         _capi.check(rc, 'add_noise')
 
 
-def pruning_scores(*_args, **_kwargs):
-    raise NotImplementedError(
-        'fgs_b200._C.pruning_scores: Speedy-Splat pruning scores are outside the accelerated hot path of this round '
-        '(SURVEY.md §8f; SPEEDYSPLAT_PRUNING.USE is false in the benchmarked configuration)')
+def pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c,
+                   cam_position, bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y,
+                   near_plane, far_plane, proper_antialiasing) -> None:
+    """rasterization_api.h:85-106: accumulates this view's Speedy-Splat pruning scores into `scores` (n,)."""
+    global _current_device
+    for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
+                    (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest'),
+                    (scores, 'scores')):
+        _check_param(t, name)
+    dev = means.device
+    with torch.cuda.device(dev):
+        n = means.shape[0]
+        total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
+        image = torch.empty((3, int(height), int(width)), dtype=torch.float32, device=dev)
+        w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
+        st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                       far_plane, proper_antialiasing)
+        _current_device = dev
+        _current.clear()
+        rc = _lib.fgs_pruning_scores(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales),
+                                     _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
+                                     _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image),
+                                     _ptr(scores), n, C.byref(st), _stream())
+        _capi.check(rc, 'pruning_scores')
+        _current.clear()

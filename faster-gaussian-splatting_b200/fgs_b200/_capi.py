@@ -64,6 +64,7 @@ SIGNATURES = {
                                                                       C.c_int32, _P]),
     'fgs_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_double,
                                  C.c_double, _P]),
+    'fgs_pruning_scores': (C.c_int, [ResizeFn, _P, _P, _P] + [_P] * 9 + [_P, _P, C.c_int32, C.POINTER(Settings), _P]),
     'fgs_update_3d_filter': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32] + [C.c_float] * 7 + [_P]),
     'fgs_relocation_adjustment': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     'fgs_add_noise': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, _P]),

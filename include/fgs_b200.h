@@ -115,6 +115,15 @@ int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* 
                   size_t n_elements, int32_t step_count, double learning_rate, double beta1, double beta2,
                   double epsilon, void* stream);
 
+/* pruning_scores.h:9-33 -- Speedy-Splat pruning scores of one view, accumulated into scores[n_primitives]:
+ * sum over pixels of (opacity * dL/dalpha)^2 with dL/d(pixel colour) == 1.  `image_scratch` is a caller
+ * buffer of 3*H*W floats.  The resize callbacks must return the current buffer when called with bytes == 0. */
+int fgs_pruning_scores(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance,
+                       const float* means, const float* scales, const float* rotations, const float* opacities,
+                       const float* sh_coefficients_0, const float* sh_coefficients_rest, const float* w2c,
+                       const float* cam_position, const float* bg_color, float* image_scratch, float* scores,
+                       int32_t n_primitives, const fgs_settings* settings, void* stream);
+
 /* filter3d/include/filter3d.h:7-20 -- Mip-Splatting 3D filter: running minimum over views of
  * distance2filter * depth for points inside the frustum dilated by `clipping_tolerance`;
  * visibility_mask is a byte (bool) tensor set to 1 for updated points. */

@@ -361,3 +361,37 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999
 def psnr(a, b):
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return 10.0 * math.log10(1.0 / max(mse, 1e-20))
+
+
+def pruning_scores(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, dtype=torch.float64):
+    """Speedy-Splat pruning scores of one view (kernels_pruning_scores.cuh:348-508): for every
+    contributing (Gaussian, pixel) pair, (opacity * dL/dalpha)^2 with dL/d(pixel colour) == 1, summed
+    over the pixels.  dL/dalpha comes from autograd with alpha as the leaf.  Returns (N,) scores."""
+    params = [p.detach().to(dtype) for p in (means, scales, rotations, opacities, sh0, sh_rest)]
+    s = s._replace(w2c=s.w2c.to(dtype), cam_position=s.cam_position.to(dtype), bg_color=s.bg_color.to(dtype))
+    with torch.no_grad():
+        proj = preprocess(*params, s)
+    vis = proj.visible.nonzero(as_tuple=True)[0]
+    order = vis[torch.argsort(proj.depth[vis], stable=True)]
+    H, Wd = s.height, s.width
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=dtype), torch.arange(Wd, dtype=dtype), indexing='ij')
+    px, py = xs.reshape(-1) + 0.5, ys.reshape(-1) + 0.5
+    m2, con, op = proj.mean2d[order], proj.conic[order], proj.opacity[order]
+    col = torch.clamp(proj.color[order], min=0.0)
+    dx = m2[:, 0:1] - px[None, :]
+    dy = m2[:, 1:2] - py[None, :]
+    q = torch.clamp(-0.5 * (con[:, 0:1] * dx * dx + con[:, 2:3] * dy * dy) - con[:, 1:2] * dx * dy, max=0.0)
+    alpha0 = op[:, None] * torch.exp(q)
+    alpha0 = alpha0 * (alpha0 >= MIN_ALPHA).to(dtype)
+    alpha = alpha0.clone().requires_grad_(True)
+    T_incl = torch.cumprod(1.0 - alpha, dim=0)
+    T_excl = torch.cat([torch.ones_like(T_incl[:1]), T_incl[:-1]], dim=0)
+    alive = (T_excl.detach() >= T_THRESHOLD).to(dtype)
+    w = T_excl * alpha * alive
+    image = torch.einsum('kp,kc->cp', w, col) + torch.prod(1.0 - alpha * alive, dim=0)[None, :] * s.bg_color[:, None]
+    image.sum().backward()
+    contrib = (alpha0 > 0) & (alive > 0)
+    per_pair = (op[:, None] * alpha.grad) ** 2 * contrib.to(dtype)
+    scores = torch.zeros(means.shape[0], dtype=dtype)
+    scores[order] = per_pair.sum(dim=1)
+    return scores

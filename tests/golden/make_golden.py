@@ -88,6 +88,19 @@ def dump_aux(ref, out_dir):
     print('aux_ops', float(f3.mean()), int(vis.sum()), float(new_o.mean()), float(means.abs().mean()))
 
 
+def dump_pruning_scores(ref, out_dir):
+    n, w, h, seed = 800, 112, 84, 6
+    sc = syn.make_scene(n, seed).to('cuda')
+    cam = syn.make_camera(seed, w, h)
+    bg = (0.2, 0.1, 0.3)
+    scores = torch.zeros(n, device='cuda')
+    ref.update_pruning_scores(scores, *sc, ref.RasterizerSettings(*util.settings_for(cam, bg=bg, device='cuda')))
+    np.savez_compressed(out_dir / 'pruning_scores.npz', scores=scores.cpu().numpy(), meta=np.array([n, w, h, seed]),
+                        bg=np.array(bg, dtype=np.float32))
+    print('pruning_scores', float(scores.sum()), int((scores > 0).sum()))
+
+
 if __name__ == '__main__':
     main()
     dump_aux(util.load_reference(), ROOT / 'gpurun_out' / 'golden')
+    dump_pruning_scores(util.load_reference(), ROOT / 'gpurun_out' / 'golden')

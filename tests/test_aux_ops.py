@@ -80,3 +80,25 @@ def test_aux_ops_cuda_vs_oracle_and_reference(cuda_device):
     means = d['means'].clone()
     fgs_b200.add_noise(d['raw_scales'], d['raw_rotations'], d['raw_opacities'], means, 0.8)
     assert torch.isfinite(means).all() and float((means - d['means']).abs().sum()) > 0
+
+
+@pytest.mark.gpu
+def test_pruning_scores_vs_oracle_and_reference(cuda_device):
+    import fgs_b200
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    n, w, h = 800, 112, 84
+    sc = syn.make_scene(n, 6)
+    cam = syn.make_camera(6, w, h)
+    bg = (0.2, 0.1, 0.3)
+    st = util.settings_for(cam, bg=bg, device='cuda')
+    dsc = sc.to('cuda')
+    scores = torch.full((n,), 0.5, device='cuda')  # accumulates on top of what is there
+    fgs_b200.update_pruning_scores(scores, *dsc, fgs_b200.RasterizerSettings(*st))
+    want = O.pruning_scores(*sc, O.Settings(*util.settings_for(cam, bg=bg))) + 0.5
+    assert util.rel_err(scores.cpu(), want) <= 5e-3
+    ref = util.load_reference()
+    if ref is not None:
+        rs = torch.full((n,), 0.5, device='cuda')
+        ref.update_pruning_scores(rs, *dsc, ref.RasterizerSettings(*st))
+        assert util.rel_err(scores, rs) <= 5e-3

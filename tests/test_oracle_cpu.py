@@ -110,3 +110,19 @@ def test_oracle_fp32_close_to_fp64():
     assert (o64.image - o32.image.double()).abs().mean().item() <= 1e-5
     for a, b in zip(g32, g64):
         assert util.rel_err(a, b) <= 2e-3
+
+
+def test_oracle_pruning_scores_matches_reference_golden():
+    f = GOLDEN / 'pruning_scores.npz'
+    if not f.exists():
+        pytest.skip('golden fixture missing')
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    z = np.load(f)
+    n, w, h, seed = [int(v) for v in z['meta']]
+    sc = syn.make_scene(n, seed)
+    cam = syn.make_camera(seed, w, h)
+    s = O.Settings(cam.w2c, cam.position, torch.from_numpy(z['bg']), 16, w, h, cam.focal_x, cam.focal_y, cam.center_x,
+                   cam.center_y, cam.near_plane, cam.far_plane, False)
+    got = O.pruning_scores(*sc, s)
+    assert util.rel_err(got, torch.from_numpy(z['scores']).double()) <= 5e-3
