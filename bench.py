@@ -312,6 +312,20 @@ def run_gpu(args, impl):
         extra['dropin_unfused'] = {'value': round(world * 1000.0 * steps / ms_u, 3), 'ms_per_step': round(ms_u / steps, 4),
                                    'e2e': round(world * 1000.0 * steps / ms_ue, 3), 'unit': 'iters/s',
                                    'note': 'diff_rasterize + FusedAdam.step, the API the reference Trainer.py calls'}
+    # second BASELINE.json metric: render ms (inference path, rasterize(..., to_chw=True)), inputs resident
+    reset_state()
+    with torch.no_grad():
+        det = [p.detach() for p in params]
+        for it in range(5):
+            be.rasterize(*det, be.RasterizerSettings(*st_dev[it % N_VIEWS]), to_chw=True)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for it in range(50):
+            be.rasterize(*det, be.RasterizerSettings(*st_dev[it % N_VIEWS]), to_chw=True)
+        r1.record()
+        torch.cuda.synchronize()
+        render_ms = r0.elapsed_time(r1) / 50
     ms_step = ms_total / steps
     value = world * acc * 1000.0 / ms_step
     e2e_value = world * acc * 1000.0 / (ms_e2e / steps)
@@ -330,6 +344,7 @@ def run_gpu(args, impl):
         'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
                 'h2d_bytes_per_step': 3 * WIDTH * HEIGHT * 4 + 64 + 12, 'd2h_bytes_per_step': 4},
         'clocks': clocks,
+        'render_ms_1080p': round(render_ms, 4),
     }
     out.update(extra)
     if impl == 'reference':
