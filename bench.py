@@ -376,8 +376,9 @@ def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use
         opt.step()
         opt.zero_grad()
         recs = _capi.profile_read()
-        # kernels per profiled group: a sort = 1 histogram kernel + one onesweep kernel per 8-bit digit place
-        per_group = {'depth sort': 1 + 4, 'tile sort': 1 + math.ceil(math.ceil(math.log2(max(T_TILES, 2))) / 8)}
+        # kernels per profiled group: a sort = one onesweep kernel per 8-bit digit place (the first-digit histograms
+        # are accumulated by the kernels that produce the keys); create_instances = main + large-footprint kernel
+        per_group = {'depth sort': 4, 'tile sort': math.ceil(math.ceil(math.log2(max(T_TILES, 2))) / 8), 'create_instances': 2}
         launches = sum(per_group.get(name, 1) for name, _ in recs)
         for name, ms in recs:
             per.setdefault(name, []).append(ms)

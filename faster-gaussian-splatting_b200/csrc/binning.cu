@@ -15,66 +15,106 @@ namespace {
 
 constexpr int kInstBlock = 256;
 
+// One thread per visible Gaussian, in depth order.  Everything the common case needs arrives with coalesced
+// loads: the Gaussian's index, its write offset and its 8-byte tile footprint (rectangle origin/width + the bit
+// mask of tiles that passed the exact test in preprocess), carried into depth order by the offsets scan.
+// Gaussians whose candidate rectangle has more than 32 tiles (rare, but the nearest -- i.e. first -- ones, so
+// one warp used to serialise hundreds of 32-tile rounds: measured, that warp WAS the kernel's duration) are
+// only appended to a work list here; create_instances_big_kernel spreads them over whole blocks.
 template <typename KeyT>
 __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
-    const uint32_t* __restrict__ sorted_idx, const uint32_t* __restrict__ offsets, const Rec* __restrict__ recs,
-    const uint32_t* __restrict__ tile_mask, KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const uint32_t* __restrict__ n_vis_dev,
-    const int grid_w) {
+    const uint32_t* __restrict__ sorted_idx, const uint32_t* __restrict__ offsets, const uint2* __restrict__ sorted_info,
+    KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const uint32_t* __restrict__ n_vis_dev,
+    const int grid_w, uint32_t* __restrict__ key_hist, const uint32_t key_hist_mask, uint32_t* __restrict__ big_count,
+    uint32_t* __restrict__ big_prims, uint32_t* __restrict__ big_offsets) {
+    // digit histogram of the tile sort's first pass, accumulated while the keys are produced
+    __shared__ uint32_t s_hist[kRadixMax];
+    s_hist[threadIdx.x] = 0;
     const uint32_t n_vis = *n_vis_dev;
+    __syncthreads();
     const uint32_t i = blockIdx.x * kInstBlock + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    if ((i & ~31u) >= n_vis) return;  // whole warp out of range
-    const bool active = i < n_vis;
-    const uint32_t prim = __ldg(sorted_idx + (active ? i : n_vis - 1));
-    const float4 q0 = __ldg(&recs[prim].q0);
-    const float4 q1 = __ldg(&recs[prim].q1);
-    const float4 q2 = __ldg(&recs[prim].q2);
-    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
-    uint32_t tx0, tx1, ty0, ty1;
-    tile_bounds_of(bx & 0xffffu, bx >> 16, by & 0xffffu, by >> 16, tx0, tx1, ty0, ty1);
-    const uint32_t tw = tx1 - tx0;
-    const uint32_t cand = active ? tw * (ty1 - ty0) : 0u;
-    const float msx = q0.x - 0.5f, msy = q0.y - 0.5f;
-    const float A = q0.z, B = q0.w, C = q1.x;
-    const float tau = q1.y + kLog2_255;  // base-2 domain, same expression as preprocess
-    uint32_t wr = active ? __ldg(offsets + i) : 0u;
-
-    if (cand > 0 && cand <= 32u) {
-        // rectangles of up to 32 tiles: preprocess kept the result of the exact tile test as a bit mask
-        uint32_t m = __ldg(tile_mask + prim);
-        while (m) {
-            const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
-            inst_keys[wr] = (KeyT)(ty * (uint32_t)grid_w + tx);
-            inst_vals[wr] = prim;
-            ++wr;
-        }
-    }
-    uint32_t big = __ballot_sync(0xffffffffu, cand > 32u);
-    while (big) {
-        const int src = __ffs((int)big) - 1;
-        big &= big - 1;
-        const float bmx = __shfl_sync(0xffffffffu, msx, src), bmy = __shfl_sync(0xffffffffu, msy, src);
-        const float bA = __shfl_sync(0xffffffffu, A, src), bB = __shfl_sync(0xffffffffu, B, src);
-        const float bC = __shfl_sync(0xffffffffu, C, src), btau = __shfl_sync(0xffffffffu, tau, src);
-        const uint32_t bx0 = __shfl_sync(0xffffffffu, tx0, src), by0 = __shfl_sync(0xffffffffu, ty0, src);
-        const uint32_t btw = __shfl_sync(0xffffffffu, tw, src), bcand = __shfl_sync(0xffffffffu, cand, src);
-        const uint32_t bprim = __shfl_sync(0xffffffffu, prim, src);
-        uint32_t bwr = __shfl_sync(0xffffffffu, wr, src);
-        for (uint32_t c0 = 0; c0 < bcand; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            const uint32_t tx = bx0 + c % btw, ty = by0 + c / btw;
-            const bool ok = c < bcand && tile_contributes2(bmx, bmy, bA, bB, bC, tx, ty, btau);
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const uint32_t pos = bwr + __popc(m & ((1u << lane) - 1u));
-                inst_keys[pos] = (KeyT)(ty * (uint32_t)grid_w + tx);
-                inst_vals[pos] = bprim;
+    if (blockIdx.x * kInstBlock >= n_vis) return;  // whole block out of range
+    if (i < n_vis) {
+        const uint32_t prim = __ldg(sorted_idx + i);
+        const uint2 info = __ldg(sorted_info + i);
+        uint32_t wr = __ldg(offsets + i);
+        if (info.x & kTileInfoBig) {
+            const uint32_t slot = atomicAdd(big_count, 1u);
+            big_prims[slot] = prim;
+            big_offsets[slot] = wr;
+        } else {
+            const uint32_t tx0 = info.x & 0xfffu, ty0 = (info.x >> 12) & 0xfffu, tw = ((info.x >> 24) & 0x1fu) + 1u;
+            uint32_t m = info.y;
+            while (m) {
+                const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                const uint32_t key = (ty0 + c / tw) * (uint32_t)grid_w + tx0 + c % tw;
+                inst_keys[wr] = (KeyT)key;
+                inst_vals[wr] = prim;
+                atomicAdd(&s_hist[key & key_hist_mask], 1u);
+                ++wr;
             }
-            bwr += __popc(m);
         }
     }
+    __syncthreads();
+    const uint32_t c = s_hist[threadIdx.x];
+    if (c) atomicAdd(key_hist + threadIdx.x, c);
+}
+
+// The Gaussians with large footprints: one BLOCK per work-list entry and round of 256 candidate tiles; the exact
+// tile test (kernels_forward.cuh:224-328 runs it per warp and 32 tiles) is re-run from the Gaussian's record with
+// the very expressions preprocess used, so the count matches the offsets that were scanned.
+template <typename KeyT>
+__global__ void __launch_bounds__(kInstBlock) create_instances_big_kernel(
+    const Rec* __restrict__ recs, KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const int grid_w,
+    uint32_t* __restrict__ key_hist, const uint32_t key_hist_mask, const uint32_t* __restrict__ big_count,
+    const uint32_t* __restrict__ big_prims, const uint32_t* __restrict__ big_offsets) {
+    __shared__ uint32_t s_hist[kRadixMax];
+    __shared__ uint32_t s_wcnt[kInstBlock / 32];
+    s_hist[threadIdx.x] = 0;
+    const uint32_t n_big = *big_count;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t item = blockIdx.x; item < n_big; item += gridDim.x) {  // block-uniform
+        const uint32_t prim = __ldg(big_prims + item);
+        uint32_t wr = __ldg(big_offsets + item);
+        const float4 q0 = __ldg(&recs[prim].q0);
+        const float4 q1 = __ldg(&recs[prim].q1);
+        const float4 q2 = __ldg(&recs[prim].q2);
+        const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+        uint32_t tx0, tx1, ty0, ty1;
+        tile_bounds_of(bx & 0xffffu, bx >> 16, by & 0xffffu, by >> 16, tx0, tx1, ty0, ty1);
+        const uint32_t tw = tx1 - tx0, cand = tw * (ty1 - ty0);
+        const float msx = q0.x - 0.5f, msy = q0.y - 0.5f;
+        const float tau = q1.y + kLog2_255;  // base-2 domain, same expression as preprocess
+        for (uint32_t c0 = 0; c0 < cand; c0 += kInstBlock) {
+            const uint32_t c = c0 + threadIdx.x;
+            const uint32_t tx = tx0 + c % tw, ty = ty0 + c / tw;
+            const bool ok = c < cand && tile_contributes2(msx, msy, q0.z, q0.w, q1.x, tx, ty, tau);
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) s_wcnt[warp] = (uint32_t)__popc(m);
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kInstBlock / 32; ++w) {
+                const uint32_t cw = s_wcnt[w];
+                before += (uint32_t)w < warp ? cw : 0u;
+                total += cw;
+            }
+            if (ok) {
+                const uint32_t pos = wr + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                const uint32_t key = ty * (uint32_t)grid_w + tx;
+                inst_keys[pos] = (KeyT)key;
+                inst_vals[pos] = prim;
+                atomicAdd(&s_hist[key & key_hist_mask], 1u);
+            }
+            wr += total;
+            __syncthreads();  // s_wcnt is rewritten by the next round
+        }
+    }
+    __syncthreads();
+    const uint32_t c = s_hist[threadIdx.x];
+    if (c) atomicAdd(key_hist + threadIdx.x, c);
 }
 
 // One thread per instance: gathers the Gaussian's 48-byte record into instance order, replaces the
@@ -92,6 +132,7 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
     if (inst >= n_inst) return;
     const uint32_t prim = __ldg(vals + inst);
     const uint32_t key = (uint32_t)keys[inst];
+    const uint32_t prev = inst > 0 ? (uint32_t)keys[inst - 1] : 0xffffffffu;  // up front: not a third dependent round trip
     const float4 q0 = __ldg(&recs[prim].q0);
     const float4 q1 = __ldg(&recs[prim].q1);
     float4 q2 = __ldg(&recs[prim].q2);
@@ -117,12 +158,9 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
     dst->q2 = q2;
     if (inst == 0) {
         ranges[key].x = 0;
-    } else {
-        const uint32_t prev = (uint32_t)keys[inst - 1];
-        if (prev != key) {
-            ranges[prev].y = inst;
-            ranges[key].x = inst;
-        }
+    } else if (prev != key) {
+        ranges[prev].y = inst;
+        ranges[key].x = inst;
     }
     if (inst == n_inst - 1) ranges[key].y = n_inst;
 }
@@ -131,17 +169,33 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
 
 template <typename KeyT>
 cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
-                                    const uint32_t* tile_mask, KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
-                                    int grid_w, cudaStream_t stream) {
+                                    const uint2* sorted_info, KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
+                                    int grid_w, uint32_t* key_hist, int key_hist_bits, uint32_t* big_count,
+                                    uint32_t* big_prims, uint32_t* big_offsets, cudaStream_t stream) {
     if (n_max <= 0) return cudaSuccess;
+    static_assert(kInstBlock == kRadixMax, "one thread per histogram bin");
+    const uint32_t mask = (1u << key_hist_bits) - 1u;
     create_instances_kernel<KeyT><<<div_up(n_max, kInstBlock), kInstBlock, 0, stream>>>(
-        sorted_idx, offsets, recs, tile_mask, inst_keys, inst_vals, n_vis_dev, grid_w);
+        sorted_idx, offsets, sorted_info, inst_keys, inst_vals, n_vis_dev, grid_w, key_hist, mask, big_count, big_prims,
+        big_offsets);
+    static int s_sms = 0;
+    if (s_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (s_sms < 1) s_sms = 1;
+    }
+    const int big_grid = n_max < 2 * s_sms ? n_max : 2 * s_sms;
+    create_instances_big_kernel<KeyT><<<big_grid, kInstBlock, 0, stream>>>(recs, inst_keys, inst_vals, grid_w, key_hist,
+                                                                          mask, big_count, big_prims, big_offsets);
     return cudaGetLastError();
 }
-template cudaError_t launch_create_instances<uint16_t>(const uint32_t*, const uint32_t*, const Rec*, const uint32_t*, uint16_t*,
-                                                       uint32_t*, const uint32_t*, int, int, cudaStream_t);
-template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, const uint32_t*, uint32_t*,
-                                                       uint32_t*, const uint32_t*, int, int, cudaStream_t);
+template cudaError_t launch_create_instances<uint16_t>(const uint32_t*, const uint32_t*, const Rec*, const uint2*, uint16_t*,
+                                                       uint32_t*, const uint32_t*, int, int, uint32_t*, int, uint32_t*,
+                                                       uint32_t*, uint32_t*, cudaStream_t);
+template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, const uint2*, uint32_t*,
+                                                       uint32_t*, const uint32_t*, int, int, uint32_t*, int, uint32_t*,
+                                                       uint32_t*, uint32_t*, cudaStream_t);
 
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,

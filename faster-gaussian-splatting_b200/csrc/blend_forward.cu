@@ -80,8 +80,12 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
         const float px = (float)pix_x + 0.5f, py = (float)pix_y + 0.5f;
         float cr = 0.f, cg = 0.f, cb = 0.f, T = 1.f;
         uint32_t n_last = 0;
-        bool done = !inside;
-        bool warp_done = __all_sync(0xffffffffu, done);
+        // the pixel's "done" flag rides in its alpha threshold: 1/255 while it is live, kDone (> any alpha,
+        // alpha <= opacity <= 1) once it left the image or its transmittance fell below 1e-4 -- one compare
+        // per Gaussian instead of compare + predicate logic
+        constexpr float kDone = 2.0f;
+        float thr = inside ? kMinAlpha : kDone;
+        bool warp_done = __all_sync(0xffffffffu, !inside);
 
         const int n = (int)(range.y - range.x);
         const int nb = (n + kBatch - 1) / kBatch;
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                 // sub-tile culling was done once at gather time (binning.cu): bit `sub` of the record's mask
                 const bool hit = lane < count && ((__float_as_uint(recs[lane].q2.y) >> sub) & 1u) != 0u;
                 uint32_t pending = __ballot_sync(0xffffffffu, hit);
+                int last_jj = -1;  // this pixel's last contributor inside the batch
                 while (pending) {
                     const int jj = __ffs((int)pending) - 1;
                     pending &= pending - 1;
@@ -117,17 +122,18 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                     const float4 q1 = recs[jj].q1;
                     const float colb = recs[jj].q2.x;
                     const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
-                    const bool c = alpha >= kMinAlpha && !done;
+                    const bool c = alpha >= thr;
                     const float ae = c ? alpha : 0.0f;  // alpha_eff = 0 leaves the pixel untouched
                     const float w = __fmul_rn(T, ae);
                     cr = fmaf(w, q1.z, cr);
                     cg = fmaf(w, q1.w, cg);
                     cb = fmaf(w, colb, cb);
                     T = __fmul_rn(T, __fsub_rn(1.0f, ae));
-                    if (c) n_last = (uint32_t)(offset + jj + 1);
-                    done = done || T < kTransmittanceThreshold;
+                    if (c) last_jj = jj;
+                    thr = T < kTransmittanceThreshold ? kDone : thr;
                 }
-                warp_done = __all_sync(0xffffffffu, done);
+                if (last_jj >= 0) n_last = (uint32_t)(offset + last_jj + 1);
+                warp_done = __all_sync(0xffffffffu, thr == kDone);
             }
             __syncwarp();
             if (!warp_done && issued < nb) issue();  // refill the slot just consumed

@@ -98,11 +98,13 @@ struct PrimitiveLayout {
     uint32_t* counters;
     Rec* recs;
     uint32_t* n_touched;
-    uint32_t* tile_mask;
+    uint2* tile_info;    // per Gaussian: tile footprint (fgs_device.cuh)
+    uint2* sorted_info;  // the footprints of the visible Gaussians in depth order
     uint32_t* keys[2];
     uint32_t* idx[2];
     uint32_t* offsets;
     uint32_t* hist;
+    uint32_t* depth_hist;  // kDepthHistReplicas copies of the depth sort's first-digit histogram (filled by preprocess)
     uint32_t* lookback;
     uint32_t* scan_lookback;
     size_t zero_bytes;  // counters .. scan_lookback are contiguous: one memset clears them all
@@ -112,12 +114,14 @@ struct PrimitiveLayout {
         const size_t nn = (size_t)(n > 0 ? n : 1);
         counters = c.take<uint32_t>(kCtrCount);
         hist = c.take<uint32_t>(4 * kRadixMax);
+        depth_hist = c.take<uint32_t>(kDepthHistReplicas * kRadixMax);
         lookback = c.take<uint32_t>(radix_sort_lookback_words(n, 32));
         scan_lookback = c.take<uint32_t>(offsets_scan_lookback_words(n));
         zero_bytes = c.bytes();
         recs = c.take<Rec>(nn);
         n_touched = c.take<uint32_t>(nn);
-        tile_mask = c.take<uint32_t>(nn);
+        tile_info = c.take<uint2>(nn);
+        sorted_info = c.take<uint2>(nn);
         keys[0] = c.take<uint32_t>(nn);
         keys[1] = c.take<uint32_t>(nn);
         idx[0] = c.take<uint32_t>(nn);
@@ -214,13 +218,20 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
     InstanceLayout<KeyT> il(blob, n_instances, end_bit);
     if (n_instances > 0) {
-        FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, pl.tile_mask, il.keys[0], il.vals[0],
-                                              pl.counters + kCtrVisible, n_visible, cam.grid_w, stream),
+        // sort scratch (histograms, then look-back words: adjacent) is cleared before create_instances,
+        // which accumulates the histogram of the tile sort's first digit while it writes the keys
+        FGS_TRY(cudaMemsetAsync(il.hist, 0, sizeof(uint32_t) * (4 * kRadixMax + radix_sort_lookback_words(n_instances, end_bit)), stream),
+                "memset tile sort scratch");
+        FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, pl.sorted_info, il.keys[0], il.vals[0],
+                                              pl.counters + kCtrVisible, n_visible, cam.grid_w, il.hist,
+                                              radix_sort_pass0_bits(end_bit), pl.counters + kCtrBigList,
+                                              /*work list: the depth sort's key buffers are dead by now*/ pl.keys[0],
+                                              pl.keys[1], stream),
                 "create_instances");
         bool in_alt = false;
         FGS_KERNEL(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
                                        n_instances, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
-                                       &in_alt, /*zero_scratch=*/true, stream),
+                                       &in_alt, /*zero_scratch=*/false, /*pass0_hist=*/il.hist, 1, stream),
                 "tile sort");
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
                                                tl.ranges, n_instances, cam.grid_w, stream),
@@ -254,6 +265,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     const int n_tiles = cam.grid_w * cam.grid_h;
     const int n_pixels = s->width * s->height;
     const int end_bit = bits_for(n_tiles - 1);
+    if (cam.grid_w >= kMaxGridDim || cam.grid_h >= kMaxGridDim) return fail_arg("fgs_forward: image larger than 4095 tiles per side");
     FGS_TRY(ensure_readback(), "readback alloc");
 
     TileLayout tsz(nullptr, n_tiles, n_pixels, training);
@@ -269,8 +281,8 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // empty tiles keep the range (0, 0); tile_max_n is written for every item by the blend forward
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
 
-    FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_mask, pl.keys[0],
-                              pl.idx[0], pl.counters, n, cam, !training, stream),
+    FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_info, pl.keys[0],
+                              pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream),
             "preprocess");
     Readback& rb = readback();
     FGS_TRY(cudaMemcpyAsync(rb.host, pl.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "count read-back");
@@ -280,10 +292,10 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     bool in_alt = false;
     FGS_KERNEL(radix_sort_pairs<uint32_t>(pl.keys[0], pl.keys[1], pl.idx[0], pl.idx[1], pl.counters + kCtrVisible, n, 32,
                                        pl.hist, pl.lookback, pl.counters + kCtrTicket0, &in_alt, /*zero_scratch=*/false,
-                                       stream),
+                                       /*pass0_hist=*/pl.depth_hist, kDepthHistReplicas, stream),
             "depth sort");
     const uint32_t* sorted_idx = pl.idx[in_alt ? 1 : 0];
-    FGS_KERNEL(launch_offsets_scan(sorted_idx, pl.n_touched, pl.offsets, pl.counters + kCtrVisible, n, pl.scan_lookback,
+    FGS_KERNEL(launch_offsets_scan(sorted_idx, pl.tile_info, pl.offsets, pl.sorted_info, pl.counters + kCtrVisible, n, pl.scan_lookback,
                                 pl.counters + kCtrTicket0 + 4, /*zero_scratch=*/false, stream),
             "offsets scan");
 
@@ -355,6 +367,28 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
 }  // namespace fgs
 
 using namespace fgs;
+
+extern "C" size_t fgs_sort_scratch_bytes(int32_t n_max, int32_t end_bit);
+
+template <typename KeyT>
+static int sort_pairs_entry(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
+                            int32_t n_max, int32_t end_bit, void* scratch, size_t scratch_bytes, int32_t* result_in_alt,
+                            void* stream) {
+    if (end_bit < 1 || end_bit > 8 * (int)sizeof(KeyT)) return fail_arg("fgs_sort_pairs: end_bit out of range for the key type");
+    if (scratch_bytes < fgs_sort_scratch_bytes(n_max, end_bit)) return fail_arg("fgs_sort_pairs: scratch too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Carver c(reinterpret_cast<char*>(scratch));
+    uint32_t* tickets = c.take<uint32_t>(8);
+    uint32_t* hist = c.take<uint32_t>(4 * kRadixMax);
+    uint32_t* lookback = c.take<uint32_t>(radix_sort_lookback_words(n_max, end_bit));
+    FGS_TRY(cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), st), "memset tickets");
+    bool in_alt = false;
+    FGS_TRY(radix_sort_pairs<KeyT>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, hist, lookback, tickets, &in_alt,
+                                   /*zero_scratch=*/true, /*pass0_hist=*/nullptr, 1, st),
+            "radix_sort_pairs");
+    if (result_in_alt) *result_in_alt = in_alt ? 1 : 0;
+    return 0;
+}
 
 extern "C" {
 
@@ -548,19 +582,15 @@ size_t fgs_sort_scratch_bytes(int32_t n_max, int32_t end_bit) {
 int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
                        int32_t n_max, int32_t end_bit, void* scratch, size_t scratch_bytes, int32_t* result_in_alt,
                        void* stream) {
-    if (scratch_bytes < fgs_sort_scratch_bytes(n_max, end_bit)) return fail_arg("fgs_sort_pairs_u32: scratch too small");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Carver c(reinterpret_cast<char*>(scratch));
-    uint32_t* tickets = c.take<uint32_t>(8);
-    uint32_t* hist = c.take<uint32_t>(4 * kRadixMax);
-    uint32_t* lookback = c.take<uint32_t>(radix_sort_lookback_words(n_max, end_bit));
-    FGS_TRY(cudaMemsetAsync(tickets, 0, 8 * sizeof(uint32_t), st), "memset tickets");
-    bool in_alt = false;
-    FGS_TRY(radix_sort_pairs<uint32_t>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, hist, lookback, tickets,
-                                       &in_alt, /*zero_scratch=*/true, st),
-            "radix_sort_pairs");
-    if (result_in_alt) *result_in_alt = in_alt ? 1 : 0;
-    return 0;
+    return sort_pairs_entry<uint32_t>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, scratch, scratch_bytes,
+                                      result_in_alt, stream);
+}
+
+int fgs_sort_pairs_u16(uint16_t* keys, uint16_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
+                       int32_t n_max, int32_t end_bit, void* scratch, size_t scratch_bytes, int32_t* result_in_alt,
+                       void* stream) {
+    return sort_pairs_entry<uint16_t>(keys, keys_alt, vals, vals_alt, n_dev, n_max, end_bit, scratch, scratch_bytes,
+                                      result_in_alt, stream);
 }
 
 }  // extern "C"

@@ -146,6 +146,21 @@ __device__ __forceinline__ void tile_bounds_of(uint32_t xmin, uint32_t xmax, uin
     ty1 = (ymax + kTileH - 1) / kTileH;
 }
 
+// ---- per-Gaussian tile footprint (8 bytes), written by preprocess, carried into depth order by the offsets scan --
+// x = tx0 | ty0 << 12 | (tw - 1) << 24 | big << 31,  y = big ? number of touched tiles : bit mask of touched tiles
+// (bit c <-> candidate tile (tx0 + c % tw, ty0 + c / tw)); big = the candidate rectangle has more than 32 tiles, in
+// which case create_instances re-runs the exact tile test from the Gaussian's record.
+constexpr uint32_t kTileInfoBig = 1u << 31;
+constexpr int kMaxGridDim = 4096;  // 12 bits per tile coordinate
+__device__ __forceinline__ uint2 pack_tile_info(uint32_t tx0, uint32_t ty0, uint32_t tw, uint32_t cand, uint32_t mask,
+                                                uint32_t n_touched) {
+    const bool big = cand > 32u;
+    return make_uint2(tx0 | (ty0 << 12) | (big ? kTileInfoBig : ((tw - 1u) << 24)), big ? n_touched : mask);
+}
+__device__ __forceinline__ uint32_t tile_info_count(uint2 info) {
+    return (info.x & kTileInfoBig) ? info.y : (uint32_t)__popc(info.y);
+}
+
 // ---- mbarrier + bulk async copy (TMA 1-D bulk; SASS: UBLKCP / SYNCS) ------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

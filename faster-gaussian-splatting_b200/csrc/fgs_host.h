@@ -14,7 +14,8 @@ enum : int {
     kCtrInstances = 1,  // I: number of (Gaussian, tile) instances
     kCtrTileQueue = 2,  // persistent blend-forward tile queue
     kCtrTileQueueBwd = 3,
-    kCtrTicket0 = 4,    // tickets for the chained-scan kernels (one per launch): 4..15
+    kCtrTicket0 = 4,    // tickets for the chained-scan kernels (one per launch): 4..14
+    kCtrBigList = 15,   // length of the work list of large-footprint Gaussians (binning.cu)
     kCtrCount = 16
 };
 
@@ -32,33 +33,42 @@ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 // ---- launchers ---------------------------------------------------------------------------------------
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
-                              uint32_t* n_touched, uint32_t* tile_mask, uint32_t* depth_keys, uint32_t* vis_indices,
-                              uint32_t* counters,
+                              uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices,
+                              uint32_t* counters, uint32_t* depth_hist,
                               int n, const Cam& cam, bool inference, cudaStream_t stream);
 
 // LSD radix sort of (key, value) pairs, onesweep style (one read + one write of the data per pass).
 // `n_dev` points at the element count on the device, `n_max` bounds it on the host (grid sizing).
 // Keys are KeyT in {uint16_t, uint32_t}; bits [0, end_bit) are sorted.  `hist` needs
 // passes * 256 uint32, `lookback` needs passes * div_up(n_max, kSortTile) * 256 uint32; both are
-// zeroed inside when `zero_scratch` (they must be adjacent: hist first) or by the caller.  Returns in *result_in_alt whether the sorted data ended in the *_alt buffers.
+// zeroed inside when `zero_scratch` (they must be adjacent: hist first) or by the caller.  A non-null
+// `pass0_hist` says the producer of the keys has already accumulated the digit histogram of the first
+// pass (bits [0, radix_sort_pass0_bits(end_bit))) there, spread over `pass0_hist_replicas` copies of 256
+// counters (summed by the first pass).  Returns in *result_in_alt whether the sorted data ended in the
+// *_alt buffers.
 template <typename KeyT>
 cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
                              int n_max, int end_bit, uint32_t* hist, uint32_t* lookback, uint32_t* tickets,
-                             bool* result_in_alt, bool zero_scratch, cudaStream_t stream);
+                             bool* result_in_alt, bool zero_scratch, const uint32_t* pass0_hist, int pass0_hist_replicas,
+                             cudaStream_t stream);
+constexpr int kDepthHistReplicas = 32;  // copies of the depth keys' first-digit histogram (spreads preprocess's atomics over L2)
 size_t radix_sort_lookback_words(int n_max, int end_bit);
 int radix_sort_passes(int end_bit);
+int radix_sort_pass0_bits(int end_bit);
 
-// offsets[i] = exclusive prefix sum over i of n_touched[sorted_idx[i]], i < *n_dev
-cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_touched, uint32_t* offsets,
+// offsets[i] = exclusive prefix sum over i of the touched-tile count of Gaussian sorted_idx[i], i < *n_dev;
+// sorted_info[i] = tile_info[sorted_idx[i]] (the footprints in depth order, so create_instances reads them coalesced)
+cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint2* tile_info, uint32_t* offsets, uint2* sorted_info,
                                 const uint32_t* n_dev, int n_max, uint32_t* lookback, uint32_t* ticket,
                                 bool zero_scratch, cudaStream_t stream);
 size_t offsets_scan_lookback_words(int n_max);
 
 template <typename KeyT>
 cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
-                                    const uint32_t* tile_mask,
+                                    const uint2* sorted_info,
                                     KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
-                                    int grid_w, cudaStream_t stream);
+                                    int grid_w, uint32_t* key_hist, int key_hist_bits, uint32_t* big_count,
+                                    uint32_t* big_prims, uint32_t* big_offsets, cudaStream_t stream);
 
 // per-tile [start, end) ranges from the tile-sorted keys + gather of the 48-byte records into
 // instance order (tile-contiguous, so the blend kernels can bulk-copy them)

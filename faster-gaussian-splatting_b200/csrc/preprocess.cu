@@ -79,9 +79,10 @@ template <bool kInference>
 __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ sh0, const float* __restrict__ sh_rest,
-    Rec* __restrict__ recs, uint32_t* __restrict__ n_touched_out, uint32_t* __restrict__ tile_mask_out,
+    Rec* __restrict__ recs, uint32_t* __restrict__ n_touched_out, uint2* __restrict__ tile_info_out,
     uint32_t* __restrict__ depth_keys,
-    uint32_t* __restrict__ vis_indices, uint32_t* __restrict__ counters, const int n, const Cam cam) {
+    uint32_t* __restrict__ vis_indices, uint32_t* __restrict__ counters, uint32_t* __restrict__ depth_hist, const int n,
+    const Cam cam) {
     __shared__ __align__(16) float s_means[kPreBlock * 3];
     __shared__ __align__(16) float s_scales[kPreBlock * 3];
     __shared__ __align__(16) float s_sh0[kPreBlock * 3];
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     }
     const bool visible = active && n_touched > 0;
     if (idx < n) n_touched_out[idx] = visible ? n_touched : 0u;
-    if (visible) tile_mask_out[idx] = tile_mask;
+    if (visible) tile_info_out[idx] = pack_tile_info(tx0, ty0, tw, cand, tile_mask, n_touched);
 
     // P9: SH -> RGB for visible Gaussians; the 180-byte rest rows are staged per warp
     const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
@@ -294,23 +295,26 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const uint32_t slot = base + __popc(vis_mask & ((1u << lane) - 1u));
     depth_keys[slot] = __float_as_uint(depth);
     vis_indices[slot] = (uint32_t)idx;
+    // digit histogram of the depth sort's first pass (low 8 key bits are mantissa noise: no aggregation to
+    // be had inside a block, so the fire-and-forget atomics are spread over kDepthHistReplicas copies)
+    atomicAdd(depth_hist + (blockIdx.x % kDepthHistReplicas) * kRadixMax + (__float_as_uint(depth) & 0xffu), 1u);
 }
 
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
-                              uint32_t* n_touched, uint32_t* tile_mask, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
-                              int n, const Cam& cam, bool inference, cudaStream_t stream) {
+                              uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
+                              uint32_t* depth_hist, int n, const Cam& cam, bool inference, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + kPreBlock - 1) / kPreBlock;
     const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
     if (inference)
         preprocess_kernel<true><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
-                                                                     recs, n_touched, tile_mask, depth_keys, vis_indices,
-                                                                     counters, n, cam);
+                                                                     recs, n_touched, tile_info, depth_keys, vis_indices,
+                                                                     counters, depth_hist, n, cam);
     else
         preprocess_kernel<false><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
-                                                                      recs, n_touched, tile_mask, depth_keys, vis_indices,
-                                                                      counters, n, cam);
+                                                                      recs, n_touched, tile_info, depth_keys, vis_indices,
+                                                                      counters, depth_hist, n, cam);
     return cudaGetLastError();
 }
 

@@ -2,11 +2,18 @@
 // instance-offset pass.  Replaces the three CUB calls of the reference's binning stage
 // (/root/reference/.../rasterization/src/forward.cu:104-127,195-202): same results (stable ascending
 // sort / exclusive prefix sum, both integer-exact), new implementation:
-//   * one histogram kernel for all digit places, then one kernel per digit place that reads and
-//     writes the data exactly once; cross-block digit offsets come from a decoupled look-back chain
-//     (status word = 2 flag bits + 30-bit count, so no fences are needed);
-//   * ranking inside a block is warp-cooperative: __match_any_sync groups equal digits, the lowest
-//     lane of each group advances the warp's private digit counter in shared memory;
+//   * one kernel per digit place.  The grid is at most one wave of co-scheduled blocks; a block owns a
+//     CONTIGUOUS chunk of 2048-key tiles, histograms the whole chunk first (16-byte key loads), publishes
+//     that histogram and resolves its cross-block digit offsets with ONE decoupled look-back (status
+//     word = 2 flag bits + 30-bit count, so no fences are needed), then ranks and scatters its tiles one
+//     after the other from a running per-digit base.  Measured on B200: with one look-back per 2048-key
+//     tile the pass time was the length of the look-back chain (tiles / 16 L2 round trips: 44 us for
+//     2.15 M pairs); per chunk the chain has <= 148 x occupancy links;
+//   * the global digit histogram of pass p+1 is accumulated by pass p while it histograms its chunk (the
+//     keys are in registers anyway); pass 0's comes from the kernel that produced the keys
+//     (create_instances) or from a one-digit histogram kernel;
+//   * ranking inside a tile is warp-cooperative: equal digits are grouped warp-wide, the lowest lane of
+//     each group advances the warp's private digit counter in shared memory;
 //   * element counts are read from device memory, so the host never waits for V before sorting.
 #include "fgs_device.cuh"
 #include "fgs_host.h"
@@ -20,7 +27,7 @@ constexpr uint32_t kFlagIncl = 2u << 30;
 constexpr uint32_t kValueMask = (1u << 30) - 1u;
 constexpr int kSortWarps = kSortBlock / 32;
 #ifndef FGS_SORT_WINDOW
-#define FGS_SORT_WINDOW 8
+#define FGS_SORT_WINDOW 4
 #endif
 constexpr int kLookWindow = FGS_SORT_WINDOW;
 
@@ -80,104 +87,146 @@ inline PassPlan make_plan(int end_bit) {
     return p;
 }
 
+// global histogram of ONE digit place (pass 0 when the producer of the keys did not supply it)
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const KeyT* __restrict__ keys,
                                                                 const uint32_t* __restrict__ n_dev,
-                                                                uint32_t* __restrict__ hist, const PassPlan plan) {
-    __shared__ uint32_t s_hist[4 * kRadixMax];
-    for (int i = threadIdx.x; i < plan.passes * kRadixMax; i += kSortBlock) s_hist[i] = 0;
+                                                                uint32_t* __restrict__ hist, const int shift,
+                                                                const int nbits) {
+    __shared__ uint32_t s_hist[kRadixMax];
+    s_hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t n = *n_dev;
-    for (uint32_t i = blockIdx.x * kSortBlock + threadIdx.x; i < n; i += gridDim.x * kSortBlock) {
-        const uint32_t k = (uint32_t)keys[i];
-        for (int p = 0; p < plan.passes; ++p)
-            atomicAdd(&s_hist[p * kRadixMax + ((k >> plan.shift[p]) & ((1u << plan.nbits[p]) - 1u))], 1u);
-    }
+    const uint32_t dmask = (1u << nbits) - 1u;
+    for (uint32_t i = blockIdx.x * kSortBlock + threadIdx.x; i < n; i += gridDim.x * kSortBlock)
+        atomicAdd(&s_hist[((uint32_t)keys[i] >> shift) & dmask], 1u);
     __syncthreads();
-    for (int i = threadIdx.x; i < plan.passes * kRadixMax; i += kSortBlock) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
+    const uint32_t c = s_hist[threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], c);
 }
 
 #ifndef FGS_SORT_MINBLOCKS
 #define FGS_SORT_MINBLOCKS 3
 #endif
+
+// groups the lanes of a warp by digit: bit l of the result is set iff lane l holds the same digit
+// (invalid lanes never match a valid one).  One ballot per digit bit; the MATCH.ANY instruction does the
+// same in one go but measured far slower on B200 (ncu: ~40 % of a pass stalled waiting for its result).
+__device__ __forceinline__ uint32_t match_digit(const uint32_t d, const bool valid, const int nbits) {
+#ifdef FGS_SORT_MATCH_ANY
+    return __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+#else
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < nbits) {  // warp-uniform
+            const bool bit = ((d >> b) & 1u) != 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
+        }
+    }
+    return m;
+#endif
+}
+
+// One digit place of the LSD sort.  Block `bid` (ticket order, so every predecessor has started) owns
+// tiles [bid * tpb, (bid + 1) * tpb) with tpb = ceil(tiles / gridDim.x).
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kernel(
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ hist,
-    uint32_t* lookback, uint32_t* ticket, const int shift, const int nbits) {
+    uint32_t* __restrict__ hist_next, uint32_t* lookback, uint32_t* ticket, const int shift, const int nbits,
+    const int shift_next, const int nbits_next, const int hist_replicas) {
+    static_assert(kSortBlock == kRadixMax, "one thread per digit");
     __shared__ uint32_t s_warp_hist[kSortWarps][kRadixMax];
     __shared__ uint32_t s_keys[kSortTile];
     __shared__ uint32_t s_vals[kSortTile];
-    __shared__ uint32_t s_base[kRadixMax];
-    __shared__ uint32_t s_lstart[kRadixMax];
+    __shared__ uint32_t s_gpos[kRadixMax];    // per tile and digit: global position of the digit's run minus its local start
+    __shared__ uint32_t s_lstart[kRadixMax];  // per tile and digit: local start of the digit's run
     __shared__ uint32_t s_tmp[kSortWarps + 1];
     __shared__ uint32_t s_cnt[kRadixMax];
+    __shared__ uint32_t s_cnt_next[kRadixMax];
     __shared__ uint32_t s_bid;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    const uint32_t n = *n_dev;
+    // this pass's global digit counts (complete: written by earlier kernels); `hist_replicas` > 1: the
+    // producer spread its atomics over that many copies (preprocess.cu)
+    uint32_t g = 0;
+    if (tid < (1 << nbits))
+        for (int r = 0; r < hist_replicas; ++r) g += hist[r * kRadixMax + tid];
     for (int i = tid; i < kSortWarps * kRadixMax; i += kSortBlock) (&s_warp_hist[0][0])[i] = 0;
     s_cnt[tid] = 0;
+    s_cnt_next[tid] = 0;
     __syncthreads();
     const uint32_t bid = s_bid;
-    const uint32_t n = *n_dev;
-    const uint32_t tile_start = bid * (uint32_t)kSortTile;
-    if (tile_start >= n) return;
-    const uint32_t tile_count = min((uint32_t)kSortTile, n - tile_start);
+    const uint32_t total_tiles = (n + (uint32_t)kSortTile - 1u) / (uint32_t)kSortTile;
+    const uint32_t tpb = (total_tiles + gridDim.x - 1u) / gridDim.x;
+    const uint32_t first_tile = bid * tpb;
+    if (first_tile >= total_tiles) return;  // blocks behind the data: nobody looks back at them
+    const uint32_t my_tiles = min(tpb, total_tiles - first_tile);
+    const uint32_t chunk_start = first_tile * (uint32_t)kSortTile;
+    const uint32_t chunk_end = min(n, chunk_start + my_tiles * (uint32_t)kSortTile);
     const uint32_t radix = 1u << nbits, dmask = radix - 1u;
+    const bool has_next = hist_next != nullptr;
+    const uint32_t dmask_next = (1u << nbits_next) - 1u;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    // ---- load keys (warp-striped) and rank them inside the warp ------------------------------------
-    const uint32_t warp_base = tile_start + (uint32_t)warp * 32u * kSortItems;
+    // ---- phase 1: digit histogram of the whole chunk (this pass and the next one) ---------------------
+    auto count_key = [&](const uint32_t k) {
+        atomicAdd(&s_cnt[(k >> shift) & dmask], 1u);
+        if (has_next) atomicAdd(&s_cnt_next[(k >> shift_next) & dmask_next], 1u);
+    };
+    // the first tile goes to registers (warp-striped) and stays there for phase 3
     uint32_t key[kSortItems];
-    uint32_t rank[kSortItems];
+    uint32_t val[kSortItems];
+    {
+        const uint32_t warp_base = chunk_start + (uint32_t)warp * 32u * kSortItems;
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t idx = warp_base + i * 32u + lane;
-        key[i] = idx < n ? (uint32_t)keys_in[idx] : 0xffffffffu;
+        for (int i = 0; i < kSortItems; ++i) {
+            const uint32_t idx = warp_base + i * 32u + lane;
+            key[i] = idx < n ? (uint32_t)keys_in[idx] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            const uint32_t idx = warp_base + i * 32u + lane;
+            val[i] = idx < n ? vals_in[idx] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i)
+            if (warp_base + i * 32u + lane < n) count_key(key[i]);
     }
-    // Early publication: a cheap shared-memory histogram of the block's digits goes out before the
-    // (much longer) ranking, so that by the time successors look back the chain of partial counts is
-    // already complete and only the inclusive wave has to propagate.
+    if (my_tiles > 1) {  // the other tiles of the chunk: 16-byte loads (tile starts are 16-byte aligned)
+        constexpr uint32_t kVec = 16u / (uint32_t)sizeof(KeyT);
+        const uint32_t rest_start = chunk_start + (uint32_t)kSortTile;
+        const uint32_t nvec = (chunk_end - rest_start) / kVec;
+        const uint4* src = reinterpret_cast<const uint4*>(keys_in + rest_start);
+        for (uint32_t v = tid; v < nvec; v += kSortBlock) {
+            const uint4 q = __ldg(src + v);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i)
-        if (warp_base + i * 32u + lane < n) atomicAdd(&s_cnt[(key[i] >> shift) & dmask], 1u);
-    __syncthreads();
-    if ((uint32_t)tid < radix)
-        st_volatile_u32(lookback + (size_t)bid * kRadixMax + tid, s_cnt[tid] | (bid == 0 ? kFlagIncl : kFlagLocal));
-    // all MATCH.ANY operations first: they do not depend on the shared-memory counters, so their (long)
-    // latencies overlap instead of serialising with the counter updates below
-    uint32_t peers[kSortItems];
-#pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const bool valid = warp_base + i * 32u + lane < n;
-        peers[i] = __match_any_sync(0xffffffffu, valid ? (key[i] >> shift) & dmask : 0xffffffffu);
-    }
-#pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const bool valid = warp_base + i * 32u + lane < n;
-        const uint32_t d = (key[i] >> shift) & dmask;
-        const uint32_t prior = valid ? s_warp_hist[warp][d] : 0u;
-        rank[i] = prior + __popc(peers[i] & lt_mask);
-        __syncwarp();
-        if (valid && lane == __ffs((int)peers[i]) - 1) s_warp_hist[warp][d] = prior + __popc(peers[i]);
-        __syncwarp();
+            for (int j = 0; j < 4; ++j) {
+                if (sizeof(KeyT) == 2) {
+                    count_key(w[j] & 0xffffu);
+                    count_key(w[j] >> 16);
+                } else {
+                    count_key(w[j]);
+                }
+            }
+        }
+        for (uint32_t i = rest_start + nvec * kVec + tid; i < chunk_end; i += kSortBlock) count_key((uint32_t)keys_in[i]);
     }
     __syncthreads();
 
-    // ---- per digit: offsets of the warps inside the block, block count, look-back -----------------
+    // ---- phase 2: publish, look back once, derive the chunk's global digit bases ------------------------
     const uint32_t d = (uint32_t)tid;
-    uint32_t cnt = 0;
-    if (d < radix) {
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const uint32_t t = s_warp_hist[w][d];
-            s_warp_hist[w][d] = cnt;
-            cnt += t;
-        }
+    const uint32_t chunk_cnt = s_cnt[tid];
+    if (d < radix)
+        st_volatile_u32(lookback + (size_t)bid * kRadixMax + d, chunk_cnt | (bid == 0 ? kFlagIncl : kFlagLocal));
+    if (has_next) {
+        const uint32_t c = s_cnt_next[tid];
+        if (c) atomicAdd(hist_next + tid, c);
     }
     // Windowed decoupled look-back: kLookWindow predecessors are read with independent loads per
     // step (one L2 latency per window instead of one per predecessor), then consumed in order until
@@ -204,90 +253,200 @@ __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kerne
             }
             j -= used;
         }
-        st_volatile_u32(lookback + (size_t)bid * kRadixMax + d, ((prefix + cnt) & kValueMask) | kFlagIncl);
+        st_volatile_u32(lookback + (size_t)bid * kRadixMax + d, ((prefix + chunk_cnt) & kValueMask) | kFlagIncl);
     }
-    const uint32_t g = d < radix ? hist[d] : 0u;
-    const uint32_t gex = block_excl_scan_256(g, s_tmp, nullptr);
-    const uint32_t lex = block_excl_scan_256(cnt, s_tmp, nullptr);
-    s_base[tid] = gex + prefix - lex;
-    s_lstart[tid] = lex;
-    __syncthreads();
+    // global position of the chunk's first key with digit d; advanced tile by tile (thread d owns digit d)
+    uint32_t base = block_excl_scan_256(g, s_tmp, nullptr) + prefix;
 
-    // ---- scatter to shared memory in block-sorted order, then stream out coalesced runs ------------
+    // ---- phase 3: rank and scatter the chunk's tiles one after the other --------------------------------
+    for (uint32_t t = 0; t < my_tiles; ++t) {
+        const uint32_t tile_start = chunk_start + t * (uint32_t)kSortTile;
+        const uint32_t tile_count = min((uint32_t)kSortTile, n - tile_start);
+        const uint32_t warp_base = tile_start + (uint32_t)warp * 32u * kSortItems;
+        if (t > 0) {
+            for (int i = tid; i < kSortWarps * kRadixMax; i += kSortBlock) (&s_warp_hist[0][0])[i] = 0;
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-        const uint32_t idx = warp_base + i * 32u + lane;
-        if (idx < n) {
-            const uint32_t dd = (key[i] >> shift) & dmask;
-            const uint32_t lp = s_lstart[dd] + s_warp_hist[warp][dd] + rank[i];
-            s_keys[lp] = key[i];
-            s_vals[lp] = vals_in[idx];
+            for (int i = 0; i < kSortItems; ++i) {
+                const uint32_t idx = warp_base + i * 32u + lane;
+                key[i] = idx < n ? (uint32_t)keys_in[idx] : 0xffffffffu;
+            }
+#pragma unroll
+            for (int i = 0; i < kSortItems; ++i) {
+                const uint32_t idx = warp_base + i * 32u + lane;
+                val[i] = idx < n ? vals_in[idx] : 0u;
+            }
+            __syncthreads();
         }
-    }
-    __syncthreads();
-    for (uint32_t lp = tid; lp < tile_count; lp += kSortBlock) {
-        const uint32_t k = s_keys[lp];
-        const uint32_t pos = s_base[(k >> shift) & dmask] + lp;
-        if (keys_out) keys_out[pos] = (KeyT)k;
-        vals_out[pos] = s_vals[lp];
+        // all matches first: they do not depend on the shared-memory counters, so their (long)
+        // latencies overlap instead of serialising with the counter updates below
+        uint32_t peers[kSortItems];
+        uint32_t rank[kSortItems];
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i)
+            peers[i] = match_digit((key[i] >> shift) & dmask, warp_base + i * 32u + lane < n, nbits);
+        // the lowest lane of every digit group advances the warp's private counter with one shared-memory
+        // atomic (same-warp shared accesses complete in program order, so item i+1 sees item i); the old
+        // value reaches the group by shuffle: the items' atomics are independent and pipeline
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            const bool valid = warp_base + i * 32u + lane < n;
+            rank[i] = 0;
+            if (valid && lane == __ffs((int)peers[i]) - 1)
+                rank[i] = atomicAdd(&s_warp_hist[warp][(key[i] >> shift) & dmask], (uint32_t)__popc(peers[i]));
+            __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            const int leader = (__ffs((int)peers[i]) - 1) & 31;
+            rank[i] = __shfl_sync(0xffffffffu, rank[i], leader) + __popc(peers[i] & lt_mask);
+        }
+        __syncthreads();
+
+        // per digit: offsets of the warps inside the tile, tile count, local start, global position
+        uint32_t cnt = 0;
+        if (d < radix) {
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const uint32_t c = s_warp_hist[w][d];
+                s_warp_hist[w][d] = cnt;
+                cnt += c;
+            }
+        }
+        const uint32_t lex = block_excl_scan_256(cnt, s_tmp, nullptr);
+        s_lstart[tid] = lex;
+        s_gpos[tid] = base - lex;
+        base += cnt;
+        __syncthreads();
+
+        // scatter to shared memory in tile-sorted order, then stream out coalesced runs
+#pragma unroll
+        for (int i = 0; i < kSortItems; ++i) {
+            if (warp_base + i * 32u + lane < n) {
+                const uint32_t dd = (key[i] >> shift) & dmask;
+                const uint32_t lp = s_lstart[dd] + s_warp_hist[warp][dd] + rank[i];
+                s_keys[lp] = key[i];
+                s_vals[lp] = val[i];
+            }
+        }
+        __syncthreads();
+        for (uint32_t lp = tid; lp < tile_count; lp += kSortBlock) {
+            const uint32_t k = s_keys[lp];
+            const uint32_t pos = s_gpos[(k >> shift) & dmask] + lp;
+            if (keys_out) keys_out[pos] = (KeyT)k;
+            vals_out[pos] = s_vals[lp];
+        }
+        // the next tile's first __syncthreads orders these reads before its writes to s_keys / s_gpos
     }
 }
 
 // ---- chained-scan exclusive prefix sum of n_touched in depth order -------------------------------
-constexpr int kScanItems = 8;
+// 4096 elements per block (16 consecutive per thread, the sorted indices arrive with 16-byte loads);
+// warp 0 resolves the block's prefix with a warp-wide decoupled look-back: 32 predecessors per L2 round trip.
+#ifndef FGS_SCAN_ITEMS
+#define FGS_SCAN_ITEMS 16
+#endif
+constexpr int kScanItems = FGS_SCAN_ITEMS;
 constexpr int kScanTile = kSortBlock * kScanItems;
+static_assert(kScanItems % 4 == 0, "16-byte index loads");
 
 __global__ void __launch_bounds__(kSortBlock) offsets_scan_kernel(const uint32_t* __restrict__ sorted_idx,
-                                                                  const uint32_t* __restrict__ n_touched,
+                                                                  const uint2* __restrict__ tile_info,
                                                                   uint32_t* __restrict__ offsets,
+                                                                  uint2* __restrict__ sorted_info,
                                                                   const uint32_t* __restrict__ n_dev,
                                                                   uint32_t* lookback, uint32_t* ticket) {
     __shared__ uint32_t s_tmp[kSortWarps + 1];
     __shared__ uint32_t s_bid;
     __shared__ uint32_t s_prefix;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    const uint32_t n = *n_dev;
     __syncthreads();
     const uint32_t bid = s_bid;
-    const uint32_t n = *n_dev;
     const uint32_t tile_start = bid * (uint32_t)kScanTile;
     if (tile_start >= n) return;
     uint32_t v[kScanItems];
     uint32_t sum = 0;
     const uint32_t first = tile_start + (uint32_t)tid * kScanItems;
+    const bool full = first + kScanItems <= n;
+    if (full) {
+        const uint4* src = reinterpret_cast<const uint4*>(sorted_idx + first);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const uint32_t i = first + k;
-        v[k] = i < n ? __ldg(n_touched + __ldg(sorted_idx + i)) : 0u;
-        sum += v[k];
+        for (int k4 = 0; k4 < kScanItems / 4; ++k4) {
+            const uint4 q = __ldg(src + k4);
+            v[4 * k4 + 0] = q.x;
+            v[4 * k4 + 1] = q.y;
+            v[4 * k4 + 2] = q.z;
+            v[4 * k4 + 3] = q.w;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(sorted_info + first);
+#pragma unroll
+        for (int k2 = 0; k2 < kScanItems / 2; ++k2) {
+            const uint2 a = __ldg(tile_info + v[2 * k2]);
+            const uint2 b = __ldg(tile_info + v[2 * k2 + 1]);
+            dst[k2] = make_uint4(a.x, a.y, b.x, b.y);
+            v[2 * k2] = tile_info_count(a);
+            v[2 * k2 + 1] = tile_info_count(b);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const uint32_t i = first + k;
+            v[k] = 0u;
+            if (i < n) {
+                const uint2 a = __ldg(tile_info + __ldg(sorted_idx + i));
+                sorted_info[i] = a;
+                v[k] = tile_info_count(a);
+            }
+        }
     }
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) sum += v[k];
     uint32_t total;
     uint32_t excl = block_excl_scan_256(sum, s_tmp, &total);
-    if (tid == 0) {
+    if (warp == 0) {
         uint32_t prefix = 0;
-        if (bid == 0) {
-            st_volatile_u32(lookback, total | kFlagIncl);
-        } else {
-            st_volatile_u32(lookback + bid, total | kFlagLocal);
-            for (int j = (int)bid - 1; j >= 0; --j) {
-                uint32_t w;
-                do {
-                    w = ld_volatile_u32(lookback + j);
-                } while ((w >> 30) == 0u);
-                prefix += w & kValueMask;
-                if (w & kFlagIncl) break;
-            }
-            st_volatile_u32(lookback + bid, ((prefix + total) & kValueMask) | kFlagIncl);
+        if (lane == 0) st_volatile_u32(lookback + bid, total | (bid == 0 ? kFlagIncl : kFlagLocal));
+        int j = (int)bid - 1;  // newest predecessor not consumed yet
+        while (j >= 0) {       // warp-uniform
+            const int idx = j - lane;
+            const uint32_t w = idx >= 0 ? ld_volatile_u32(lookback + idx) : kFlagIncl;  // before block 0: inclusive 0
+            const uint32_t not_ready = ~__ballot_sync(0xffffffffu, (w >> 30) != 0u);
+            const uint32_t incl = __ballot_sync(0xffffffffu, (w & kFlagIncl) != 0u);
+            const int n_ready = not_ready ? __ffs((int)not_ready) - 1 : 32;  // leading published entries
+            const uint32_t ready_mask = n_ready == 32 ? 0xffffffffu : (1u << n_ready) - 1u;
+            const uint32_t incl_in = incl & ready_mask;
+            const int take = incl_in ? __ffs((int)incl_in) : n_ready;  // entries consumed, the inclusive one included
+            prefix += __reduce_add_sync(0xffffffffu, lane < take ? (w & kValueMask) : 0u);
+            if (incl_in) break;
+            j -= take;
         }
-        s_prefix = prefix;
+        if (lane == 0) {
+            if (bid > 0) st_volatile_u32(lookback + bid, ((prefix + total) & kValueMask) | kFlagIncl);
+            s_prefix = prefix;
+        }
     }
     __syncthreads();
     excl += s_prefix;
+    if (full) {
+        uint4* dst = reinterpret_cast<uint4*>(offsets + first);
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const uint32_t i = first + k;
-        if (i < n) offsets[i] = excl;
-        excl += v[k];
+        for (int k4 = 0; k4 < kScanItems / 4; ++k4) {
+            uint4 q;
+            q.x = excl;
+            q.y = q.x + v[4 * k4 + 0];
+            q.z = q.y + v[4 * k4 + 1];
+            q.w = q.z + v[4 * k4 + 2];
+            excl = q.w + v[4 * k4 + 3];
+            dst[k4] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const uint32_t i = first + k;
+            if (i < n) offsets[i] = excl;
+            excl += v[k];
+        }
     }
 }
 
@@ -302,11 +461,25 @@ size_t radix_sort_lookback_words(int n_max, int end_bit) {
 template <typename KeyT>
 cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_t* vals_alt, const uint32_t* n_dev,
                              int n_max, int end_bit, uint32_t* hist, uint32_t* lookback, uint32_t* tickets,
-                             bool* result_in_alt, bool zero_scratch, cudaStream_t stream) {
+                             bool* result_in_alt, bool zero_scratch, const uint32_t* pass0_hist, int pass0_hist_replicas,
+                             cudaStream_t stream) {
     *result_in_alt = false;
     if (n_max <= 0) return cudaSuccess;
     const PassPlan plan = make_plan(end_bit);
-    const int nblocks = div_up(n_max, kSortTile);
+    const int tiles = div_up(n_max, kSortTile);
+    static int s_wave = 0;  // blocks of onesweep_kernel<KeyT> one wave holds
+    if (s_wave == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, onesweep_kernel<KeyT>, kSortBlock, 0);
+        if (occ < 1) occ = 1;
+#ifdef FGS_SORT_WAVE_CAP
+        if (occ > FGS_SORT_WAVE_CAP) occ = FGS_SORT_WAVE_CAP;
+#endif
+        s_wave = sms * occ;
+    }
+    const int grid = tiles < s_wave ? tiles : s_wave;
     if (zero_scratch) {
         cudaError_t e;
         if (lookback == hist + 4 * kRadixMax) {  // adjacent: one memset
@@ -318,16 +491,21 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
         }
         if (e != cudaSuccess) return e;
     }
-    const int hist_grid = nblocks < 148 * 8 ? nblocks : 148 * 8;
-    radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan);
+    if (!pass0_hist) {
+        const int hist_grid = tiles < 148 * 4 ? tiles : 148 * 4;
+        radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan.shift[0], plan.nbits[0]);
+    }
     KeyT* kin = keys;
     KeyT* kout = keys_alt;
     uint32_t* vin = vals;
     uint32_t* vout = vals_alt;
     for (int p = 0; p < plan.passes; ++p) {
-        onesweep_kernel<KeyT><<<nblocks, kSortBlock, 0, stream>>>(
-            kin, vin, kout, vout, n_dev, hist + p * kRadixMax, lookback + (size_t)p * nblocks * kRadixMax,
-            tickets + p, plan.shift[p], plan.nbits[p]);
+        const bool last = p + 1 == plan.passes;
+        onesweep_kernel<KeyT><<<grid, kSortBlock, 0, stream>>>(
+            kin, vin, kout, vout, n_dev, p == 0 && pass0_hist ? pass0_hist : hist + p * kRadixMax,
+            last ? nullptr : hist + (p + 1) * kRadixMax, lookback + (size_t)p * tiles * kRadixMax, tickets + p,
+            plan.shift[p], plan.nbits[p], last ? 0 : plan.shift[p + 1], last ? 1 : plan.nbits[p + 1],
+            p == 0 && pass0_hist ? pass0_hist_replicas : 1);
         KeyT* tk = kin;
         kin = kout;
         kout = tk;
@@ -339,14 +517,16 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
     return cudaGetLastError();
 }
 
+int radix_sort_pass0_bits(int end_bit) { return make_plan(end_bit).nbits[0]; }
+
 template cudaError_t radix_sort_pairs<uint16_t>(uint16_t*, uint16_t*, uint32_t*, uint32_t*, const uint32_t*, int, int,
-                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, cudaStream_t);
+                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, const uint32_t*, int, cudaStream_t);
 template cudaError_t radix_sort_pairs<uint32_t>(uint32_t*, uint32_t*, uint32_t*, uint32_t*, const uint32_t*, int, int,
-                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, cudaStream_t);
+                                                uint32_t*, uint32_t*, uint32_t*, bool*, bool, const uint32_t*, int, cudaStream_t);
 
 size_t offsets_scan_lookback_words(int n_max) { return (size_t)div_up(n_max > 0 ? n_max : 1, kScanTile); }
 
-cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_touched, uint32_t* offsets,
+cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint2* tile_info, uint32_t* offsets, uint2* sorted_info,
                                 const uint32_t* n_dev, int n_max, uint32_t* lookback, uint32_t* ticket,
                                 bool zero_scratch, cudaStream_t stream) {
     if (n_max <= 0) return cudaSuccess;
@@ -354,8 +534,8 @@ cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint32_t* n_to
         cudaError_t e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * offsets_scan_lookback_words(n_max), stream);
         if (e != cudaSuccess) return e;
     }
-    offsets_scan_kernel<<<div_up(n_max, kScanTile), kSortBlock, 0, stream>>>(sorted_idx, n_touched, offsets, n_dev,
-                                                                           lookback, ticket);
+    offsets_scan_kernel<<<div_up(n_max, kScanTile), kSortBlock, 0, stream>>>(sorted_idx, tile_info, offsets, sorted_info,
+                                                                           n_dev, lookback, ticket);
     return cudaGetLastError();
 }
 

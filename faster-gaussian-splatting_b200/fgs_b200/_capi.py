@@ -72,6 +72,8 @@ SIGNATURES = {
     'fgs_profile_read': (C.c_int, [C.c_char_p, C.c_size_t]),
     'fgs_sort_pairs_u32': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,
                                       C.POINTER(C.c_int32), _P]),
+    'fgs_sort_pairs_u16': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,
+                                      C.POINTER(C.c_int32), _P]),
     'fgs_sort_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
 }
 

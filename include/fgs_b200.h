@@ -150,6 +150,10 @@ int fgs_profile_read(char* out, size_t out_bytes);
 int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                        const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,
                        size_t scratch_bytes, int32_t* result_in_alt, void* stream);
+/* same with 16-bit keys (the instantiation used for the tile sort when the tile grid has <= 65536 tiles) */
+int fgs_sort_pairs_u16(uint16_t* keys, uint16_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                       const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,
+                       size_t scratch_bytes, int32_t* result_in_alt, void* stream);
 size_t fgs_sort_scratch_bytes(int32_t n_max, int32_t end_bit);
 
 #ifdef __cplusplus

@@ -65,13 +65,16 @@ def test_radix_sort_pairs_matches_stable_sort(cuda_device):
     from fgs_b200 import _capi
     lib = _capi.load()
     g = torch.Generator(device='cpu').manual_seed(1)
-    for n_max, n, end_bit in [(1, 1, 32), (5000, 4097, 32), (300000, 262144 + 17, 32), (200000, 200000, 14),
-                              (100000, 0, 32), (70000, 65536, 7)]:
+    # the last four cases are larger than one wave of 2048-key tiles: blocks own multi-tile chunks
+    for n_max, n, end_bit, kbits in [(1, 1, 32, 32), (5000, 4097, 32, 32), (300000, 262144 + 17, 32, 32),
+                                     (200000, 200000, 14, 32), (100000, 0, 32, 32), (70000, 65536, 7, 32),
+                                     (3000000, 2999999, 32, 32), (2500000, 2400003, 14, 32),
+                                     (2200000, 2150001, 14, 16), (3000000, 3000000, 16, 16), (5000, 4097, 9, 16)]:
         hi = (1 << end_bit) if end_bit < 32 else (1 << 32)
         keys = torch.randint(0, min(hi, 1 << 31), (n_max,), generator=g, dtype=torch.int64)
         if end_bit == 32:
             keys[::3] = keys[::3] // 65536  # many duplicates and empty high digits
-        keys = keys.to(torch.int32 if hi <= (1 << 31) else torch.int64).to(torch.int32).cuda()
+        keys = keys.to(torch.int32 if kbits == 32 else torch.int16).cuda()
         vals = torch.arange(n_max, dtype=torch.int32, device='cuda')
         keys_alt, vals_alt = torch.empty_like(keys), torch.empty_like(vals)
         n_dev = torch.tensor([n], dtype=torch.int32, device='cuda')
@@ -79,13 +82,14 @@ def test_radix_sort_pairs_matches_stable_sort(cuda_device):
         scratch = torch.empty(sb, dtype=torch.uint8, device='cuda')
         k0, v0 = keys.clone(), vals.clone()
         in_alt = C.c_int32(0)
-        rc = lib.fgs_sort_pairs_u32(keys.data_ptr(), keys_alt.data_ptr(), vals.data_ptr(), vals_alt.data_ptr(),
-                                    n_dev.data_ptr(), n_max, end_bit, scratch.data_ptr(), sb, C.byref(in_alt),
-                                    torch.cuda.current_stream().cuda_stream)
+        fn = lib.fgs_sort_pairs_u32 if kbits == 32 else lib.fgs_sort_pairs_u16
+        rc = fn(keys.data_ptr(), keys_alt.data_ptr(), vals.data_ptr(), vals_alt.data_ptr(),
+                n_dev.data_ptr(), n_max, end_bit, scratch.data_ptr(), sb, C.byref(in_alt),
+                torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, 'sort')
         torch.cuda.synchronize()
         ks, vs = (keys_alt, vals_alt) if in_alt.value else (keys, vals)
-        ref_k = k0[:n].to(torch.int64) & 0xffffffff
+        ref_k = k0[:n].to(torch.int64) & (0xffffffff if kbits == 32 else 0xffff)
         order = torch.sort(ref_k, stable=True).indices
         assert torch.equal(vs[:n].cpu(), v0[:n][order].cpu()), (n_max, n, end_bit)
         assert torch.equal(ks[:n].cpu(), k0[:n][order].cpu()), (n_max, n, end_bit)
