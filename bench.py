@@ -113,8 +113,10 @@ def make_problem(device, n=N_GAUSSIANS, w=WIDTH, h=HEIGHT, views=N_VIEWS):
     from fgs_b200 import synthetic as syn
     sc = syn.make_scene(n, 0)
     cams = [syn.make_camera(k, w, h, n_views=views) for k in range(views)]
-    targets = [syn.make_target(w, h, seed=k) for k in range(views)]
-    return sc, cams, targets
+    # ground-truth images are 8-bit (as image datasets are): the e2e path ships them over PCIe as uint8 and
+    # converts on the device; the resident path trains on the very same (quantised) float targets
+    targets8 = [(syn.make_target(w, h, seed=k) * 255.0).round().clamp(0, 255).to(torch.uint8) for k in range(views)]
+    return sc, cams, targets8
 
 
 def settings_tuple(cam, device, bg):
@@ -160,7 +162,7 @@ def run_gpu(args, impl):
     opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
     bg = torch.zeros(3, device=dev)
     st_dev = [settings_tuple(c, dev, bg) for c in cams]
-    gt_dev = [t.to(dev) for t in targets]
+    gt_dev = [t.to(dev).float().div_(255.0) for t in targets]
     gt_pin = [t.pin_memory() for t in targets]
     w2c_pin = [c.w2c.pin_memory() for c in cams]
     pos_pin = [c.position.pin_memory() for c in cams]
@@ -208,7 +210,7 @@ def run_gpu(args, impl):
     # host memory every step (double-buffered on a copy stream so the transfer overlaps the previous
     # step's kernels -- an input pipeline, as in any trainer), the loss is read back every step.
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [{'gt': torch.empty_like(gt_dev[0]), 'w2c': torch.empty(4, 4, device=dev), 'pos': torch.empty(3, device=dev),
+    bufs = [{'gt8': torch.empty_like(gt_dev[0], dtype=torch.uint8), 'w2c': torch.empty(4, 4, device=dev), 'pos': torch.empty(3, device=dev),
              'ready': torch.cuda.Event(), 'free': torch.cuda.Event()} for _ in range(2)]
 
     def prefetch(it):
@@ -216,7 +218,7 @@ def run_gpu(args, impl):
         k = view_of(it)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(b['free'])
-            b['gt'].copy_(gt_pin[k], non_blocking=True)
+            b['gt8'].copy_(gt_pin[k], non_blocking=True)
             b['w2c'].copy_(w2c_pin[k], non_blocking=True)
             b['pos'].copy_(pos_pin[k], non_blocking=True)
             b['ready'].record(copy_stream)
@@ -229,19 +231,32 @@ def run_gpu(args, impl):
     loss_evt = [torch.cuda.Event() for _ in range(2)]
     loss_log = []
 
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def read_loss(it, loss):
         slot = it % 2
-        loss_pin[slot].copy_(loss.detach().reshape(1), non_blocking=True)
-        loss_evt[slot].record(torch.cuda.current_stream())
+        loss = loss.detach().reshape(1)
+        loss_ready[slot].record(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):  # device -> host on the copy stream: the compute stream does not wait for it
+            copy_stream.wait_event(loss_ready[slot])
+            loss_pin[slot].copy_(loss, non_blocking=True)
+            loss.record_stream(copy_stream)
+            loss_evt[slot].record(copy_stream)
         prev = (it - 1) % 2
         if it > 0 and loss_evt[prev].query() is not None:
             loss_evt[prev].synchronize()
             loss_log.append(float(loss_pin[prev][0]))
         return loss_log[-1] if loss_log else 0.0
 
+    diag = {'h2d': True, 'd2h': True}  # FGS_BENCH_DIAG switches the two halves of the e2e path off in turn
+
     def step_e2e(it, fused=None):
         if acc > 1:
             return read_loss(it, accumulate_step(it))
+        if not diag['h2d']:
+            k = view_of(it)
+            loss = train_view(st_dev[k], gt_dev[k], use_fused if fused is None else fused)
+            return read_loss(it, loss) if diag['d2h'] else loss
         if e2e_state['primed'] < it:
             for b in bufs:
                 b['free'].record(torch.cuda.current_stream())
@@ -252,9 +267,10 @@ def run_gpu(args, impl):
         k = view_of(it)
         torch.cuda.current_stream().wait_event(b['ready'])
         st = (b['w2c'], b['pos']) + st_dev[k][2:]
-        loss = train_view(st, b['gt'], use_fused if fused is None else fused)
+        gt = b['gt8'].float().div_(255.0)  # uint8 -> float on the device
         b['free'].record(torch.cuda.current_stream())
-        return read_loss(it, loss)
+        loss = train_view(st, gt, use_fused if fused is None else fused)
+        return read_loss(it, loss) if diag['d2h'] else loss
 
     init_params = [p.detach().clone() for p in params]
 
@@ -270,13 +286,13 @@ def run_gpu(args, impl):
     def timed(fn, steps, warmup, sampler=None):
         reset_state()
         e2e_state['primed'] = -1
+        if sampler:  # sampled from the warm-up on (same load as the timed steps): the timed region alone can be
+            sampler.start()  # shorter than nvidia-smi's start-up + sampling period
         for it in range(warmup):
             fn(it)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
@@ -284,7 +300,16 @@ def run_gpu(args, impl):
             fn(warmup + it)
         e1.record()
         torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            # keep the identical load running (untimed) until nvidia-smi has delivered a few samples
+            t_end, it2 = time.time() + 4.0, warmup + steps
+            while len(sampler.lines) < 5 and time.time() < t_end:
+                for _ in range(20):
+                    fn(it2)
+                    it2 += 1
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -303,6 +328,11 @@ def run_gpu(args, impl):
         for r in range(4):
             ms_d, _ = timed(step_resident, steps, warmup)
             print(f'[diag] loop {r}: {ms_d / steps:.4f} ms/step', file=sys.stderr)
+        for h2d, d2h in ((True, True), (False, True), (True, False), (False, False)):
+            diag['h2d'], diag['d2h'] = h2d, d2h
+            ms_d, _ = timed(step_e2e, steps, warmup)
+            print(f'[diag] e2e h2d={h2d} d2h={d2h}: {ms_d / steps:.4f} ms/step', file=sys.stderr)
+        diag['h2d'] = diag['d2h'] = True
     ms_total, clocks = timed(step_resident, steps, warmup, sampler)
     ms_e2e, _ = timed(step_e2e, steps, max(warmup, 10))
     extra = {}
@@ -342,7 +372,8 @@ def run_gpu(args, impl):
                                       else 'backward, then FusedAdam.step'),
                    'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
         'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
-                'h2d_bytes_per_step': 3 * WIDTH * HEIGHT * 4 + 64 + 12, 'd2h_bytes_per_step': 4},
+                'h2d_bytes_per_step': 3 * WIDTH * HEIGHT + 64 + 12, 'd2h_bytes_per_step': 4,
+                'note': 'per step: uint8 target image + camera (w2c, position) from pinned host memory, loss scalar back'},
         'clocks': clocks,
         'render_ms_1080p': round(render_ms, 4),
     }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
     const uint32_t* __restrict__ sorted_idx, const uint32_t* __restrict__ offsets, const uint2* __restrict__ sorted_info,
     KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const uint32_t* __restrict__ n_vis_dev,
     const int grid_w, uint32_t* __restrict__ key_hist, const uint32_t key_hist_mask, uint32_t* __restrict__ big_count,
-    uint32_t* __restrict__ big_prims, uint32_t* __restrict__ big_offsets) {
+    uint32_t* __restrict__ big_prims, uint32_t* __restrict__ big_offsets, const uint32_t capacity) {
     // digit histogram of the tile sort's first pass, accumulated while the keys are produced
     __shared__ uint32_t s_hist[kRadixMax];
     s_hist[threadIdx.x] = 0;
@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_kernel(
             big_offsets[slot] = wr;
         } else {
             const uint32_t tx0 = info.x & 0xfffu, ty0 = (info.x >> 12) & 0xfffu, tw = ((info.x >> 24) & 0x1fu) + 1u;
-            uint32_t m = info.y;
+            // `capacity`: the instance buffers may have been sized speculatively (c_abi.cu); never write past them
+            uint32_t m = wr + (uint32_t)__popc(info.y) <= capacity ? info.y : 0u;
             while (m) {
                 const uint32_t c = (uint32_t)__ffs((int)m) - 1u;
                 m &= m - 1u;
@@ -68,7 +69,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kInstBlock) create_instances_big_kernel(
     const Rec* __restrict__ recs, KeyT* __restrict__ inst_keys, uint32_t* __restrict__ inst_vals, const int grid_w,
     uint32_t* __restrict__ key_hist, const uint32_t key_hist_mask, const uint32_t* __restrict__ big_count,
-    const uint32_t* __restrict__ big_prims, const uint32_t* __restrict__ big_offsets) {
+    const uint32_t* __restrict__ big_prims, const uint32_t* __restrict__ big_offsets, const uint32_t capacity) {
     __shared__ uint32_t s_hist[kRadixMax];
     __shared__ uint32_t s_wcnt[kInstBlock / 32];
     s_hist[threadIdx.x] = 0;
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(kInstBlock) create_instances_big_kernel(
                 before += (uint32_t)w < warp ? cw : 0u;
                 total += cw;
             }
-            if (ok) {
-                const uint32_t pos = wr + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            const uint32_t pos = wr + before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (ok && pos < capacity) {
                 const uint32_t key = ty * (uint32_t)grid_w + tx;
                 inst_keys[pos] = (KeyT)key;
                 inst_vals[pos] = prim;
@@ -126,8 +127,9 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restrict__ keys,
                                                             const uint32_t* __restrict__ vals,
                                                             const Rec* __restrict__ recs, Rec* __restrict__ inst_recs,
-                                                            uint2* __restrict__ ranges, const uint32_t n_inst,
-                                                            const uint32_t grid_w) {
+                                                            uint2* __restrict__ ranges, const uint32_t* __restrict__ n_inst_dev,
+                                                            const uint32_t capacity, const uint32_t grid_w) {
+    const uint32_t n_inst = min(*n_inst_dev, capacity);
     const uint32_t inst = blockIdx.x * 256u + threadIdx.x;
     if (inst >= n_inst) return;
     const uint32_t prim = __ldg(vals + inst);
@@ -171,13 +173,13 @@ template <typename KeyT>
 cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* offsets, const Rec* recs,
                                     const uint2* sorted_info, KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
                                     int grid_w, uint32_t* key_hist, int key_hist_bits, uint32_t* big_count,
-                                    uint32_t* big_prims, uint32_t* big_offsets, cudaStream_t stream) {
+                                    uint32_t* big_prims, uint32_t* big_offsets, int capacity, cudaStream_t stream) {
     if (n_max <= 0) return cudaSuccess;
     static_assert(kInstBlock == kRadixMax, "one thread per histogram bin");
     const uint32_t mask = (1u << key_hist_bits) - 1u;
     create_instances_kernel<KeyT><<<div_up(n_max, kInstBlock), kInstBlock, 0, stream>>>(
         sorted_idx, offsets, sorted_info, inst_keys, inst_vals, n_vis_dev, grid_w, key_hist, mask, big_count, big_prims,
-        big_offsets);
+        big_offsets, (uint32_t)capacity);
     static int s_sms = 0;
     if (s_sms == 0) {
         int dev = 0;
@@ -187,28 +189,29 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
     }
     const int big_grid = n_max < 2 * s_sms ? n_max : 2 * s_sms;
     create_instances_big_kernel<KeyT><<<big_grid, kInstBlock, 0, stream>>>(recs, inst_keys, inst_vals, grid_w, key_hist,
-                                                                          mask, big_count, big_prims, big_offsets);
+                                                                          mask, big_count, big_prims, big_offsets,
+                                                                          (uint32_t)capacity);
     return cudaGetLastError();
 }
 template cudaError_t launch_create_instances<uint16_t>(const uint32_t*, const uint32_t*, const Rec*, const uint2*, uint16_t*,
                                                        uint32_t*, const uint32_t*, int, int, uint32_t*, int, uint32_t*,
-                                                       uint32_t*, uint32_t*, cudaStream_t);
+                                                       uint32_t*, uint32_t*, int, cudaStream_t);
 template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, const uint2*, uint32_t*,
                                                        uint32_t*, const uint32_t*, int, int, uint32_t*, int, uint32_t*,
-                                                       uint32_t*, uint32_t*, cudaStream_t);
+                                                       uint32_t*, uint32_t*, int, cudaStream_t);
 
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
-                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, int grid_w,
-                                     cudaStream_t stream) {
-    if (n_instances <= 0) return cudaSuccess;
-    ranges_gather_kernel<KeyT><<<(unsigned)((n_instances + 255) / 256), 256, 0, stream>>>(
-        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, (uint32_t)n_instances, (uint32_t)grid_w);
+                                     Rec* inst_recs, uint2* tile_ranges, const uint32_t* n_instances_dev, int capacity,
+                                     int grid_w, cudaStream_t stream) {
+    if (capacity <= 0) return cudaSuccess;
+    ranges_gather_kernel<KeyT><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(
+        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, n_instances_dev, (uint32_t)capacity, (uint32_t)grid_w);
     return cudaGetLastError();
 }
-template cudaError_t launch_ranges_and_gather<uint16_t>(const uint16_t*, const uint32_t*, const Rec*, Rec*, uint2*, int,
-                                                        int, cudaStream_t);
-template cudaError_t launch_ranges_and_gather<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, Rec*, uint2*, int,
-                                                        int, cudaStream_t);
+template cudaError_t launch_ranges_and_gather<uint16_t>(const uint16_t*, const uint32_t*, const Rec*, Rec*, uint2*,
+                                                        const uint32_t*, int, int, cudaStream_t);
+template cudaError_t launch_ranges_and_gather<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, Rec*, uint2*,
+                                                        const uint32_t*, int, int, cudaStream_t);
 
 }  // namespace fgs

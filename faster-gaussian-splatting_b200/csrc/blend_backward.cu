@@ -271,7 +271,10 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                     const float od = exp2f(q1.y) * dlda;
                     u = c ? od * od : 0.0f;
                 }
-                if (__any_sync(0xffffffffu, c)) {
+                // every Gaussian that reaches the sub-tile takes a slot (98 % of them contribute to at least one
+                // pixel: voting on that and branching cost more than the few all-zero slots); lanes 0-2 copy its
+                // record out of the ring
+                {
                     ws.u[nslots][lane] = u;
                     ws.w[nslots][lane] = w;
                     if (lane < 3)

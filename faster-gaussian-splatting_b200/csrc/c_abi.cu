@@ -192,10 +192,14 @@ Cam make_cam(const fgs_settings& s, const float* w2c, const float* cam_position,
     return c;
 }
 
-// pinned read-back slot + event, created once per process
+// pinned read-back slot, side stream and events, created once per process.  The 8-byte copy of (V, I) runs
+// on its own stream so that the launching stream goes from preprocess straight into the depth sort (a copy
+// queued between two kernels of one stream costs a hand-over to the copy engine and back).
 struct Readback {
     uint32_t* host = nullptr;
-    cudaEvent_t event = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t counted = nullptr;  // preprocess done (launching stream)
+    cudaEvent_t event = nullptr;    // copy done (side stream)
 };
 Readback& readback() {
     static Readback rb;
@@ -206,35 +210,55 @@ cudaError_t ensure_readback() {
     if (rb.host) return cudaSuccess;
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&rb.host), 64, cudaHostAllocDefault);
     if (e != cudaSuccess) return e;
+    e = cudaStreamCreateWithFlags(&rb.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&rb.counted, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
     return cudaEventCreateWithFlags(&rb.event, cudaEventDisableTiming);
 }
 
+// Instance-buffer capacity the next forward is launched with before its own instance count has come back
+// from the device (0: none yet).  Sizing speculatively keeps the host ahead of the GPU: the one read-back of
+// (V, I) is then only *checked* after everything has been queued, instead of stalling the launch sequence
+// between the offsets scan and create_instances.  Process-wide, single-threaded host use (like the reference's
+// function-local static stream, forward.cu:47-53).
+int g_capacity_hint = 0;
+
+int next_capacity_hint(int n_instances, int current) {
+    // grow with 25 % head-room, shrink only when more than half of the buffer is unused: sizes stay stable
+    const long long want = (long long)n_instances + n_instances / 4 + 65536;
+    if (n_instances <= current && (long long)current <= 2 * want) return current;
+    return want > 0x7fffffffLL ? 0x7fffffff : (int)want;
+}
+
+// everything after the offsets scan: instances, tile sort, ranges + record gather, blend.  `capacity` is the
+// number of instances the instance buffers are sized for (>= the true count, or the caller re-runs this).
 template <typename KeyT>
 int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl, const TileLayout& tl,
-                   const uint32_t* sorted_idx, int n_visible, int n_instances, int n_tiles, int end_bit,
-                   const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
-    InstanceLayout<KeyT> sizing(nullptr, n_instances, end_bit);
+                   const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit, const Cam& cam,
+                   float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
+    InstanceLayout<KeyT> sizing(nullptr, capacity, end_bit);
     char* blob = resize(user_instance, sizing.bytes);
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
-    InstanceLayout<KeyT> il(blob, n_instances, end_bit);
-    if (n_instances > 0) {
+    InstanceLayout<KeyT> il(blob, capacity, end_bit);
+    if (capacity > 0) {
         // sort scratch (histograms, then look-back words: adjacent) is cleared before create_instances,
         // which accumulates the histogram of the tile sort's first digit while it writes the keys
-        FGS_TRY(cudaMemsetAsync(il.hist, 0, sizeof(uint32_t) * (4 * kRadixMax + radix_sort_lookback_words(n_instances, end_bit)), stream),
+        FGS_TRY(cudaMemsetAsync(il.hist, 0, sizeof(uint32_t) * (4 * kRadixMax + radix_sort_lookback_words(capacity, end_bit)), stream),
                 "memset tile sort scratch");
         FGS_KERNEL(launch_create_instances<KeyT>(sorted_idx, pl.offsets, pl.recs, pl.sorted_info, il.keys[0], il.vals[0],
-                                              pl.counters + kCtrVisible, n_visible, cam.grid_w, il.hist,
+                                              pl.counters + kCtrVisible, n, cam.grid_w, il.hist,
                                               radix_sort_pass0_bits(end_bit), pl.counters + kCtrBigList,
                                               /*work list: the depth sort's key buffers are dead by now*/ pl.keys[0],
-                                              pl.keys[1], stream),
+                                              pl.keys[1], capacity, stream),
                 "create_instances");
         bool in_alt = false;
         FGS_KERNEL(radix_sort_pairs<KeyT>(il.keys[0], il.keys[1], il.vals[0], il.vals[1], pl.counters + kCtrInstances,
-                                       n_instances, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
+                                       capacity, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
                                        &in_alt, /*zero_scratch=*/false, /*pass0_hist=*/il.hist, 1, stream),
                 "tile sort");
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
-                                               tl.ranges, n_instances, cam.grid_w, stream),
+                                               tl.ranges, pl.counters + kCtrInstances, capacity, cam.grid_w, stream),
                 "ranges_and_gather");
     }
     BlendFwdArgs a{};
@@ -251,6 +275,15 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     a.clamp_output = clamp_output;
     FGS_KERNEL(launch_blend_forward(a, cam, stream), "blend_forward");
     return 0;
+}
+
+int finish_forward_any(bool keys16, fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl,
+                       const TileLayout& tl, const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit,
+                       const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
+    return keys16 ? finish_forward<uint16_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
+                                             image, training, to_chw, clamp_output, stream)
+                  : finish_forward<uint32_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
+                                             image, training, to_chw, clamp_output, stream);
 }
 
 int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
@@ -285,8 +318,10 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
                               pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream),
             "preprocess");
     Readback& rb = readback();
-    FGS_TRY(cudaMemcpyAsync(rb.host, pl.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "count read-back");
-    FGS_TRY(cudaEventRecord(rb.event, stream), "event record");
+    FGS_TRY(cudaEventRecord(rb.counted, stream), "event record");
+    FGS_TRY(cudaStreamWaitEvent(rb.stream, rb.counted, 0), "read-back stream wait");
+    FGS_TRY(cudaMemcpyAsync(rb.host, pl.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, rb.stream), "count read-back");
+    FGS_TRY(cudaEventRecord(rb.event, rb.stream), "event record");
 
     // depth order: bits [0, 32) of the positive float depth (sign bit is always 0 after the near cull)
     bool in_alt = false;
@@ -299,21 +334,40 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
                                 pl.counters + kCtrTicket0 + 4, /*zero_scratch=*/false, stream),
             "offsets scan");
 
+    // Launch the rest with the capacity the previous forward suggested, and only then look at this forward's
+    // own count (the read-back has long completed by then).  No suggestion yet: wait for the count first.
+    const bool keys16 = end_bit <= 16;
+    int capacity = g_capacity_hint;
+    if (capacity > 0) {
+        const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
+                                          image, training, to_chw, clamp_output, stream);
+        if (rc != 0) return rc;
+    }
     FGS_TRY(cudaEventSynchronize(rb.event), "count read-back wait");
     const int n_visible = (int)rb.host[0];
     const int n_instances = (int)rb.host[1];
     if (n_instances < 0) return fail_arg("fgs_forward: more than 2^31 instances");
+    if (capacity == 0 || n_instances > capacity) {
+        if (capacity > 0) {
+            // the speculative pass ran out of room (its kernels clamp to the capacity, nothing was overrun):
+            // reset what it consumed -- blend queues, sort tickets, work-list length, tile ranges -- and redo it
+            FGS_TRY(cudaMemsetAsync(pl.counters + kCtrTileQueue, 0, sizeof(uint32_t) * (kCtrCount - kCtrTileQueue), stream),
+                    "memset counters (redo)");
+            FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges (redo)");
+        }
+        capacity = n_instances;
+        const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
+                                          image, training, to_chw, clamp_output, stream);
+        if (rc != 0) return rc;
+    }
+    g_capacity_hint = next_capacity_hint(n_instances, g_capacity_hint);
     if (state_out) {
         state_out->n_instances = n_instances;
         state_out->n_buckets = 0;
         state_out->selector = 0;
         state_out->n_visible = n_visible;
     }
-    if (end_bit <= 16)
-        return finish_forward<uint16_t>(resize, user_instance, pl, tl, sorted_idx, n_visible, n_instances, n_tiles,
-                                        end_bit, cam, image, training, to_chw, clamp_output, stream);
-    return finish_forward<uint32_t>(resize, user_instance, pl, tl, sorted_idx, n_visible, n_instances, n_tiles, end_bit,
-                                    cam, image, training, to_chw, clamp_output, stream);
+    return 0;
 }
 
 int backward_impl(const float* grad_image, const float* image, const float* means, const float* scales,
@@ -551,6 +605,9 @@ int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const flo
             "add_noise");
     return 0;
 }
+
+void fgs_debug_set_capacity_hint(int32_t capacity) { g_capacity_hint = capacity > 0 ? capacity : 0; }
+int32_t fgs_debug_get_capacity_hint(void) { return g_capacity_hint; }
 
 void fgs_profile_enable(int32_t on) {
     prof().enabled = on != 0;

@@ -197,6 +197,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (Ampere-style cp.async, SASS LDGSTS): no register staging, the issuing
+// thread only waits at cp_async_wait_all()
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // named barrier over a subset of the CTA, with an AND reduction of a predicate (BAR.RED.AND)
 __device__ __forceinline__ bool named_bar_and(int id, int nthreads, bool pred) {
     int r;

@@ -68,14 +68,15 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
                                     const uint2* sorted_info,
                                     KeyT* inst_keys, uint32_t* inst_vals, const uint32_t* n_vis_dev, int n_max,
                                     int grid_w, uint32_t* key_hist, int key_hist_bits, uint32_t* big_count,
-                                    uint32_t* big_prims, uint32_t* big_offsets, cudaStream_t stream);
+                                    uint32_t* big_prims, uint32_t* big_offsets, int capacity, cudaStream_t stream);
 
 // per-tile [start, end) ranges from the tile-sorted keys + gather of the 48-byte records into
-// instance order (tile-contiguous, so the blend kernels can bulk-copy them)
+// instance order (tile-contiguous, so the blend kernels can bulk-copy them).  The instance count is read
+// from the device and clamped to `capacity` (the size the instance buffers were allocated for).
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
-                                     Rec* inst_recs, uint2* tile_ranges, int n_instances, int grid_w,
-                                     cudaStream_t stream);
+                                     Rec* inst_recs, uint2* tile_ranges, const uint32_t* n_instances_dev, int capacity,
+                                     int grid_w, cudaStream_t stream);
 
 struct BlendFwdArgs {
     const Rec* inst_recs;

@@ -106,6 +106,11 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     } else if (tid < 12) {
         s_w2c[tid] = __ldg(cam.w2c + tid);
     }
+    // this thread's opacity logit and quaternion: issued before the staging barrier so that their latency
+    // overlaps the staged loads (measured: two exposed DRAM round trips after the barrier otherwise)
+    const int idx = first + tid;
+    const float raw_opacity = __ldg(opacities + (idx < n ? idx : first));
+    const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + (idx < n ? idx : first));
     stage_rows<3>(s_means, means + (size_t)first * 3, rows * 3, tid, kPreBlock);
     stage_rows<3>(s_scales, scales + (size_t)first * 3, rows * 3, tid, kPreBlock);
     stage_rows<3>(s_sh0, sh0 + (size_t)first * 3, rows * 3, tid, kPreBlock);
@@ -115,7 +120,6 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
 #pragma unroll
     for (int i = 0; i < 12; ++i) W[i] = s_w2c[i];
 
-    const int idx = first + tid;
     bool active = idx < n;
     const int r = active ? tid : 0;  // inactive tail threads mirror row 0 and stay alive for warp collectives
 
@@ -125,13 +129,12 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     if (depth < cam.near_plane || depth > cam.far_plane) active = false;
 
     // P2: activated opacity, cull below 1/255
-    float opacity = sigmoidf_(__ldg(opacities + (active ? idx : first)));
+    float opacity = sigmoidf_(raw_opacity);
     if (opacity < kMinAlpha) active = false;
 
     // P3: covariance from exp(2 s) and the unnormalised quaternion (r, x, y, z)
     const float3 var = make_float3(__expf(2.0f * s_scales[3 * r]), __expf(2.0f * s_scales[3 * r + 1]),
                                    __expf(2.0f * s_scales[3 * r + 2]));
-    const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + (idx < n ? idx : first));
     const float qxx = q.y * q.y, qyy = q.z * q.z, qzz = q.w * q.w;
     const float qxy = q.y * q.z, qxz = q.y * q.w, qyz = q.z * q.w;
     const float qrx = q.x * q.y, qry = q.x * q.z, qrz = q.x * q.w;
@@ -211,6 +214,27 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const uint32_t cand = active ? tw * (ty1 - ty0) : 0u;
     if (cand == 0) active = false;
 
+    // P9 prefetch: the 180-byte SH rest rows of the warp (32 consecutive rows = one contiguous 5760-byte span) start
+    // streaming into shared memory now, asynchronously (cp.async, SASS LDGSTS), and are waited for only when the
+    // colour is evaluated, after the exact tile count below
+    const int nrest = cam.total_sh_rest;
+    const int active_bases = min(cam.active_sh_bases, nrest + 1);
+    float* my_rest = s_rest + warp * (32 * 45);
+    bool rest_staged = false;
+    {
+        const int wfirst = first + warp * 32;
+        const int wrows = max(0, min(32, n - wfirst));
+        const float* wsrc = sh_rest + (size_t)wfirst * 45;
+        const uint32_t cand_mask = __ballot_sync(0xffffffffu, active);
+        if (nrest == 15 && active_bases > 4 && __popc(cand_mask) >= 8 && (reinterpret_cast<uintptr_t>(wsrc) & 15u) == 0) {
+            const int n_floats = wrows * 45, n4 = n_floats >> 2;
+            for (int i = lane; i < n4; i += 32) cp_async_16(my_rest + 4 * i, wsrc + 4 * i);
+            cp_async_commit();
+            for (int i = (n4 << 2) + lane; i < n_floats; i += 32) my_rest[i] = __ldg(wsrc + i);
+            rest_staged = true;
+        }
+    }
+
     // P8: exact number of touched tiles
     const float msx = m2x - 0.5f, msy = m2y - 0.5f;
     uint32_t n_touched = 0;
@@ -248,25 +272,28 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     if (idx < n) n_touched_out[idx] = visible ? n_touched : 0u;
     if (visible) tile_info_out[idx] = pack_tile_info(tx0, ty0, tw, cand, tile_mask, n_touched);
 
-    // P9: SH -> RGB for visible Gaussians; the 180-byte rest rows are staged per warp
+    // P10/P11 (first half): reserve the warp's slots in the (depth key, index) list -- one atomic per warp, issued
+    // here so that its round trip overlaps the colour evaluation; order inside the warp is preserved
     const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
-    if (vis_mask == 0) return;
-    const int nrest = cam.total_sh_rest;
-    const int active_bases = min(cam.active_sh_bases, nrest + 1);
-    float* my_rest = s_rest + warp * (32 * 45);
-    const float* rest_ptr = nullptr;
-    if (active_bases > 1) {
-        if (nrest == 15 && active_bases > 4 && __popc(vis_mask) >= 8) {
-            // whole-warp span: 32 consecutive rows of 45 floats are one contiguous 5760-byte block
-            const int wfirst = first + warp * 32;
-            const int wrows = max(0, min(32, n - wfirst));
-            stage_rows<45>(my_rest, sh_rest + (size_t)wfirst * 45, wrows * 45, lane, 32);
-            __syncwarp();
-            rest_ptr = my_rest + lane * 45;
-        } else {
-            rest_ptr = sh_rest + (size_t)(idx < n ? idx : first) * (size_t)(nrest * 3);
+    uint32_t base = 0;
+    if (vis_mask != 0) {
+        const int leader = __ffs((int)vis_mask) - 1;
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, visible ? n_touched : 0u);
+        if (lane == leader) {
+            base = atomicAdd(&counters[kCtrVisible], (uint32_t)__popc(vis_mask));
+            atomicAdd(&counters[kCtrInstances], wsum);
         }
     }
+    // P9: SH -> RGB for visible Gaussians
+    if (rest_staged) {
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    if (vis_mask == 0) return;
+    const float* rest_ptr = nullptr;
+    if (active_bases > 1)
+        rest_ptr = rest_staged ? my_rest + lane * 45 : sh_rest + (size_t)(idx < n ? idx : first) * (size_t)(nrest * 3);
+    base = __shfl_sync(0xffffffffu, base, __ffs((int)vis_mask) - 1);
     if (!visible) return;
     float3 dir = make_float3(mean.x - __ldg(cam.cam_pos), mean.y - __ldg(cam.cam_pos + 1), mean.z - __ldg(cam.cam_pos + 2));
     const float inv_len = rsqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
@@ -283,15 +310,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
                          __uint_as_float((uint32_t)idx));
     recs[idx] = rec;
 
-    // P10/P11: append (depth key, index) -- one atomic per warp, order inside the warp preserved
-    const int leader = __ffs((int)vis_mask) - 1;
-    uint32_t base = 0;
-    const uint32_t wsum = __reduce_add_sync(vis_mask, n_touched);
-    if (lane == leader) {
-        base = atomicAdd(&counters[kCtrVisible], (uint32_t)__popc(vis_mask));
-        atomicAdd(&counters[kCtrInstances], wsum);
-    }
-    base = __shfl_sync(vis_mask, base, leader);
+    // P10/P11 (second half): append (depth key, index)
     const uint32_t slot = base + __popc(vis_mask & ((1u << lane) - 1u));
     depth_keys[slot] = __float_as_uint(depth);
     vis_indices[slot] = (uint32_t)idx;

@@ -92,11 +92,11 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const KeyT* __restrict__ keys,
                                                                 const uint32_t* __restrict__ n_dev,
                                                                 uint32_t* __restrict__ hist, const int shift,
-                                                                const int nbits) {
+                                                                const int nbits, const uint32_t n_cap) {
     __shared__ uint32_t s_hist[kRadixMax];
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t n = *n_dev;
+    const uint32_t n = min(*n_dev, n_cap);
     const uint32_t dmask = (1u << nbits) - 1u;
     for (uint32_t i = blockIdx.x * kSortBlock + threadIdx.x; i < n; i += gridDim.x * kSortBlock)
         atomicAdd(&s_hist[((uint32_t)keys[i] >> shift) & dmask], 1u);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kerne
     const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ hist,
     uint32_t* __restrict__ hist_next, uint32_t* lookback, uint32_t* ticket, const int shift, const int nbits,
-    const int shift_next, const int nbits_next, const int hist_replicas) {
+    const int shift_next, const int nbits_next, const int hist_replicas, const uint32_t n_cap) {
     static_assert(kSortBlock == kRadixMax, "one thread per digit");
     __shared__ uint32_t s_warp_hist[kSortWarps][kRadixMax];
     __shared__ uint32_t s_keys[kSortTile];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kerne
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
-    const uint32_t n = *n_dev;
+    const uint32_t n = min(*n_dev, n_cap);  // n_cap: the host-side bound the buffers were sized for
     // this pass's global digit counts (complete: written by earlier kernels); `hist_replicas` > 1: the
     // producer spread its atomics over that many copies (preprocess.cu)
     uint32_t g = 0;
@@ -493,7 +493,8 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
     }
     if (!pass0_hist) {
         const int hist_grid = tiles < 148 * 4 ? tiles : 148 * 4;
-        radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan.shift[0], plan.nbits[0]);
+        radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan.shift[0], plan.nbits[0],
+                                                                      (uint32_t)n_max);
     }
     KeyT* kin = keys;
     KeyT* kout = keys_alt;
@@ -505,7 +506,7 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
             kin, vin, kout, vout, n_dev, p == 0 && pass0_hist ? pass0_hist : hist + p * kRadixMax,
             last ? nullptr : hist + (p + 1) * kRadixMax, lookback + (size_t)p * tiles * kRadixMax, tickets + p,
             plan.shift[p], plan.nbits[p], last ? 0 : plan.shift[p + 1], last ? 1 : plan.nbits[p + 1],
-            p == 0 && pass0_hist ? pass0_hist_replicas : 1);
+            p == 0 && pass0_hist ? pass0_hist_replicas : 1, (uint32_t)n_max);
         KeyT* tk = kin;
         kin = kout;
         kout = tk;

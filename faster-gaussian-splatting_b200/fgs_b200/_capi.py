@@ -68,6 +68,8 @@ SIGNATURES = {
     'fgs_update_3d_filter': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32] + [C.c_float] * 7 + [_P]),
     'fgs_relocation_adjustment': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     'fgs_add_noise': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, _P]),
+    'fgs_debug_set_capacity_hint': (None, [C.c_int32]),
+    'fgs_debug_get_capacity_hint': (C.c_int32, []),
     'fgs_profile_enable': (None, [C.c_int32]),
     'fgs_profile_read': (C.c_int, [C.c_char_p, C.c_size_t]),
     'fgs_sort_pairs_u32': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,

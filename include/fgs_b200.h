@@ -146,6 +146,12 @@ int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const flo
 void fgs_profile_enable(int32_t on);
 int fgs_profile_read(char* out, size_t out_bytes);
 
+/* fgs_forward / fgs_inference size the instance buffers with the capacity the previous call suggested and
+ * check their own instance count afterwards (one re-run if it did not fit).  These two let the unit tests force
+ * the re-run path (a tiny hint) or the cold path (0). */
+void fgs_debug_set_capacity_hint(int32_t capacity);
+int32_t fgs_debug_get_capacity_hint(void);
+
 /* Building blocks exported for the unit tests (each is one stage of fgs_forward). */
 int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                        const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,

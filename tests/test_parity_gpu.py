@@ -151,6 +151,32 @@ def test_inference_matches_training_forward(cuda_device):
     assert (hwc.permute(2, 0, 1) - img.clamp(0, 1)).abs().max().item() <= 1e-6
 
 
+def test_speculative_instance_capacity_paths(cuda_device):
+    """fgs_forward sizes the instance buffers with the capacity the previous call suggested and checks its own
+    count afterwards: the cold path (no hint), the re-run path (hint too small) and the normal path (hint large
+    enough, also far too large) must give the same image and the same gradients."""
+    from fgs_b200 import _capi, synthetic as syn
+    lib = _capi.load()
+    sc, cam = _scene(20000, 320, 240)
+    st = util.settings_for(cam, bg=(0.1, 0.2, 0.3), device='cuda')
+    gi = syn.make_grad_image(320, 240).cuda()
+    results = []
+    for hint in (0, 1000, 3, None, 50_000_000):
+        if hint is not None:
+            lib.fgs_debug_set_capacity_hint(hint)  # None: whatever the previous call left behind
+        img, grads = _render_mine(sc, st, gi)
+        torch.cuda.synchronize()
+        assert lib.fgs_debug_get_capacity_hint() > 0
+        results.append((img, grads))
+    lib.fgs_debug_set_capacity_hint(0)
+    img0, g0 = results[0]
+    assert img0.abs().sum().item() > 0
+    for img, grads in results[1:]:
+        assert torch.equal(img, img0)  # same instances, same order, same arithmetic
+        for a, b, name in zip(grads, g0, NAMES):
+            assert util.rel_err(a, b) <= 1e-5, name  # float atomics: order of accumulation differs
+
+
 def test_empty_and_degenerate_inputs(cuda_device):
     import fgs_b200
     sc, cam = _scene(64, 64, 48)
