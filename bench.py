@@ -283,11 +283,12 @@ def run_gpu(args, impl):
                 p.grad = None
         opt.state.clear()
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sample_clocks=False):
         reset_state()
         e2e_state['primed'] = -1
-        if sampler:  # sampled from the warm-up on (same load as the timed steps): the timed region alone can be
-            sampler.start()  # shorter than nvidia-smi's start-up + sampling period
+        smp = sampler if (sample_clocks and rank == 0) else None
+        if smp:  # sampled from the warm-up on (same load as the timed steps): the timed region alone can be
+            smp.start()  # shorter than nvidia-smi's start-up + sampling period
         for it in range(warmup):
             fn(it)
         torch.cuda.synchronize()
@@ -301,15 +302,24 @@ def run_gpu(args, impl):
         e1.record()
         torch.cuda.synchronize()
         clocks = None
-        if sampler:
-            # keep the identical load running (untimed) until nvidia-smi has delivered a few samples
+        if sample_clocks:
+            # keep the identical load running (untimed) until nvidia-smi has delivered a few samples.  Every rank
+            # must run the same number of steps (fn contains collectives): rank 0 decides, the others follow.
             t_end, it2 = time.time() + 4.0, warmup + steps
-            while len(sampler.lines) < 5 and time.time() < t_end:
+            while True:
+                more = smp is not None and len(smp.lines) < 5 and time.time() < t_end
+                if dist is not None:
+                    flag = torch.tensor([1 if more else 0], device=dev)
+                    dist.broadcast(flag, 0)
+                    more = bool(int(flag.item()))
+                if not more:
+                    break
                 for _ in range(20):
                     fn(it2)
                     it2 += 1
                 torch.cuda.synchronize()
-            clocks = sampler.stop()
+            if smp:
+                clocks = smp.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -333,7 +343,7 @@ def run_gpu(args, impl):
             ms_d, _ = timed(step_e2e, steps, warmup)
             print(f'[diag] e2e h2d={h2d} d2h={d2h}: {ms_d / steps:.4f} ms/step', file=sys.stderr)
         diag['h2d'] = diag['d2h'] = True
-    ms_total, clocks = timed(step_resident, steps, warmup, sampler)
+    ms_total, clocks = timed(step_resident, steps, warmup, sample_clocks=True)
     ms_e2e, _ = timed(step_e2e, steps, max(warmup, 10))
     extra = {}
     if use_fused:  # also report the strict drop-in path: diff_rasterize backward + separate FusedAdam.step

@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const KeyT* __re
 #ifndef FGS_SORT_MINBLOCKS
 #define FGS_SORT_MINBLOCKS 3
 #endif
+#ifndef FGS_SORT_WAVE_CAP
+#define FGS_SORT_WAVE_CAP 2
+#endif
 
 // groups the lanes of a warp by digit: bit l of the result is set iff lane l holds the same digit
 // (invalid lanes never match a valid one).  One ballot per digit bit; the MATCH.ANY instruction does the
@@ -474,9 +477,9 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, onesweep_kernel<KeyT>, kSortBlock, 0);
         if (occ < 1) occ = 1;
-#ifdef FGS_SORT_WAVE_CAP
+        // two resident blocks per SM measured best on B200 (A/B in profiles/r1b_results.md): fewer links in the
+        // look-back chain at the cost of more tiles per block
         if (occ > FGS_SORT_WAVE_CAP) occ = FGS_SORT_WAVE_CAP;
-#endif
         s_wave = sms * occ;
     }
     const int grid = tiles < s_wave ? tiles : s_wave;
