@@ -41,6 +41,43 @@ def allreduce_gradients(params: Sequence[torch.Tensor], densification_info: torc
         w.wait()
 
 
+def allreduce_and_step(params: Sequence[torch.Tensor], optimizer, densification_info: torch.Tensor | None = None,
+                       group=None, step_group=None) -> None:
+    """`allreduce_gradients` followed by `optimizer.step()`, pipelined: the all-reduces are launched largest tensor
+    first (the same order on every rank) and each tensor's Adam update is queued as soon as ITS all-reduce has
+    completed, so the optimizer kernels of the big tensors run while NCCL is still reducing the small ones.
+    Same result as the two separate calls (the update of a tensor only depends on that tensor's summed gradient).
+
+    `optimizer` is a FusedAdam (one tensor per param group); `step_group(param_group)` overrides how one group is
+    stepped (used by the CPU tests)."""
+    import torch.distributed as dist
+    step_one = step_group if step_group is not None else optimizer.step_group
+    group_of = {id(g['params'][0]): g for g in optimizer.param_groups}
+    for p in params:
+        if id(p) not in group_of:
+            raise KeyError('allreduce_and_step: parameter is not managed by the optimizer')
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    order = sorted(range(len(params)), key=lambda i: -params[i].numel())  # stable: ties keep the caller's order
+    works = []
+    if distributed:
+        for i in order:
+            if params[i].grad is None:
+                raise RuntimeError('allreduce_and_step: parameter without gradient (every rank must render a view)')
+            works.append(dist.all_reduce(params[i].grad, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        if densification_info is not None and densification_info.numel() > 0:
+            works.append(dist.all_reduce(densification_info, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for k, i in enumerate(order):
+        if distributed:
+            works[k].wait()  # stream-ordered: the compute stream waits for this collective only
+        step_one(group_of[id(params[i])])
+    for w in works[len(order):]:
+        w.wait()
+    managed = {id(p) for p in params}
+    for g in optimizer.param_groups:  # groups the caller did not hand in: plain local step
+        if id(g['params'][0]) not in managed:
+            step_one(g)
+
+
 def accumulate_views(render_and_backward, views: Iterable[int]) -> int:
     """Gradient accumulation over this rank's views: calls `render_and_backward(view)` for each, which
     must run forward + loss.backward() so that .grad accumulates.  Returns the number of views."""

@@ -23,14 +23,20 @@ class FusedAdam(torch.optim.Adam):
     @torch.no_grad()
     def step(self) -> None:
         for group in self.param_groups:
-            assert len(group['params']) == 1, 'more than one tensor in group'
-            param = group['params'][0]
-            if param.grad is None or param.numel() == 0:
-                continue
-            state = self._state_for(param)
-            state['step'] += 1
-            _C.adam_step(param.grad, param, state['exp_avg'], state['exp_avg_sq'], state['step'], group['lr'],
-                         *group['betas'], group['eps'])
+            self.step_group(group)
+
+    @torch.no_grad()
+    def step_group(self, group: dict) -> None:
+        """The update of ONE param group (what `step` does for each of them).  The view-parallel path calls it
+        tensor by tensor, as soon as that tensor's gradient all-reduce has completed (fgs_b200/parallel.py)."""
+        assert len(group['params']) == 1, 'more than one tensor in group'
+        param = group['params'][0]
+        if param.grad is None or param.numel() == 0:
+            return
+        state = self._state_for(param)
+        state['step'] += 1
+        _C.adam_step(param.grad, param, state['exp_avg'], state['exp_avg_sq'], state['step'], group['lr'],
+                     *group['betas'], group['eps'])
 
     def group_of(self, param: torch.Tensor) -> dict:
         for group in self.param_groups:

@@ -47,6 +47,72 @@ def _worker(rank, world, port, n_views, out_dict):
     dist.destroy_process_group()
 
 
+def _worker_pipelined(rank, world, port, out_dict):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from fgs_b200 import parallel
+    from oracle import torch_oracle as O
+    shapes = [(40, 3), (40, 3), (40, 4), (40, 1), (40, 1, 3), (40, 15, 3)]
+    lrs = [1e-2, 2e-2, 3e-2, 4e-2, 5e-2, 6e-2]
+
+    def fresh():
+        torch.manual_seed(0)
+        params = [torch.randn(s).requires_grad_(True) for s in shapes]
+        for i, p in enumerate(params):
+            p.grad = torch.randn(p.shape, generator=torch.Generator().manual_seed(100 * rank + i))
+        opt = torch.optim.Adam([{'params': [p], 'lr': lr} for p, lr in zip(params, lrs)], lr=0.0, eps=1e-15)
+        state = {id(p): (torch.zeros_like(p), torch.zeros_like(p)) for p in params}
+        stepped = []
+
+        def step_group(g):
+            p = g['params'][0]
+            m, v = state[id(p)]
+            with torch.no_grad():
+                O.adam_step(p, p.grad, m, v, 1, g['lr'])
+            stepped.append(tuple(p.shape))
+        return params, opt, step_group, stepped
+
+    # pipelined: all-reduce largest first, step each tensor as its reduction completes
+    pa, oa, sga, order = fresh()
+    dens = torch.full((2, 40), float(rank + 1))
+    parallel.allreduce_and_step(pa, oa, densification_info=dens, step_group=sga)
+    # reference: all-reduce everything, then step every group
+    pb, ob, sgb, _ = fresh()
+    parallel.allreduce_gradients(pb)
+    for g in ob.param_groups:
+        sgb(g)
+    out_dict[rank] = ([p.detach().clone() for p in pa], [p.detach().clone() for p in pb], order, dens.clone())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_allreduce_and_step_equals_allreduce_then_step():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_pipelined, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        pa, pb, order, dens = out[rank]
+        for a, b in zip(pa, pb):
+            assert torch.equal(a, b), 'pipelined update differs from all-reduce followed by step'
+        assert order[0] == (40, 15, 3) and len(order) == 6, order  # largest tensor first, every group stepped once
+        assert torch.equal(dens, torch.full((2, 40), 3.0))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b), 'ranks diverged'
+
+
+def test_allreduce_and_step_without_process_group_is_a_plain_step():
+    from fgs_b200 import parallel
+    p = torch.ones(3, requires_grad=True)
+    q = torch.ones(2, requires_grad=True)
+    p.grad, q.grad = torch.full((3,), 2.0), torch.full((2,), 1.0)
+    opt = torch.optim.Adam([{'params': [p], 'lr': 0.1}, {'params': [q], 'lr': 0.1}], lr=0.0)
+    seen = []
+    parallel.allreduce_and_step([p], opt, step_group=lambda g: seen.append(g['params'][0].numel()))
+    assert seen == [3, 2]  # the managed tensor, then the group the caller did not hand in
+
+
 def test_shard_views_partition():
     from fgs_b200 import parallel
     for world in (1, 2, 3, 8):
