@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
                                                             const Rec* __restrict__ recs, Rec* __restrict__ inst_recs,
                                                             uint2* __restrict__ ranges, const uint32_t* __restrict__ n_inst_dev,
                                                             const uint32_t capacity, const uint32_t grid_w) {
-    const uint32_t n_inst = min(*n_inst_dev, capacity);
+    const uint32_t n_inst = bounded_count(n_inst_dev, capacity);
     const uint32_t inst = blockIdx.x * 256u + threadIdx.x;
     if (inst >= n_inst) return;
     const uint32_t prim = __ldg(vals + inst);

@@ -349,8 +349,10 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     if (n_instances < 0) return fail_arg("fgs_forward: more than 2^31 instances");
     if (capacity == 0 || n_instances > capacity) {
         if (capacity > 0) {
-            // the speculative pass ran out of room (its kernels clamp to the capacity, nothing was overrun):
-            // reset what it consumed -- blend queues, sort tickets, work-list length, tile ranges -- and redo it
+            // the speculative pass ran out of room: create_instances skipped every write that did not fit and
+            // the stages behind it saw an empty instance list (bounded_count), so nothing was overrun and nothing
+            // uninitialised was read.  Reset what it consumed -- blend queues, sort tickets, work-list length,
+            // tile ranges -- and redo it with the exact size
             FGS_TRY(cudaMemsetAsync(pl.counters + kCtrTileQueue, 0, sizeof(uint32_t) * (kCtrCount - kCtrTileQueue), stream),
                     "memset counters (redo)");
             FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges (redo)");

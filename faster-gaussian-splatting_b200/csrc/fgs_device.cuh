@@ -67,6 +67,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// Element count of a device-sized array whose buffers were allocated for `capacity` elements.  The instance
+// buffers may be sized speculatively (c_abi.cu); if the true count turns out larger, the producer has skipped
+// every write that did not fit, so part of the array is uninitialised: consumers then treat it as EMPTY (never
+// as "the first `capacity` elements") and the host re-runs the stage with the exact size.
+__device__ __forceinline__ uint32_t bounded_count(const uint32_t* __restrict__ count_dev, uint32_t capacity) {
+    const uint32_t n = *count_dev;
+    return n <= capacity ? n : 0u;
+}
+
 // ---- exact tile test: kernel_utils.cuh:71-114 ("will_primitive_contribute") -------------------------
 // mean is the 2D mean shifted by -0.5 (pixel-centre coordinates), conic = (A, B, C).
 // Rectangle of pixel centres [rx0, rx0 + ext_x] x [ry0, ry0 + ext_y]; the reference uses it with

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kSortBlock) radix_hist_kernel(const KeyT* __re
     __shared__ uint32_t s_hist[kRadixMax];
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t n = min(*n_dev, n_cap);
+    const uint32_t n = bounded_count(n_dev, n_cap);
     const uint32_t dmask = (1u << nbits) - 1u;
     for (uint32_t i = blockIdx.x * kSortBlock + threadIdx.x; i < n; i += gridDim.x * kSortBlock)
         atomicAdd(&s_hist[((uint32_t)keys[i] >> shift) & dmask], 1u);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kSortBlock, FGS_SORT_MINBLOCKS) onesweep_kerne
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_bid = atomicAdd(ticket, 1u);
-    const uint32_t n = min(*n_dev, n_cap);  // n_cap: the host-side bound the buffers were sized for
+    const uint32_t n = bounded_count(n_dev, n_cap);  // n_cap: the host-side bound the buffers were sized for
     // this pass's global digit counts (complete: written by earlier kernels); `hist_replicas` > 1: the
     // producer spread its atomics over that many copies (preprocess.cu)
     uint32_t g = 0;
