@@ -258,6 +258,57 @@ def preprocess(means, scales, rotations, opacities, sh0, sh_rest, s: Settings) -
     return Projected(visible, depth, mean2d, conic, opacity, color, bounds, n_touched)
 
 
+class Binned(NamedTuple):
+    tile_ranges: torch.Tensor   # (T,2) int64: [start, end) of every tile's list inside `instances`
+    instances: torch.Tensor     # (I,) int64: Gaussian index per instance, tile-major, front-to-back inside a tile
+    tile_ids: torch.Tensor      # (I,) int64: tile id (ty * grid_w + tx) per instance, ascending
+
+
+@torch.no_grad()
+def binning(proj: Projected, s: Settings) -> Binned:
+    """Integer restatement of the binning stage: kernels_forward.cuh:224-328 (create_instances_cu: one
+    (tile id, Gaussian index) pair per candidate tile of the Gaussian's tile rectangle, kernel_utils.cuh:61-68, that
+    passes the exact tile test, generated in global depth order), the stable sort by tile id (forward.cu:195-202)
+    and extract_instance_ranges_cu (:330-348).  Depth order = ascending raw float bits of the positive depth
+    (:205, forward.cu:104-110); Gaussians with EXACTLY equal depth are ordered by index here (the reference leaves
+    that order to its atomic slot allocation, :204-208)."""
+    grid_w = (s.width + TILE_W - 1) // TILE_W
+    grid_h = (s.height + TILE_H - 1) // TILE_H
+    vis = proj.visible.nonzero(as_tuple=True)[0]
+    depth_bits = proj.depth[vis].to(torch.float32).view(torch.int32).to(torch.int64)
+    order = vis[torch.argsort(depth_bits, stable=True)]
+    b = proj.screen_bounds[order]
+    tx0, tx1 = b[:, 0] // TILE_W, (b[:, 1] + TILE_W - 1) // TILE_W
+    ty0, ty1 = b[:, 2] // TILE_H, (b[:, 3] + TILE_H - 1) // TILE_H
+    mean2d, conic = proj.mean2d[order], proj.conic[order]
+    tau = torch.log(proj.opacity[order] * MIN_ALPHA_RCP)
+    ms = (mean2d[:, 0] - 0.5, mean2d[:, 1] - 0.5)
+    w, h = tx1 - tx0, ty1 - ty0
+    rank = torch.arange(order.numel())  # position in depth order
+    keys, ranks = [], []
+    for oy in range(int(h.max().item()) if h.numel() else 0):
+        for ox in range(int(w.max().item()) if w.numel() else 0):
+            sel = ((h > oy) & (w > ox)).nonzero(as_tuple=True)[0]
+            if sel.numel() == 0:
+                continue
+            ok = will_primitive_contribute((ms[0][sel], ms[1][sel]), (conic[sel, 0], conic[sel, 1], conic[sel, 2]),
+                                           tx0[sel] + ox, ty0[sel] + oy, tau[sel])
+            sel = sel[ok]
+            keys.append((ty0[sel] + oy) * grid_w + tx0[sel] + ox)
+            ranks.append(rank[sel])
+    if keys:
+        keys, ranks = torch.cat(keys), torch.cat(ranks)
+        # stable sort by tile id of pairs generated in depth order == sort by (tile id, depth rank)
+        perm = torch.argsort(keys * (order.numel() + 1) + ranks)
+        keys, ranks = keys[perm], ranks[perm]
+    else:
+        keys, ranks = torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)
+    counts = torch.bincount(keys, minlength=grid_w * grid_h)
+    ends = torch.cumsum(counts, 0)
+    ranges = torch.stack([ends - counts, ends], dim=1)
+    return Binned(ranges, order[ranks], keys)
+
+
 class RenderOut(NamedTuple):
     image: torch.Tensor           # (3,H,W)
     proj: Projected

@@ -126,3 +126,63 @@ def test_oracle_pruning_scores_matches_reference_golden():
                    cam.center_y, cam.near_plane, cam.far_plane, False)
     got = O.pruning_scores(*sc, s)
     assert util.rel_err(got, torch.from_numpy(z['scores']).double()) <= 5e-3
+
+
+def test_binning_oracle_is_consistent_with_preprocess_and_dense_blend():
+    """The integer restatement of the binning stage (oracle.binning): instance count == sum of the exact tile
+    counts of preprocess, every tile's list is front-to-back, and it is complete w.r.t. the dense blend: every
+    (pixel, Gaussian) pair with alpha >= 1/255 has the Gaussian in the list of the pixel's tile,
+    so the tiled reference algorithm and the dense oracle blend the same pairs."""
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    n, w, h = 600, 96, 60
+    sc = syn.make_scene(n, 3)
+    cam = syn.make_camera(3, w, h)
+    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), 16, w, h, cam.focal_x, cam.focal_y, cam.center_x,
+                   cam.center_y, cam.near_plane, cam.far_plane, False)
+    params = [p.double() for p in sc]
+    proj = O.preprocess(*params, s)
+    bn = O.binning(proj, s)
+    grid_w, grid_h = (w + 15) // 16, (h + 11) // 12
+    assert bn.tile_ranges.shape == (grid_w * grid_h, 2)
+    assert int(bn.instances.numel()) == int(proj.n_touched_tiles[proj.visible].sum()) > 0
+    assert int(bn.tile_ranges[-1, 1]) == bn.instances.numel() and int(bn.tile_ranges[0, 0]) == 0
+    assert torch.equal(bn.tile_ranges[1:, 0], bn.tile_ranges[:-1, 1])          # contiguous, tile-major
+    assert torch.equal(bn.tile_ids, torch.sort(bn.tile_ids).values)
+    member = torch.zeros(grid_w * grid_h, n, dtype=torch.bool)
+    for t in range(grid_w * grid_h):
+        a, b = (int(v) for v in bn.tile_ranges[t])
+        lst = bn.instances[a:b]
+        assert bool(proj.visible[lst].all())
+        d = proj.depth[lst]
+        assert bool((d[1:] >= d[:-1]).all()), 'tile list not front-to-back'
+        assert lst.unique().numel() == lst.numel(), 'a Gaussian twice in one tile list'
+        member[t, lst] = True
+    # dense alphas of all visible Gaussians on all pixels (kernels_forward.cuh:460-465)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing='ij')
+    px, py = xs.reshape(-1) + 0.5, ys.reshape(-1) + 0.5
+    vis = proj.visible.nonzero(as_tuple=True)[0]
+    dx = proj.mean2d[vis, 0:1] - px[None]
+    dy = proj.mean2d[vis, 1:2] - py[None]
+    c = proj.conic[vis]
+    q = -0.5 * (c[:, 0:1] * dx * dx + c[:, 2:3] * dy * dy) - c[:, 1:2] * dx * dy
+    alpha = proj.opacity[vis, None] * torch.exp(torch.clamp(q, max=0.0))
+    tile_of_pixel = ((ys.reshape(-1) // 12) * grid_w + xs.reshape(-1) // 16).long()
+    need = alpha >= (1.0 / 255.0) * (1.0 + 1e-9)  # strictly above the threshold: float edge cases aside
+    listed = member[tile_of_pixel][:, vis].T       # (V, P): Gaussian in the list of the pixel's tile
+    assert int(need.sum()) > 1000
+    assert bool(listed[need].all()), 'a contributing (pixel, Gaussian) pair is missing from the tile lists'
+    # and the lists are tight: most listed pairs' tiles do contain a contributing pixel
+    assert listed.any(dim=1).all()
+
+
+def test_binning_oracle_empty_scene():
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    sc = syn.make_scene(10, 0)
+    cam = syn.make_camera(0, 64, 48)
+    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), 16, 64, 48, cam.focal_x, cam.focal_y, cam.center_x,
+                   cam.center_y, 1e6, 1e7, False)  # everything in front of the near plane
+    proj = O.preprocess(*sc, s)
+    bn = O.binning(proj, s)
+    assert bn.instances.numel() == 0 and int(bn.tile_ranges.sum()) == 0
