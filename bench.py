@@ -158,8 +158,13 @@ def run_gpu(args, impl):
         return None
 
     sc, cams, targets = make_problem(dev)
-    params = [p.to(dev).contiguous().requires_grad_(True) for p in sc]
-    opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
+    peer = None
+    if getattr(args, 'peer_adam', False) and dist is not None and impl == 'mine':
+        peer = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS)
+        params, opt = peer.params, peer
+    else:
+        params = [p.to(dev).contiguous().requires_grad_(True) for p in sc]
+        opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
     bg = torch.zeros(3, device=dev)
     st_dev = [settings_tuple(c, dev, bg) for c in cams]
     gt_dev = [t.to(dev).float().div_(255.0) for t in targets]
@@ -183,7 +188,7 @@ def run_gpu(args, impl):
             img = be.diff_rasterize(*params, empty, rs)
         loss = (img - gt).abs().mean()
         loss.backward()
-        if dist is not None:
+        if dist is not None and peer is None:
             # (parallel.allreduce_and_step pipelines the per-tensor Adam behind the all-reduces; it is covered by the
             # gloo tests but has no NCCL measurement yet, so the benchmark stays on the path that was measured)
             parallel.allreduce_gradients(params)
@@ -283,7 +288,10 @@ def run_gpu(args, impl):
             for p, p0 in zip(params, init_params):
                 p.copy_(p0)
                 p.grad = None
-        opt.state.clear()
+        if peer is not None:
+            peer.reset()
+        else:
+            opt.state.clear()
 
     def timed(fn, steps, warmup, sample_clocks=False):
         reset_state()
@@ -554,6 +562,9 @@ def main():
     ap.add_argument('--impl', default='mine', choices=['mine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--unfused', action='store_true', help='headline on the drop-in path (backward, then FusedAdam.step)')
+    ap.add_argument('--peer-adam', action='store_true',
+                    help='N > 1 only, EXPERIMENTAL: gradient reduction + Adam + parameter broadcast in one kernel over '
+                         'NVLink peer memory (fgs_b200.parallel.PeerAdam) instead of NCCL all-reduce + FusedAdam.step')
     args = ap.parse_args()
     if not torch.cuda.is_available():
         if args.impl == 'reference':

@@ -1,0 +1,216 @@
+// peer_adam.cu -- view-parallel training: gradient reduction + Adam + parameter broadcast in ONE kernel over
+// NVLink / NVSwitch peer memory.
+//
+// No reference counterpart (the reference trains one view per iteration on one GPU, Trainer.py:180,
+// Renderer.py:58-61).  Semantics = gradient accumulation over the batch followed by the
+// reference's dense Adam (adam/src/adam.cu:24-33,54-56): p, m, v after the step equal what every rank would hold
+// after "all-reduce(sum) the gradients, then FusedAdam.step" -- up to the order of the W-term gradient sum, which
+// here is fixed (rank 0 first), so all replicas stay bit-identical.
+//
+// Every rank keeps the six gradient tensors and the six parameter tensors in two flat symmetric-memory buffers
+// (same layout on every rank, every tensor region padded to a multiple of 4 floats) whose peer addresses are known
+// to all ranks.  Rank r owns, of every tensor, the r-th of W contiguous slices (in float4 units).  One launch:
+//     g  = sum over q of  peer_grads[q][i]          (W-1 of the loads cross NVLink)
+//     Adam on (p, m, v)[i] with the rank's SHARD of the moments (Adam's HBM traffic / W, moments memory / W)
+//     peer_params[q][i] = p  for every q             (W-1 of the stores cross NVLink)
+// i.e. reduce-scatter + sharded Adam + all-gather with the same wire bytes as one all-reduce, without staging the
+// reduced gradient in HBM.  The caller brackets the launch with two symmetric-memory barriers (all gradients
+// written before; all parameter stores landed after).
+//
+// STATUS: written at the end of round 1 after the probe in profiles/r1_multigpu.md (peer reads 717 GB/s, NVLS
+// available); compiled, exported, covered on the host side -- NOT yet run on hardware (the round's GPU budget was
+// spent).  fgs_b200.parallel.allreduce_gradients + FusedAdam.step remains the measured default.
+#include <cmath>
+#include <cstdio>
+
+#include "../../include/fgs_b200.h"
+#include "fgs_device.cuh"
+#include "fgs_host.h"
+
+namespace fgs {
+
+namespace {
+
+constexpr int kPeerBlock = 256;
+
+struct PeerAdamArgs {
+    const float4* grads[FGS_MAX_PEERS];  // peer addresses of the flat gradient buffers, index = rank
+    float4* params[FGS_MAX_PEERS];       // peer addresses of the flat parameter buffers
+    float4* exp_avg;                     // this rank's shard of the first moments (float4 index = shard_off + j)
+    float4* exp_avg_sq;
+    uint32_t begin[6];      // first float4 of this rank's slice of tensor t inside the flat buffers
+    uint32_t count[6];      // float4s in that slice
+    uint32_t shard_off[6];  // first float4 of tensor t inside the moment shards
+    float step_size[6];     // lr / (1 - beta1^t)
+    float b2[6];            // 1 / sqrt(1 - beta2^t)
+    float beta1, beta2, eps;
+    int world, rank;
+    uint32_t total;         // sum of count[]
+};
+
+__device__ __forceinline__ float4 ld_peer(const float4* p) {  // L2-only (the data is rewritten by its owner every step)
+    return __ldcg(p);
+}
+
+__device__ __forceinline__ void adam1(float g, float& p, float& m, float& v, float step_size, float beta1, float beta2,
+                                      float eps, float b2) {  // adam.cu:24-33
+    const float g2 = g * g;
+    m = fmaf(beta1, m - g, g);
+    v = fmaf(beta2, v - g2, g2);
+    p -= step_size * m / (sqrtf(v) * b2 + eps);
+}
+
+__global__ void __launch_bounds__(kPeerBlock) peer_adam_kernel(const PeerAdamArgs a) {
+    for (uint32_t idx = blockIdx.x * kPeerBlock + threadIdx.x; idx < a.total; idx += gridDim.x * kPeerBlock) {
+        uint32_t j = idx;
+        int t = 0;
+        while (t < 5 && j >= a.count[t]) {
+            j -= a.count[t];
+            ++t;
+        }
+        const size_t e = (size_t)a.begin[t] + j;
+        // all W gradient loads in flight before the first one is consumed
+        float4 g[FGS_MAX_PEERS];
+#pragma unroll
+        for (int q = 0; q < FGS_MAX_PEERS; ++q)
+            if (q < a.world) g[q] = ld_peer(a.grads[q] + e);
+        float4 p = a.params[a.rank][e];
+        float4 m = a.exp_avg[a.shard_off[t] + j];
+        float4 v = a.exp_avg_sq[a.shard_off[t] + j];
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < FGS_MAX_PEERS; ++q) {  // fixed order: every replica receives the same bits
+            if (q < a.world) {
+                s.x += g[q].x;
+                s.y += g[q].y;
+                s.z += g[q].z;
+                s.w += g[q].w;
+            }
+        }
+        const float ss = a.step_size[t], b2 = a.b2[t];
+        adam1(s.x, p.x, m.x, v.x, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.y, p.y, m.y, v.y, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.z, p.z, m.z, v.z, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.w, p.w, m.w, v.w, ss, a.beta1, a.beta2, a.eps, b2);
+        a.exp_avg[a.shard_off[t] + j] = m;
+        a.exp_avg_sq[a.shard_off[t] + j] = v;
+#pragma unroll
+        for (int q = 0; q < FGS_MAX_PEERS; ++q)
+            if (q < a.world) a.params[q][e] = p;
+    }
+}
+
+// slice of tensor t (count floats, padded to float4s) owned by `rank`: [begin4, begin4 + count4), chunk4 per rank
+void slice_of(uint64_t count, int world, int rank, uint64_t* chunk4, uint64_t* begin4, uint64_t* count4) {
+    const uint64_t n4 = (count + 3) / 4;
+    const uint64_t c = (n4 + (uint64_t)world - 1) / (uint64_t)world;
+    const uint64_t b = (uint64_t)rank * c < n4 ? (uint64_t)rank * c : n4;
+    const uint64_t e = b + c < n4 ? b + c : n4;
+    *chunk4 = c;
+    *begin4 = b;
+    *count4 = e - b;
+}
+
+thread_local char g_peer_err[256] = "";
+
+}  // namespace
+
+}  // namespace fgs
+
+using namespace fgs;
+
+extern "C" {
+
+const char* fgs_peer_last_error(void) { return g_peer_err; }
+
+size_t fgs_peer_adam_shard_floats(const uint64_t counts[6], int32_t world) {
+    if (!counts || world < 1) return 0;
+    uint64_t total4 = 0;
+    for (int t = 0; t < 6; ++t) {
+        uint64_t c, b, n;
+        slice_of(counts[t], world, 0, &c, &b, &n);
+        total4 += c;
+    }
+    return (size_t)(4 * total4);
+}
+
+int fgs_peer_adam_slice(const uint64_t counts[6], int32_t world, int32_t rank, uint64_t begin_floats[6],
+                        uint64_t count_floats[6], uint64_t shard_offset_floats[6]) {
+    if (!counts || world < 1 || rank < 0 || rank >= world) return -1;
+    uint64_t off4 = 0;
+    for (int t = 0; t < 6; ++t) {
+        uint64_t c, b, n;
+        slice_of(counts[t], world, rank, &c, &b, &n);
+        if (begin_floats) begin_floats[t] = 4 * b;
+        if (count_floats) count_floats[t] = 4 * n;
+        if (shard_offset_floats) shard_offset_floats[t] = 4 * off4;
+        off4 += c;
+    }
+    return 0;
+}
+
+int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                       float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
+                       const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
+                       double eps, void* stream) {
+    auto fail = [](const char* msg) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
+        return -1;
+    };
+    if (!peer_grads || !peer_params || !exp_avg_shard || !exp_avg_sq_shard || !offsets || !counts || !step || !lr)
+        return fail("fgs_peer_adam_step: NULL argument");
+    if (world < 1 || world > FGS_MAX_PEERS || rank < 0 || rank >= world) return fail("fgs_peer_adam_step: bad world/rank");
+    PeerAdamArgs a{};
+    for (int q = 0; q < world; ++q) {
+        if (!peer_grads[q] || !peer_params[q]) return fail("fgs_peer_adam_step: NULL peer pointer");
+        if ((reinterpret_cast<uintptr_t>(peer_grads[q]) | reinterpret_cast<uintptr_t>(peer_params[q])) & 15u)
+            return fail("fgs_peer_adam_step: peer buffers must be 16-byte aligned");
+        a.grads[q] = reinterpret_cast<const float4*>(peer_grads[q]);
+        a.params[q] = reinterpret_cast<float4*>(peer_params[q]);
+    }
+    if ((reinterpret_cast<uintptr_t>(exp_avg_shard) | reinterpret_cast<uintptr_t>(exp_avg_sq_shard)) & 15u)
+        return fail("fgs_peer_adam_step: moment shards must be 16-byte aligned");
+    a.exp_avg = reinterpret_cast<float4*>(exp_avg_shard);
+    a.exp_avg_sq = reinterpret_cast<float4*>(exp_avg_sq_shard);
+    uint64_t off4 = 0, total = 0;
+    for (int t = 0; t < 6; ++t) {
+        if (offsets[t] & 3u) return fail("fgs_peer_adam_step: tensor offsets must be multiples of 4 floats");
+        uint64_t c, b, n;
+        slice_of(counts[t], world, rank, &c, &b, &n);
+        if (offsets[t] / 4 + b + n > 0xffffffffull || off4 + c > 0xffffffffull) return fail("fgs_peer_adam_step: buffers too large");
+        a.begin[t] = (uint32_t)(offsets[t] / 4 + b);
+        a.count[t] = (uint32_t)n;
+        a.shard_off[t] = (uint32_t)off4;
+        off4 += c;
+        total += n;
+        // bias corrections in double on the host, adam.cu:54-56
+        a.step_size[t] = (float)(lr[t] / (1.0 - std::pow(beta1, (double)step[t])));
+        a.b2[t] = (float)(1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step[t])));
+    }
+    a.beta1 = (float)beta1;
+    a.beta2 = (float)beta2;
+    a.eps = (float)eps;
+    a.world = world;
+    a.rank = rank;
+    a.total = (uint32_t)total;
+    if (total == 0) return 0;
+    static int s_grid = 0;
+    if (s_grid == 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_adam_kernel, kPeerBlock, 0);
+        s_grid = (sms > 0 ? sms : 1) * (occ > 0 ? occ : 1);  // one persistent wave, grid-stride
+    }
+    const uint64_t want = (total + kPeerBlock - 1) / kPeerBlock;
+    const int grid = want < (uint64_t)s_grid ? (int)want : s_grid;
+    peer_adam_kernel<<<grid, kPeerBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -105,6 +105,24 @@ def _backward_common(image, primitive_buffers, w2c, cam_position, bg_color, grad
     return dev, st, state, w2c_c, pos_c, bg_c, gi, dens_ptr
 
 
+_grad_outputs = None
+
+
+def set_gradient_outputs(tensors) -> None:
+    """Where `backward` writes the six gradients: None (default) = freshly allocated tensors, as the reference does
+    (rasterization_api.cu:127-134); or six preallocated contiguous CUDA float tensors of the parameters' shapes,
+    e.g. views of a symmetric-memory buffer that peer GPUs read (fgs_b200.parallel.PeerAdam).  The returned
+    gradients ARE these tensors (autograd then stores them as .grad without a copy)."""
+    global _grad_outputs
+    if tensors is not None:
+        tensors = list(tensors)
+        if len(tensors) != 6:
+            raise ValueError('set_gradient_outputs: six tensors expected (means, scales, rotations, opacities, sh0, sh_rest)')
+        for t in tensors:
+            _check_param(t, 'gradient output')
+    _grad_outputs = tensors
+
+
 def backward(densification_info, grad_image, image, means, scales, rotations, opacities, sh_coefficients_rest,
              primitive_buffers, tile_buffers, instance_buffers, bucket_buffers, w2c, cam_position, bg_color,
              active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
@@ -116,9 +134,19 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
         proper_antialiasing, n_instances)
     with torch.cuda.device(dev):
         n = means.shape[0]
-        grads = [torch.empty_like(p) for p in (means, scales, rotations, opacities)]
-        g_sh0 = torch.empty((n, 1, 3), dtype=torch.float32, device=dev)
-        g_rest = torch.empty_like(sh_coefficients_rest)
+        if _grad_outputs is None:
+            grads = [torch.empty_like(p) for p in (means, scales, rotations, opacities)]
+            g_sh0 = torch.empty((n, 1, 3), dtype=torch.float32, device=dev)
+            g_rest = torch.empty_like(sh_coefficients_rest)
+        else:
+            # fresh tensor objects over the same memory: autograd adopts a gradient as .grad without a copy only if
+            # nobody else holds a reference to the object it was handed
+            outs = [t.view(t.shape) for t in _grad_outputs]
+            grads, g_sh0, g_rest = outs[:4], outs[4], outs[5]
+            shapes = [tuple(p.shape) for p in (means, scales, rotations, opacities)] + [(n, 1, 3), tuple(sh_coefficients_rest.shape)]
+            for t, shape in zip(_grad_outputs, shapes):
+                if tuple(t.shape) != shape or t.device != dev:
+                    raise RuntimeError(f'gradient output has shape {tuple(t.shape)} on {t.device}, expected {shape} on {dev}')
         scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)
         rc = _lib.fgs_backward(_ptr(gi), _ptr(image), _ptr(means), _ptr(scales), _ptr(rotations), _ptr(opacities),
                                _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c),

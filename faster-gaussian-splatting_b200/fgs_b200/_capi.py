@@ -47,6 +47,7 @@ _P = C.c_void_p
 _PtrArr6 = C.c_void_p * 6
 _I32Arr6 = C.c_int32 * 6
 _F64Arr6 = C.c_double * 6
+_U64Arr6 = C.c_uint64 * 6
 
 # name -> (restype, argtypes); must list every function declared in include/fgs_b200.h
 SIGNATURES = {
@@ -68,6 +69,11 @@ SIGNATURES = {
     'fgs_update_3d_filter': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32] + [C.c_float] * 7 + [_P]),
     'fgs_relocation_adjustment': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     'fgs_add_noise': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, _P]),
+    'fgs_peer_adam_step': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _U64Arr6, _U64Arr6, _I32Arr6, _F64Arr6,
+                                      C.c_double, C.c_double, C.c_double, _P]),
+    'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),
+    'fgs_peer_adam_slice': (C.c_int, [_U64Arr6, C.c_int32, C.c_int32, _U64Arr6, _U64Arr6, _U64Arr6]),
+    'fgs_peer_last_error': (C.c_char_p, []),
     'fgs_debug_set_capacity_hint': (None, [C.c_int32]),
     'fgs_debug_get_capacity_hint': (C.c_int32, []),
     'fgs_profile_enable': (None, [C.c_int32]),

@@ -86,3 +86,100 @@ def accumulate_views(render_and_backward, views: Iterable[int]) -> int:
         render_and_backward(v)
         n += 1
     return n
+
+
+# ---- reduce + Adam + broadcast over NVLink peer memory (EXPERIMENTAL: host-tested, not yet run on hardware) ---------
+def peer_layout(shapes: Sequence[Sequence[int]]) -> tuple[list[int], list[int], int]:
+    """Flat layout shared by every rank: (offsets, counts, total) in floats; every tensor region starts at a
+    multiple of 4 floats and is padded to one (include/fgs_b200.h, fgs_peer_adam_step)."""
+    offsets, counts, off = [], [], 0
+    for shape in shapes:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        offsets.append(off)
+        counts.append(n)
+        off += (n + 3) // 4 * 4
+    return offsets, counts, off
+
+
+class PeerAdam:
+    """Dense Adam over a view-parallel group without an all-reduce: gradients and parameters live in symmetric memory
+    (`torch.distributed._symmetric_memory`), one kernel per step (csrc/peer_adam.cu) sums this rank's slice of every
+    gradient tensor over all peers, applies Adam with the rank's shard of the moments and stores the new parameters
+    to every peer.  Same result as `allreduce_gradients` + `FusedAdam.step` (gradients SUMMED over ranks), replicas
+    bit-identical by construction.
+
+        opt = PeerAdam(initial_parameter_tensors, lrs)       # on every rank, identical values
+        img = diff_rasterize(*opt.params, dens, settings); loss(img).backward(); opt.step(); opt.zero_grad()
+
+    `opt.params` are leaf tensors viewing the symmetric parameter buffer; while the object is alive, the
+    rasterizer's backward writes its gradients straight into the symmetric gradient buffer."""
+
+    def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
+                 group=None) -> None:
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _C, _capi
+        if len(tensors) != 6 or len(lrs) != 6:
+            raise ValueError('PeerAdam: six tensors / learning rates (means, scales, rotations, opacities, sh0, sh_rest)')
+        self._C, self._capi, self._ctypes = _C, _capi, C
+        self._lib = _capi.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = tensors[0].device
+        self.shapes = [tuple(t.shape) for t in tensors]
+        self.offsets, self.counts, total = peer_layout(self.shapes)
+        self.lrs, self.betas, self.eps, self.steps = [float(x) for x in lrs], betas, float(eps), 0
+        self._pbuf = symm.empty(total, dtype=torch.float32, device=dev)
+        self._gbuf = symm.empty(total, dtype=torch.float32, device=dev)
+        self._pbuf.zero_()
+        self._gbuf.zero_()
+        self._ph = symm.rendezvous(self._pbuf, self.group.group_name)
+        self._gh = symm.rendezvous(self._gbuf, self.group.group_name)
+        view = lambda buf, i: buf[self.offsets[i]:self.offsets[i] + self.counts[i]].view(self.shapes[i])
+        with torch.no_grad():
+            for i, t in enumerate(tensors):
+                view(self._pbuf, i).copy_(t)
+        self.params = [view(self._pbuf, i).requires_grad_(True) for i in range(6)]
+        self.grads = [view(self._gbuf, i) for i in range(6)]
+        shard = int(self._lib.fgs_peer_adam_shard_floats((C.c_uint64 * 6)(*self.counts), self.world))
+        self.exp_avg = torch.zeros(shard, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=dev)
+        self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in self._gh.buffer_ptrs])
+        self._pptrs = (C.c_void_p * self.world)(*[int(p) for p in self._ph.buffer_ptrs])
+        _C.set_gradient_outputs(self.grads)
+        self._ph.barrier()  # every replica initialised before anyone steps
+
+    def step(self) -> None:
+        C = self._ctypes
+        for p, g in zip(self.params, self.grads):
+            if p.grad is None:
+                raise RuntimeError('PeerAdam.step: parameter without gradient (every rank must render a view)')
+            if p.grad.data_ptr() != g.data_ptr():  # gradient produced elsewhere (e.g. a regulariser): bring it in
+                g.copy_(p.grad)
+        self.steps += 1
+        stream = torch.cuda.current_stream().cuda_stream
+        self._gh.barrier()  # stream-ordered: every rank's gradients are complete
+        rc = self._lib.fgs_peer_adam_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
+                                          self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),
+                                          (C.c_uint64 * 6)(*self.counts), (C.c_int32 * 6)(*[self.steps] * 6),
+                                          (C.c_double * 6)(*self.lrs), float(self.betas[0]), float(self.betas[1]),
+                                          self.eps, stream)
+        if rc != 0:
+            raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+        self._ph.barrier()  # every rank's parameter stores have landed before the next forward reads them
+
+    def zero_grad(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    def reset(self) -> None:
+        """Fresh optimizer state (moments and step count); the parameters are left alone."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.steps = 0
+
+    def close(self) -> None:
+        self._C.set_gradient_outputs(None)

@@ -140,6 +140,29 @@ int fgs_relocation_adjustment(const float* old_opacities, const float* old_scale
 int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
                   const float* random_samples, float* means, int32_t n_primitives, float current_lr, void* stream);
 
+/* ---- view-parallel training over NVLink peer memory (no reference counterpart: the reference is single-GPU,
+ * Renderer.py:58-61).  EXPERIMENTAL: compiled and host-tested, not yet run on hardware (see csrc/peer_adam.cu).
+ *
+ * Every rank keeps its six gradient tensors in one flat buffer and its six parameter tensors in another, both in
+ * symmetric memory with the same layout on every rank: tensor t occupies floats [offsets[t], offsets[t] + counts[t]),
+ * offsets[t] a multiple of 4, the region padded with zeros to a multiple of 4 floats.  peer_grads[q] / peer_params[q]
+ * are the addresses of rank q's buffers as mapped into THIS process.  One call on every rank, bracketed by
+ * cross-rank barriers (all gradients written before, all parameter stores landed after), leaves on every rank the
+ * parameters that "all-reduce(sum) the gradients, then fgs_adam_step on every tensor" would leave; the Adam moments
+ * are sharded: rank r keeps them only for its slice of every tensor (fgs_peer_adam_slice), packed into two arrays of
+ * fgs_peer_adam_shard_floats(counts, world) floats. */
+#define FGS_MAX_PEERS 8
+int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                       float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
+                       const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1,
+                       double beta2, double eps, void* stream);
+size_t fgs_peer_adam_shard_floats(const uint64_t counts[6], int32_t world);
+/* rank's slice of every tensor: first float (relative to the tensor), number of floats (padding included),
+ * position of the slice's moments inside the shard arrays; any output pointer may be NULL */
+int fgs_peer_adam_slice(const uint64_t counts[6], int32_t world, int32_t rank, uint64_t begin_floats[6],
+                        uint64_t count_floats[6], uint64_t shard_offset_floats[6]);
+const char* fgs_peer_last_error(void);
+
 /* Optional per-kernel timing for bench.py: while enabled every kernel (group) launched by the entry
  * points above is bracketed by CUDA events on the caller's stream.  fgs_profile_read waits for them
  * and writes one "name=milliseconds@start_offset_ms\n" line per launch, in launch order, then clears the list. */

@@ -1,0 +1,116 @@
+"""PeerAdam (csrc/peer_adam.cu, fgs_b200/parallel.py): gradient reduction + Adam + parameter broadcast over NVLink
+peer memory.  Host-side layout arithmetic on CPU; the kernel itself needs two GPUs of one node (skipped otherwise)."""
+import ctypes as C
+import os
+import socket
+
+import pytest
+import torch
+
+SHAPES = [(1003, 3), (1003, 3), (1003, 4), (1003, 1), (1003, 1, 3), (1003, 15, 3)]
+
+
+def test_peer_layout_and_slices_partition_every_tensor():
+    from fgs_b200 import _capi, parallel
+    lib = _capi.load()
+    offsets, counts, total = parallel.peer_layout(SHAPES)
+    assert all(o % 4 == 0 for o in offsets) and total % 4 == 0
+    assert counts == [1003 * 3, 1003 * 3, 1003 * 4, 1003, 1003 * 3, 1003 * 45]
+    for a, b, c in zip(offsets, offsets[1:] + [total], counts):
+        assert b - a == (c + 3) // 4 * 4                      # regions padded to float4s, back to back
+    arr = lambda v: (C.c_uint64 * 6)(*v)
+    for world in (1, 2, 3, 5, 8):
+        shard = lib.fgs_peer_adam_shard_floats(arr(counts), world)
+        covered = [0] * 6
+        for rank in range(world):
+            begin, count, shard_off = arr([0] * 6), arr([0] * 6), arr([0] * 6)
+            assert lib.fgs_peer_adam_slice(arr(counts), world, rank, begin, count, shard_off) == 0
+            for t in range(6):
+                assert begin[t] == covered[t] and begin[t] % 4 == 0 and count[t] % 4 == 0
+                covered[t] += count[t]
+                assert shard_off[t] + count[t] <= shard
+                if t:
+                    assert shard_off[t] >= shard_off[t - 1]
+        assert covered == [(c + 3) // 4 * 4 for c in counts]    # the W slices tile every padded tensor exactly
+        assert shard * world >= sum(covered) and shard % 4 == 0
+    assert lib.fgs_peer_adam_slice(arr(counts), 2, 2, arr([0] * 6), arr([0] * 6), arr([0] * 6)) != 0  # rank outside the world
+
+
+def test_peer_adam_step_rejects_bad_arguments_without_touching_the_gpu():
+    from fgs_b200 import _capi
+    lib = _capi.load()
+    arr64 = lambda v: (C.c_uint64 * 6)(*v)
+    ptrs = (C.c_void_p * 2)(16, 32)
+    rc = lib.fgs_peer_adam_step(ptrs, ptrs, 9, 0, 16, 16, arr64([0] * 6), arr64([4] * 6), (C.c_int32 * 6)(*[1] * 6),
+                                (C.c_double * 6)(*[1e-3] * 6), 0.9, 0.999, 1e-15, None)
+    assert rc != 0 and b'world' in lib.fgs_peer_last_error()
+    rc = lib.fgs_peer_adam_step(ptrs, ptrs, 2, 0, 16, 16, arr64([2, 0, 0, 0, 0, 0]), arr64([4] * 6),
+                                (C.c_int32 * 6)(*[1] * 6), (C.c_double * 6)(*[1e-3] * 6), 0.9, 0.999, 1e-15, None)
+    assert rc != 0 and b'multiples of 4' in lib.fgs_peer_last_error()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    import fgs_b200
+    from fgs_b200 import parallel, synthetic as syn
+    from tests import util
+    n, w, h = 4000, 160, 120
+    sc = syn.make_scene(n, 0)
+    lrs = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]
+    cams = [syn.make_camera(k, w, h) for k in range(4)]
+    gis = [syn.make_grad_image(w, h, seed=k).to(dev) for k in range(4)]
+
+    def settings(k):
+        return fgs_b200.RasterizerSettings(*util.settings_for(cams[k], device=dev))
+
+    # reference semantics: all-reduce (sum) of the gradients, dense FusedAdam on every rank
+    pa = [p.to(dev).clone().requires_grad_(True) for p in sc]
+    oa = fgs_b200.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15)
+    for it in range(2):
+        k = 2 * it + rank
+        fgs_b200.diff_rasterize(*pa, torch.empty(0), settings(k)).backward(gis[k])
+        parallel.allreduce_gradients(pa)
+        oa.step()
+        oa.zero_grad()
+    # one kernel over peer memory
+    ob = parallel.PeerAdam([p.to(dev) for p in sc], lrs)
+    for it in range(2):
+        k = 2 * it + rank
+        fgs_b200.diff_rasterize(*ob.params, torch.empty(0), settings(k)).backward(gis[k])
+        ob.step()
+        ob.zero_grad()
+    torch.cuda.synchronize()
+    ob.close()
+    errs = [util.rel_err(b.detach() - p0.to(dev), a.detach() - p0.to(dev)) for a, b, p0 in zip(pa, ob.params, sc)]
+    flat = torch.cat([p.detach().reshape(-1) for p in ob.params])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    out[rank] = (errs, bool(torch.equal(both[0], both[1])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_adam_equals_allreduce_then_fused_adam_on_two_gpus():
+    if os.environ.get('FGS_TEST_PEER_ADAM') != '1':
+        pytest.skip('opt-in (FGS_TEST_PEER_ADAM=1) until the kernel has had its first run on hardware')
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs of one node')
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for rank in range(2):
+        errs, identical = out[rank]
+        assert identical, 'replicas diverged'
+        assert max(errs) <= 2e-3, errs   # Adam's first steps are sign-like in the gradient: aggregate comparison
