@@ -13,11 +13,21 @@
 #include "../../include/fgs_b200.h"
 #include "fgs_device.cuh"
 #include "fgs_host.h"
+#include "fgs_launch.h"
 
 namespace fgs {
 namespace {
 
 thread_local char g_err[512] = "";
+}  // namespace
+
+// error sink of the self-contained operator files (loss.cu, densify.cu): same text buffer as everything else
+int report_error(int code, const char* where, const char* detail) {
+    std::snprintf(g_err, sizeof(g_err), "%s: %s", where, detail);
+    return code;
+}
+
+namespace {
 
 int fail(cudaError_t e, const char* where) {
     std::snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));

@@ -6,7 +6,9 @@ The eight public names of the reference backend (/root/reference/FasterGSCudaBac
 plus `diff_rasterize_fused` (backward + Adam in one kernel).  Accessing any of them loads
 libfgs_b200.so; there is no fallback if it is missing (ImportError).  The helper modules
 `fgs_b200.synthetic` (benchmark scenes) and `fgs_b200.parallel` (view-parallel all-reduce) are pure
-Python and do not load the library."""
+Python and do not load the library.  Callers either side of the rasterizer: `fgs_b200.loss`
+(L1 + DSSIM fused with its gradient) and `fgs_b200.densification` (fused prune / densify / reorder of the
+parameters and their Adam state)."""
 import importlib
 
 __all__ = ['diff_rasterize', 'diff_rasterize_fused', 'rasterize', 'update_pruning_scores', 'RasterizerSettings',
@@ -17,6 +19,6 @@ def __getattr__(name):
     if name in __all__:
         tb = importlib.import_module('.torch_bindings', __name__)
         return getattr(tb, name)
-    if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel'):
+    if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel', 'loss', 'densification'):
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(f'module {__name__!r} has no attribute {name!r}')

@@ -69,6 +69,11 @@ SIGNATURES = {
     'fgs_update_3d_filter': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32] + [C.c_float] * 7 + [_P]),
     'fgs_relocation_adjustment': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     'fgs_add_noise': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_float, _P]),
+    'fgs_loss_scratch_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'fgs_loss_forward': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
+    'fgs_loss_backward': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P]),
+    'fgs_loss_forward_backward': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P,
+                                             _P]),
     'fgs_peer_adam_step': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _U64Arr6, _U64Arr6, _I32Arr6, _F64Arr6,
                                       C.c_double, C.c_double, C.c_double, _P]),
     'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),

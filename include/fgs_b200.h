@@ -140,6 +140,27 @@ int fgs_relocation_adjustment(const float* old_opacities, const float* old_scale
 int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
                   const float* random_samples, float* means, int32_t n_primitives, float current_lr, void* stream);
 
+/* ---- photometric loss fused with its gradient (the step between forward and backward of a training iteration).
+ * Replaces /root/reference/Loss.py:15-16,26-33 as called from Trainer.py:191-196:
+ *     loss = lambda_l1 * mean|image - target| + lambda_dssim * (1 - mean SSIM(image, target))
+ * with SSIM as in NeRFICG's fused_dssim / the published fused-ssim kernel (11x11 Gaussian window, sigma 1.5, zero
+ * padding, C1 = 0.01^2, C2 = 0.03^2; not in the reference tree: parity pinned by oracle/loss_oracle.py only).
+ * image and grad_image are (3,H,W) float32; target is (3,H,W) float32, or uint8 (value / 255) if target_is_u8.
+ * `scratch` is a caller-owned device buffer of fgs_loss_scratch_bytes(width, height) bytes, 128-byte aligned, that
+ * must stay untouched between fgs_loss_forward and the matching fgs_loss_backward.  loss_out receives three
+ * floats on the device: the weighted loss, the L1 term, the DSSIM term.  grad_loss is a DEVICE pointer to
+ * dL/dloss (NULL: 1); nothing here synchronises with the host. */
+size_t fgs_loss_scratch_bytes(int32_t width, int32_t height);
+int fgs_loss_forward(const float* image, const void* target, int32_t target_is_u8, int32_t width, int32_t height,
+                     float lambda_l1, float lambda_dssim, void* scratch, float* loss_out, void* stream);
+int fgs_loss_backward(const float* image, const void* target, int32_t target_is_u8, int32_t width, int32_t height,
+                      float lambda_l1, float lambda_dssim, const void* scratch, const float* grad_loss,
+                      float* grad_image, void* stream);
+/* forward and backward (with dL/dloss = 1) in one call: what a trainer that calls loss.backward() right away needs */
+int fgs_loss_forward_backward(const float* image, const void* target, int32_t target_is_u8, int32_t width,
+                              int32_t height, float lambda_l1, float lambda_dssim, void* scratch, float* loss_out,
+                              float* grad_image, void* stream);
+
 /* ---- view-parallel training over NVLink peer memory (no reference counterpart: the reference is single-GPU,
  * Renderer.py:58-61).  EXPERIMENTAL: compiled and host-tested, not yet run on hardware (see csrc/peer_adam.cu).
  *

@@ -1,0 +1,291 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  A thread-per-CUDA-thread emulator that lets g++ compile and run the
+// kernel SOURCE of csrc/*.cu on host memory, so that indexing, barrier placement, warp collectives and the
+// C-ABI launch logic of a kernel can be checked in a container without a GPU (and under -fsanitize=thread,
+// which turns a missing __syncthreads() into a reported data race).  It is never part of the product: nothing
+// under faster-gaussian-splatting_b200/ includes it, and the emulated libraries are built into tests/cuda_emu/_build/.
+//
+// Model: blocks run one after another; every CUDA thread of the running block is a std::thread.
+//   __shared__      -> static (one block at a time, so one copy is the block's copy)
+//   __syncthreads() -> std::barrier over the live threads of the block (a thread that returns drops out, as on
+//                      hardware since Volta)
+//   warp collectives (__shfl_*_sync, __ballot_sync, __any_sync, __all_sync, __syncwarp) -> per-warp barrier +
+//                      exchange slots; every live lane of the warp must take part (full-mask use only)
+//   atomics         -> GCC __atomic builtins / CAS loops
+// Not modelled: memory-model subtleties between blocks (blocks are sequential), fast-math rounding, PTX.
+#pragma once
+#ifndef FGS_CUDA_EMU
+#define FGS_CUDA_EMU 1
+#endif
+
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __shared__ static
+#define __constant__ static
+
+struct uint3 {
+    unsigned x, y, z;
+};
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct alignas(8) float2 {
+    float x, y;
+};
+struct float3 {
+    float x, y, z;
+};
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+struct alignas(8) uint2 {
+    unsigned x, y;
+};
+struct alignas(16) uint4 {
+    unsigned x, y, z, w;
+};
+struct alignas(8) int2 {
+    int x, y;
+};
+struct alignas(4) uchar4 {
+    unsigned char x, y, z, w;
+};
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return {x, y}; }
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+    std::memset(p, v, n);
+    return cudaSuccess;
+}
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    std::memcpy(d, s, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+
+namespace cuda_emu {
+
+struct WarpCtx {
+    std::barrier<> bar;
+    uint64_t slot[32];
+    std::atomic<unsigned> live;  // lanes that have not returned yet
+    explicit WarpCtx(int lanes) : bar(lanes), live(lanes >= 32 ? 0xffffffffu : ((1u << lanes) - 1u)) {
+        std::memset(slot, 0, sizeof(slot));
+    }
+};
+struct BlockCtx {
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<WarpCtx>> warps;
+    explicit BlockCtx(int threads) : bar(threads) {
+        for (int w = 0; w * 32 < threads; ++w) warps.emplace_back(new WarpCtx(std::min(32, threads - w * 32)));
+    }
+};
+
+inline thread_local uint3 t_threadIdx, t_blockIdx;
+inline thread_local dim3 t_blockDim, t_gridDim;
+inline thread_local BlockCtx* t_block = nullptr;
+inline thread_local WarpCtx* t_warp = nullptr;
+inline thread_local int t_lane = 0;
+
+template <typename F>
+void launch(dim3 grid, dim3 block, F&& body) {
+    const int threads = (int)(block.x * block.y * block.z);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                BlockCtx ctx(threads);
+                std::vector<std::thread> pool;
+                pool.reserve(threads);
+                for (int t = 0; t < threads; ++t)
+                    pool.emplace_back([&, t] {
+                        t_threadIdx = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+                        t_blockIdx = {bx, by, bz};
+                        t_blockDim = block;
+                        t_gridDim = grid;
+                        t_block = &ctx;
+                        t_warp = ctx.warps[t / 32].get();
+                        t_lane = t % 32;
+                        body();
+                        t_warp->live.fetch_and(~(1u << t_lane));
+                        t_warp->bar.arrive_and_drop();  // a finished thread no longer takes part in barriers
+                        ctx.bar.arrive_and_drop();
+                    });
+                for (auto& th : pool) th.join();
+            }
+}
+
+template <typename T>
+inline T exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "exchange: at most 8 bytes");
+    WarpCtx& w = *t_warp;
+    uint64_t raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    w.slot[t_lane] = raw;
+    w.bar.arrive_and_wait();
+    raw = w.slot[src_lane & 31];
+    w.bar.arrive_and_wait();
+    T r;
+    std::memcpy(&r, &raw, sizeof(T));
+    return r;
+}
+
+}  // namespace cuda_emu
+
+#define threadIdx (cuda_emu::t_threadIdx)
+#define blockIdx (cuda_emu::t_blockIdx)
+#define blockDim (cuda_emu::t_blockDim)
+#define gridDim (cuda_emu::t_gridDim)
+constexpr int warpSize = 32;
+
+inline void __syncthreads() { cuda_emu::t_block->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::t_warp->bar.arrive_and_wait(); }
+
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+    const int base = cuda_emu::t_lane & ~(width - 1);
+    return cuda_emu::exchange(v, base + (src & (width - 1)));
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask, int width = 32) {
+    (void)width;
+    return cuda_emu::exchange(v, cuda_emu::t_lane ^ lane_mask);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned, T v, unsigned delta, int width = 32) {
+    const int src = cuda_emu::t_lane + (int)delta;
+    const bool in = (src & ~(width - 1)) == (cuda_emu::t_lane & ~(width - 1));
+    const T r = cuda_emu::exchange(v, in ? src : cuda_emu::t_lane);
+    return in ? r : v;
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta, int width = 32) {
+    const int src = cuda_emu::t_lane - (int)delta;
+    const bool in = src >= 0 && (src & ~(width - 1)) == (cuda_emu::t_lane & ~(width - 1));
+    const T r = cuda_emu::exchange(v, in ? src : cuda_emu::t_lane);
+    return in ? r : v;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = pred ? 1u : 0u;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) r |= (unsigned)(w.slot[l] & 1u) << l;
+    r &= w.live.load();  // a lane that has returned does not vote
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
+
+// ---- atomics --------------------------------------------------------------------------------------------------
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(p);
+    uint32_t old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+    float f;
+    do {
+        std::memcpy(&f, &old, 4);
+        f += v;
+        std::memcpy(&want, &f, 4);
+    } while (!__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    std::memcpy(&f, &old, 4);
+    return f;
+}
+inline double atomicAdd(double* p, double v) {
+    uint64_t* u = reinterpret_cast<uint64_t*>(p);
+    uint64_t old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+    double f;
+    do {
+        std::memcpy(&f, &old, 8);
+        f += v;
+        std::memcpy(&want, &f, 8);
+    } while (!__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    std::memcpy(&f, &old, 8);
+    return f;
+}
+inline unsigned atomicMin(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+inline int atomicMin(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+    return old;
+}
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+
+// ---- intrinsics -----------------------------------------------------------------------------------------------
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline float __expf(float x) { return std::exp(x); }
+inline float __logf(float x) { return std::log(x); }
+inline float __log2f(float x) { return std::log2(x); }
+inline float __powf(float a, float b) { return std::pow(a, b); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+inline float __saturatef(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+// fabsf / fmaxf / fminf / fmaf / expf ...: the C library's global-namespace functions (<cmath>)
+template <typename T>
+inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T>
+inline T max(T a, T b) { return a < b ? b : a; }
+inline unsigned min(unsigned a, int b) { return min(a, (unsigned)b); }
+inline unsigned min(int a, unsigned b) { return min((unsigned)a, b); }
+
+// kernel launch through a macro shared with the nvcc build (csrc/fgs_launch.h)
+#define FGS_LAUNCH(kernel, grid, block, stream, ...) cuda_emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
