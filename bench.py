@@ -179,6 +179,9 @@ def run_gpu(args, impl):
         return (it * world + rank) % N_VIEWS
 
     use_fused = (impl == 'mine') and dist is None and not args.unfused
+    fused_loss = (impl == 'mine') and getattr(args, 'fused_loss', False)
+    if fused_loss:
+        from fgs_b200 import loss as loss_mod
 
     def train_view(st, gt, fused):
         rs = be.RasterizerSettings(*st)
@@ -186,8 +189,15 @@ def run_gpu(args, impl):
             img = be.diff_rasterize_fused(*params, empty, rs, opt)
         else:
             img = be.diff_rasterize(*params, empty, rs)
-        loss = (img - gt).abs().mean()
-        loss.backward()
+        if fused_loss:  # csrc/loss.cu: loss value and d loss / d image in one kernel, uint8 or float target
+            terms, grad_image = loss_mod.l1_dssim_loss_and_grad(img.detach(), gt, 1.0, 0.0)
+            img.backward(grad_image)
+            loss = terms[0]
+        else:
+            if gt.dtype == torch.uint8:
+                gt = gt.float().div_(255.0)  # uint8 -> float on the device
+            loss = (img - gt).abs().mean()
+            loss.backward()
         if dist is not None and peer is None:
             # (parallel.allreduce_and_step pipelines the per-tensor Adam behind the all-reduces; it is covered by the
             # gloo tests but has no NCCL measurement yet, so the benchmark stays on the path that was measured)
@@ -274,9 +284,13 @@ def run_gpu(args, impl):
         k = view_of(it)
         torch.cuda.current_stream().wait_event(b['ready'])
         st = (b['w2c'], b['pos']) + st_dev[k][2:]
-        gt = b['gt8'].float().div_(255.0)  # uint8 -> float on the device
-        b['free'].record(torch.cuda.current_stream())
-        loss = train_view(st, gt, use_fused if fused is None else fused)
+        if fused_loss:  # the loss kernel reads the uint8 staging buffer itself: released after the step
+            loss = train_view(st, b['gt8'], use_fused if fused is None else fused)
+            b['free'].record(torch.cuda.current_stream())
+        else:
+            gt = b['gt8'].float().div_(255.0)  # uint8 -> float on the device
+            b['free'].record(torch.cuda.current_stream())
+            loss = train_view(st, gt, use_fused if fused is None else fused)
         return read_loss(it, loss) if diag['d2h'] else loss
 
     init_params = [p.detach().clone() for p in params]
@@ -390,6 +404,7 @@ def run_gpu(args, impl):
                    'parallelism': f'view-dp{world}' if world > 1 else 'single',
                    'optimizer_path': ('fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' if use_fused
                                       else 'backward, then FusedAdam.step'),
+                   'loss_path': 'fused L1 kernel (csrc/loss.cu)' if fused_loss else 'torch ops: (img - gt).abs().mean()',
                    'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
         'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
                 'h2d_bytes_per_step': 3 * WIDTH * HEIGHT + 64 + 12, 'd2h_bytes_per_step': 4,
@@ -562,6 +577,9 @@ def main():
     ap.add_argument('--impl', default='mine', choices=['mine', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--unfused', action='store_true', help='headline on the drop-in path (backward, then FusedAdam.step)')
+    ap.add_argument('--fused-loss', action='store_true',
+                    help='EXPERIMENTAL (not yet measured on hardware): L1 loss and its gradient from csrc/loss.cu instead '
+                         'of the seven torch kernels of (img - gt).abs().mean() + backward')
     ap.add_argument('--peer-adam', action='store_true',
                     help='N > 1 only, EXPERIMENTAL: gradient reduction + Adam + parameter broadcast in one kernel over '
                          'NVLink peer memory (fgs_b200.parallel.PeerAdam) instead of NCCL all-reduce + FusedAdam.step')

@@ -141,15 +141,15 @@ def test_loss_gpu_full_size_properties(cuda_device):
     # uint8 target == the same target converted by torch
     assert float((grad - grad_f).abs().sum() / grad_f.abs().sum()) <= 1e-5 and torch.allclose(terms, terms_f, rtol=0, atol=1e-6)
     assert abs(float(terms[1]) - float((image - tf).abs().mean())) <= 1e-6
-    # SSIM(x, x) == 1 -> DSSIM 0 and zero DSSIM gradient
+    # SSIM(x, x) == 1 -> DSSIM 0 and zero DSSIM gradient (up to fp32 cancellation in E[x^2] - mu^2)
     t2, g2 = L.l1_dssim_loss_and_grad(tf, tf, 0.0, 1.0)
-    assert abs(float(t2[2])) <= 1e-6 and float(g2.abs().max()) <= 1e-9
-    # directional derivative of the loss along a random direction == <grad, direction> (fp32 finite difference)
-    d = torch.randn(3, h, w, generator=g).to(cuda_device)
-    eps = 1e-2
+    assert abs(float(t2[2])) <= 5e-6 and float(g2.abs().max()) <= 1e-9
+    # directional derivative along sign(grad) == sum |grad| (central difference of the fp32 loss; signal ~3, noise ~1e-4)
+    _, gd = L.l1_dssim_loss_and_grad(image, target, 0.0, 1.0)
+    d = torch.sign(gd)
+    eps = 2e-3
     lp, _ = L.l1_dssim_loss_and_grad(image + eps * d, target, 0.0, 1.0)
     lm, _ = L.l1_dssim_loss_and_grad(image - eps * d, target, 0.0, 1.0)
-    _, gd = L.l1_dssim_loss_and_grad(image, target, 0.0, 1.0)
     fd = (float(lp[0]) - float(lm[0])) / (2 * eps)
-    an = float((gd.double() * d.double()).sum())
-    assert abs(fd - an) <= 5e-2 * max(abs(an), 1e-6), (fd, an)
+    an = float(gd.double().abs().sum())
+    assert abs(fd - an) <= 1e-2 * an, (fd, an)
