@@ -6,6 +6,9 @@
 #ifndef FGS_CUDA_EMU
 #include <cuda_runtime.h>
 #define FGS_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// same launch; tells the emulator that the kernel has no barrier and no warp collective, so it may run the CUDA
+// threads one after the other instead of as host threads
+#define FGS_LAUNCH_SERIAL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
 namespace fgs {

@@ -43,6 +43,12 @@ class ForwardState(C.Structure):
     ]
 
 
+class RowTensor(C.Structure):
+    """struct fgs_row_tensor"""
+    _fields_ = [('src', C.c_void_p), ('appended', C.c_void_p), ('dst', C.c_void_p), ('row_floats', C.c_int32),
+                ('role', C.c_int32)]
+
+
 _P = C.c_void_p
 _PtrArr6 = C.c_void_p * 6
 _I32Arr6 = C.c_int32 * 6
@@ -74,6 +80,14 @@ SIGNATURES = {
     'fgs_loss_backward': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P, _P]),
     'fgs_loss_forward_backward': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P,
                                              _P]),
+    'fgs_gather_rows': (C.c_int, [C.POINTER(RowTensor), C.c_int32, _P, C.c_int64, C.c_int64, _P, _P, _P, _P]),
+    'fgs_zero_rows': (C.c_int, [_P, _P, C.c_int32, _P, C.c_int64, _P]),
+    'fgs_densify_scratch_bytes': (C.c_size_t, [C.c_int32]),
+    'fgs_plan_count': (C.c_int, [_P, C.c_int32, _P, C.POINTER(C.c_uint32), _P]),
+    'fgs_plan_emit': (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    'fgs_adc_flags': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, _P, _P]),
+    'fgs_morton_keys': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    'fgs_gather_u32': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
     'fgs_peer_adam_step': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _U64Arr6, _U64Arr6, _I32Arr6, _F64Arr6,
                                       C.c_double, C.c_double, C.c_double, _P]),
     'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),

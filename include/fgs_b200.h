@@ -161,6 +161,68 @@ int fgs_loss_forward_backward(const float* image, const void* target, int32_t ta
                               int32_t height, float lambda_l1, float lambda_dssim, void* scratch, float* loss_out,
                               float* grad_image, void* stream);
 
+/* ---- densification / pruning / reordering of the Gaussians together with their Adam state (csrc/densify.cu).
+ * Replaces the torch-op implementations in /root/reference/Model.py:276-310 (prune, sort), :312-366
+ * (adaptive_density_control), :340-347,:436-443 (extend_param_groups), :406,:449 (reset_state), :459-463
+ * (apply_morton_ordering); NeRFICG's Optim.adam_utils / CudaUtils.MortonEncoding behind them are not in the
+ * reference tree (behaviour restated from the call sites; Morton code: 21 bits per axis of the position normalised
+ * to the bounding box, x most significant).
+ *
+ * Everything is "build a row plan, then move rows".  A plan entry (int64, one per OUTPUT row) is
+ *     bits 0..31 source row | bits 32..33 kind | bits 34..63 row of the split's normal sample
+ * kind 0 = existing Gaussian (Adam state moves with it), 1 = clone (state zero), 2 / 3 = first / second child of a
+ * split (mean displaced by R(q/|q|) (exp(s) * z), scale log(0.625 exp(s)), state zero).  A torch int64 index tensor
+ * is therefore a valid plan (kind 0).  All pointers are device pointers unless named *_host. */
+#define FGS_MAX_ROW_TENSORS 24
+#define FGS_ROW_COPY 0   /* rows are copied whatever the kind (rotations, opacities, SH, auxiliary per-Gaussian data) */
+#define FGS_ROW_STATE 1  /* Adam moment: copied for kind 0, zero otherwise */
+#define FGS_ROW_MEANS 2  /* (N,3) means: split children are displaced */
+#define FGS_ROW_SCALES 3 /* (N,3) raw log-scales: split children are shrunk by 1.6 */
+typedef struct fgs_row_tensor {
+    const float* src;      /* (N_in, row_floats) */
+    const float* appended; /* rows for output rows >= n_copy, (n_out - n_copy, row_floats); NULL = zeros */
+    float* dst;            /* (n_out, row_floats) */
+    int32_t row_floats;
+    int32_t role;          /* FGS_ROW_* */
+} fgs_row_tensor;
+
+/* dst[j] = row plan[j] of src for j < n_copy (plan == NULL: row j), appended[j - n_copy] (or zeros) behind; every
+ * tensor in ONE launch.  split_* are only read if the plan contains kinds 2 / 3: the SOURCE scales (N_in,3),
+ * rotations (N_in,4) and the (2 * n_split, 3) standard-normal samples (Model.py:332 draws them with randn_like). */
+int fgs_gather_rows(const fgs_row_tensor* tensors_host, int32_t n_tensors, const int64_t* plan, int64_t n_out,
+                    int64_t n_copy, const float* split_scales, const float* split_rotations,
+                    const float* split_samples, void* stream);
+/* tensors[t][index[k]] = 0 rows (Adam state reset, Model.py:406,449) */
+int fgs_zero_rows(float* const* tensors_host, const int32_t* row_floats_host, int32_t n_tensors, const int64_t* index,
+                  int64_t n_index, void* stream);
+
+/* Order-preserving plans from one flags byte per Gaussian: bit 0 keep the Gaussian, bit 1 keep a clone of it,
+ * bit 2 keep its two split children, bit 3 it is split (kept or not: fixes the sample rows).  Output order =
+ * the reference's: kept originals, kept clones, first children, second children, each in index order.
+ * fgs_plan_count returns (and waits for) the four totals {kept, clones, split pairs kept, splits} -- the one host
+ * synchronisation, needed to allocate the outputs (n_out = kept + clones + 2 * pairs); fgs_plan_emit then writes the
+ * n_out plan entries.  `scratch`: fgs_densify_scratch_bytes(n) bytes, untouched between the two calls.
+ * A boolean mask (uint8 0/1) is a flags array with only bit 0: prune(mask) = count + emit + gather. */
+size_t fgs_densify_scratch_bytes(int32_t n_primitives);
+int fgs_plan_count(const uint8_t* flags, int32_t n_primitives, void* scratch, uint32_t totals_host[4], void* stream);
+int fgs_plan_emit(const uint8_t* flags, int32_t n_primitives, const void* scratch, int64_t* plan, void* stream);
+/* Model.py:314-321,359-365: flags of adaptive_density_control.  densification_info is (2,N); the thresholds are the
+ * reference's host-side scalars: small_scale_log = log(percent_dense * extent), min_opacity_logit =
+ * log(min_opacity / (1 - min_opacity)), large_scale_log = log(0.1 * extent) (only used if prune_large). */
+int fgs_adc_flags(const float* densification_info, const float* scales, const float* rotations, const float* opacities,
+                  int32_t n_primitives, float grad_threshold, float small_scale_log, float min_opacity_logit,
+                  int32_t prune_large, float large_scale_log, uint8_t* flags, void* stream);
+
+/* Morton codes of the means (any output may be NULL): the 63-bit code, its low / high 32-bit halves as radix-sort keys
+ * and the identity permutation to sort along.  Two stable fgs_sort_pairs_u32 passes (low half, then -- after
+ * fgs_gather_u32 of the high half into the new order -- high half) give the Morton order.
+ * `scratch`: fgs_densify_scratch_bytes(n) bytes. */
+int fgs_morton_keys(const float* means, int32_t n_primitives, void* scratch, int64_t* codes, uint32_t* key_lo,
+                    uint32_t* key_hi, uint32_t* iota, void* stream);
+/* dst[i] = src[index[i]] (dst may be NULL) and / or index_as_i64[i] = index[i] (may be NULL) */
+int fgs_gather_u32(const uint32_t* src, const uint32_t* index, uint32_t* dst, int64_t* index_as_i64, int32_t n,
+                   void* stream);
+
 /* ---- view-parallel training over NVLink peer memory (no reference counterpart: the reference is single-GPU,
  * Renderer.py:58-61).  EXPERIMENTAL: compiled and host-tested, not yet run on hardware (see csrc/peer_adam.cu).
  *

@@ -140,6 +140,29 @@ void launch(dim3 grid, dim3 block, F&& body) {
             }
 }
 
+// Kernels without barriers or warp collectives (declared so at the launch site with FGS_LAUNCH_SERIAL): every CUDA
+// thread runs to completion on the calling host thread, one after the other.  A barrier inside such a kernel
+// dereferences the null block context: the declaration is checked, not trusted.
+template <typename F>
+void launch_serial(dim3 grid, dim3 block, F&& body) {
+    t_block = nullptr;
+    t_warp = nullptr;
+    t_blockDim = block;
+    t_gridDim = grid;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                t_blockIdx = {bx, by, bz};
+                for (unsigned tz = 0; tz < block.z; ++tz)
+                    for (unsigned ty = 0; ty < block.y; ++ty)
+                        for (unsigned tx = 0; tx < block.x; ++tx) {
+                            t_threadIdx = {tx, ty, tz};
+                            t_lane = (int)((tx + block.x * (ty + block.y * tz)) % 32);
+                            body();
+                        }
+            }
+}
+
 template <typename T>
 inline T exchange(T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "exchange: at most 8 bytes");
@@ -269,6 +292,8 @@ inline float __fdividef(float a, float b) { return a / b; }
 inline float __frcp_rn(float a) { return 1.0f / a; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
 inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
 inline float __saturatef(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
@@ -289,3 +314,4 @@ inline unsigned min(int a, unsigned b) { return min((unsigned)a, b); }
 
 // kernel launch through a macro shared with the nvcc build (csrc/fgs_launch.h)
 #define FGS_LAUNCH(kernel, grid, block, stream, ...) cuda_emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define FGS_LAUNCH_SERIAL(kernel, grid, block, stream, ...) cuda_emu::launch_serial((grid), (block), [&] { kernel(__VA_ARGS__); })
