@@ -20,12 +20,15 @@
 // STATUS: written at the end of round 1 after the probe in profiles/r1_multigpu.md (peer reads 717 GB/s, NVLS
 // available); compiled, exported, covered on the host side -- NOT yet run on hardware (the round's GPU budget was
 // spent).  fgs_b200.parallel.allreduce_gradients + FusedAdam.step remains the measured default.
+//
+// This file is also compiled by g++ against tests/cuda_emu/cuda_emu.h (test-only emulator) -- see fgs_launch.h: the
+// slicing / sharding logic is checked on the CPU by running W "ranks" one after the other on host buffers.
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 
 #include "../../include/fgs_b200.h"
-#include "fgs_device.cuh"
-#include "fgs_host.h"
+#include "fgs_launch.h"
 
 namespace fgs {
 
@@ -204,7 +207,8 @@ int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params
     }
     const uint64_t want = (total + kPeerBlock - 1) / kPeerBlock;
     const int grid = want < (uint64_t)s_grid ? (int)want : s_grid;
-    peer_adam_kernel<<<grid, kPeerBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    auto k = peer_adam_kernel;
+    FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step: %s", cudaGetErrorString(e));

@@ -88,6 +88,11 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }  // a 3-SM "GPU"
+template <typename K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 2; return cudaSuccess; }
 
 namespace cuda_emu {
 
@@ -284,6 +289,8 @@ inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 // ---- intrinsics -----------------------------------------------------------------------------------------------
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline T __ldcg(const T* p) { return *p; }
 inline float __expf(float x) { return std::exp(x); }
 inline float __logf(float x) { return std::log(x); }
 inline float __log2f(float x) { return std::log2(x); }

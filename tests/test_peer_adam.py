@@ -49,6 +49,79 @@ def test_peer_adam_step_rejects_bad_arguments_without_touching_the_gpu():
     assert rc != 0 and b'multiples of 4' in lib.fgs_peer_last_error()
 
 
+@pytest.mark.parametrize('world', [1, 2, 3, 8])
+def test_peer_adam_kernel_emulated_ranks(world):
+    """The kernel SOURCE of csrc/peer_adam.cu under the test-only CUDA emulator (tests/cuda_emu): W "ranks" with their own
+    gradient / parameter buffers in host memory run one after the other (every rank writes a disjoint slice of every
+    peer's parameters, so sequential == concurrent), two steps; every replica must hold the parameters that
+    sum-of-gradients + dense Adam produces, bit-identical across replicas, and the sharded moments must reassemble
+    to the dense ones."""
+    import numpy as np
+    from fgs_b200 import parallel
+    from tests import cuda_emu
+    lib = cuda_emu.build('peer_adam')
+    lib.fgs_peer_adam_shard_floats.restype = C.c_size_t
+    shapes = [(101, 3), (101, 3), (101, 4), (101, 1), (101, 1, 3), (101, 15, 3)]
+    offsets, counts, total = parallel.peer_layout(shapes)
+    arr64 = lambda v: (C.c_uint64 * 6)(*v)
+    rng = np.random.default_rng(world)
+    lrs, b1, b2, eps = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4], 0.9, 0.999, 1e-15
+    p0 = np.zeros(total, dtype=np.float32)
+    for o, c in zip(offsets, counts):
+        p0[o:o + c] = rng.standard_normal(c).astype(np.float32)
+    params = [p0.copy() for _ in range(world)]
+    shard = lib.fgs_peer_adam_shard_floats(arr64(counts), world)
+    m_sh = [np.zeros(shard, dtype=np.float32) for _ in range(world)]
+    v_sh = [np.zeros(shard, dtype=np.float32) for _ in range(world)]
+    # dense reference in float32, gradients summed rank 0 first
+    p_ref, m_ref, v_ref = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for step in (1, 2):
+        grads = []
+        for q in range(world):
+            g = np.zeros(total, dtype=np.float32)
+            for o, c in zip(offsets, counts):
+                g[o:o + c] = (rng.standard_normal(c) * 1e-3).astype(np.float32)
+            grads.append(g)
+        gp = (C.c_void_p * world)(*[g.ctypes.data for g in grads])
+        pp = (C.c_void_p * world)(*[p.ctypes.data for p in params])
+        for rank in range(world):
+            rc = lib.fgs_peer_adam_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data), C.c_void_p(v_sh[rank].ctypes.data),
+                                        arr64(offsets), arr64(counts), (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs),
+                                        C.c_double(b1), C.c_double(b2), C.c_double(eps), None)
+            assert rc == 0, lib.fgs_peer_last_error()
+        gsum = np.zeros(total, dtype=np.float32)
+        for g in grads:
+            gsum = gsum + g
+        for t, (o, c) in enumerate(zip(offsets, counts)):
+            sl = slice(o, o + c)
+            g = gsum[sl]
+            m_ref[sl] = np.float32(b1) * (m_ref[sl] - g) + g
+            v_ref[sl] = np.float32(b2) * (v_ref[sl] - g * g) + g * g
+            ss = np.float32(lrs[t] / (1.0 - b1 ** step))
+            bb = np.float32(1.0 / np.sqrt(1.0 - b2 ** step))
+            p_ref[sl] = p_ref[sl] - ss * m_ref[sl] / (np.sqrt(v_ref[sl]) * bb + np.float32(eps))
+        for q in range(1, world):
+            assert np.array_equal(params[q], params[0]), f'replica {q} differs after step {step}'
+        for o, c, lr in zip(offsets, counts, lrs):
+            # fma vs two roundings in the moments, amplified where beta1 (m - g) + g cancels: a fraction of one update
+            np.testing.assert_allclose(params[0][o:o + c], p_ref[o:o + c], rtol=2e-6, atol=5e-7 + 1e-4 * lr)
+    # the moment shards, reassembled through fgs_peer_adam_slice, are the dense moments
+    m_full, v_full = np.zeros_like(p0), np.zeros_like(p0)
+    for rank in range(world):
+        begin, count, soff = arr64([0] * 6), arr64([0] * 6), arr64([0] * 6)
+        assert lib.fgs_peer_adam_slice(arr64(counts), world, rank, begin, count, soff) == 0
+        for t in range(6):
+            lo = offsets[t] + begin[t]
+            m_full[lo:lo + count[t]] = m_sh[rank][soff[t]:soff[t] + count[t]]
+            v_full[lo:lo + count[t]] = v_sh[rank][soff[t]:soff[t] + count[t]]
+    # aggregate comparison: fma vs two roundings where beta (x - g) + g cancels gives isolated 1e-4 relative outliers
+    for o, c in zip(offsets, counts):
+        for got, want in ((m_full, m_ref), (v_full, v_ref)):
+            # v = beta2 (v - g^2) + g^2 loses three digits to cancellation (beta2 = 0.999), in the reference as here
+            assert np.abs(got[o:o + c] - want[o:o + c]).sum() <= 2e-4 * np.abs(want[o:o + c]).sum()
+        assert np.all(m_full[o + c:o + (c + 3) // 4 * 4] == 0)  # the padding of every tensor region stays zero
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
