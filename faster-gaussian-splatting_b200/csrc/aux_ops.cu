@@ -113,7 +113,7 @@ cudaError_t launch_update_3d_filter(const float* positions, const float* w2c, fl
     const float ox = center_x - 0.5f * wf, oy = center_y - 0.5f * hf;
     const float left = (-bf * wf - ox) / focal_x, right = (bf * wf - ox) / focal_x;
     const float top = (-bf * hf - oy) / focal_y, bottom = (bf * hf - oy) / focal_y;
-    filter3d_kernel<<<div_up(n, kAuxBlock), kAuxBlock, 0, stream>>>(positions, w2c, filter_3d, visibility, n, left, right,
+    FGS_LAUNCH_SERIAL(filter3d_kernel, div_up(n, kAuxBlock), kAuxBlock, stream, positions, w2c, filter_3d, visibility, n, left, right,
                                                                   top, bottom, near_plane, distance2filter);
     return cudaGetLastError();
 }
@@ -134,7 +134,7 @@ cudaError_t launch_relocation(const float* old_opacities, const float* old_scale
         if (e != cudaSuccess) return e;
         g_reloc_ready = true;
     }
-    relocation_kernel<<<div_up(n, kAuxBlock), kAuxBlock, 0, stream>>>(old_opacities, old_scales, n_samples, new_opacities,
+    FGS_LAUNCH_SERIAL(relocation_kernel, div_up(n, kAuxBlock), kAuxBlock, stream, old_opacities, old_scales, n_samples, new_opacities,
                                                                     new_scales, n);
     return cudaGetLastError();
 }
@@ -142,7 +142,7 @@ cudaError_t launch_relocation(const float* old_opacities, const float* old_scale
 cudaError_t launch_add_noise(const float* raw_scales, const float* raw_rotations, const float* raw_opacities,
                              const float* noise, float* means, int n, float lr, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    add_noise_kernel<<<div_up(n, kAuxBlock), kAuxBlock, 0, stream>>>(raw_scales, raw_rotations, raw_opacities, noise, means,
+    FGS_LAUNCH_SERIAL(add_noise_kernel, div_up(n, kAuxBlock), kAuxBlock, stream, raw_scales, raw_rotations, raw_opacities, noise, means,
                                                                    n, lr);
     return cudaGetLastError();
 }

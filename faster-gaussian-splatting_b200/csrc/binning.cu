@@ -177,7 +177,7 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
     if (n_max <= 0) return cudaSuccess;
     static_assert(kInstBlock == kRadixMax, "one thread per histogram bin");
     const uint32_t mask = (1u << key_hist_bits) - 1u;
-    create_instances_kernel<KeyT><<<div_up(n_max, kInstBlock), kInstBlock, 0, stream>>>(
+    FGS_LAUNCH(create_instances_kernel<KeyT>, div_up(n_max, kInstBlock), kInstBlock, stream,
         sorted_idx, offsets, sorted_info, inst_keys, inst_vals, n_vis_dev, grid_w, key_hist, mask, big_count, big_prims,
         big_offsets, (uint32_t)capacity);
     static int s_sms = 0;
@@ -188,7 +188,7 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
         if (s_sms < 1) s_sms = 1;
     }
     const int big_grid = n_max < 2 * s_sms ? n_max : 2 * s_sms;
-    create_instances_big_kernel<KeyT><<<big_grid, kInstBlock, 0, stream>>>(recs, inst_keys, inst_vals, grid_w, key_hist,
+    FGS_LAUNCH(create_instances_big_kernel<KeyT>, big_grid, kInstBlock, stream, recs, inst_keys, inst_vals, grid_w, key_hist,
                                                                           mask, big_count, big_prims, big_offsets,
                                                                           (uint32_t)capacity);
     return cudaGetLastError();
@@ -205,7 +205,7 @@ cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* so
                                      Rec* inst_recs, uint2* tile_ranges, const uint32_t* n_instances_dev, int capacity,
                                      int grid_w, cudaStream_t stream) {
     if (capacity <= 0) return cudaSuccess;
-    ranges_gather_kernel<KeyT><<<(unsigned)((capacity + 255) / 256), 256, 0, stream>>>(
+    FGS_LAUNCH(ranges_gather_kernel<KeyT>, (unsigned)((capacity + 255) / 256), 256, stream,
         sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, n_instances_dev, (uint32_t)capacity, (uint32_t)grid_w);
     return cudaGetLastError();
 }

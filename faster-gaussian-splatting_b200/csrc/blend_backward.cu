@@ -143,7 +143,7 @@ __device__ __noinline__ void flush_scores(WarpSmem& ws, const int nslots, const 
 // with dL/d(pixel colour) == 1 (kernels_pruning_scores.cuh:440-506); same traversal, different phase A payload.
 template <bool kScores>
 __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwdArgs a, const Cam cam) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FGS_DYNAMIC_SMEM(unsigned char, smem_raw, 128);
     WarpSmem* all = reinterpret_cast<WarpSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem& ws = all[warp];
@@ -318,7 +318,7 @@ static cudaError_t launch_blend_backward_t(const BlendBwdArgs& a, const Cam& cam
     }
     const int items = a.n_tiles * kBlendWarps;
     const int g = s_grid < (items + kWarps - 1) / kWarps ? s_grid : (items + kWarps - 1) / kWarps;
-    blend_backward_kernel<kScores><<<g, kThreads, smem, stream>>>(a, cam);
+    FGS_LAUNCH_SMEM(blend_backward_kernel<kScores>, g, kThreads, smem, stream, a, cam);
     return cudaGetLastError();
 }
 

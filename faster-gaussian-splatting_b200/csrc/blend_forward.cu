@@ -196,9 +196,9 @@ cudaError_t launch_blend_forward(const BlendFwdArgs& a, const Cam& cam, cudaStre
     const int items = a.n_tiles * kBlendWarps;
     const int g = grid < (items + kWarps - 1) / kWarps ? grid : (items + kWarps - 1) / kWarps;
     if (a.training)
-        blend_forward_kernel<true><<<g, kThreads, 0, stream>>>(a, cam);
+        FGS_LAUNCH(blend_forward_kernel<true>, g, kThreads, stream, a, cam);
     else
-        blend_forward_kernel<false><<<g, kThreads, 0, stream>>>(a, cam);
+        FGS_LAUNCH(blend_forward_kernel<false>, g, kThreads, stream, a, cam);
     return cudaGetLastError();
 }
 

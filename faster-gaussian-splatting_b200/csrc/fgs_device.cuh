@@ -3,8 +3,12 @@
 // Semantics restated from the reference (cited per item); the code, data layout and
 // kernel decomposition are new and sm_100a-only.
 #pragma once
+#ifndef FGS_CUDA_EMU
 #include <cuda_runtime.h>
+#endif
 #include <cstdint>
+
+#include "fgs_launch.h"
 
 namespace fgs {
 
@@ -170,6 +174,24 @@ __device__ __forceinline__ uint32_t tile_info_count(uint2 info) {
     return (info.x & kTileInfoBig) ? info.y : (uint32_t)__popc(info.y);
 }
 
+#ifdef FGS_CUDA_EMU
+// ---- the same primitives on the test-only CPU emulator (tests/cuda_emu/cuda_emu.h): copies complete at issue, the
+// mbarrier is a small state machine behind a mutex.  Checks indexing and phase logic, not asynchrony. ----------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { cuda_emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { cuda_emu::mbar_arrive(bar, 0); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { cuda_emu::mbar_arrive(bar, bytes); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return cuda_emu::mbar_try_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) std::this_thread::yield();
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    cuda_emu::bulk_copy(smem_dst, gmem_src, bytes, bar);
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) { std::memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
 // ---- mbarrier + bulk async copy (TMA 1-D bulk; SASS: UBLKCP / SYNCS) ------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -227,6 +249,8 @@ __device__ __forceinline__ bool named_bar_and(int id, int nthreads, bool pred) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+#endif  // FGS_CUDA_EMU
 
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 

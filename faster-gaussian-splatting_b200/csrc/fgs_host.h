@@ -1,6 +1,8 @@
 // fgs_host.h -- host-side declarations shared by the kernels' launchers and the C-ABI drivers.
 #pragma once
+#ifndef FGS_CUDA_EMU
 #include <cuda_runtime.h>
+#endif
 #include <cstddef>
 #include <cstdint>
 

@@ -9,6 +9,9 @@
 // same launch; tells the emulator that the kernel has no barrier and no warp collective, so it may run the CUDA
 // threads one after the other instead of as host threads
 #define FGS_LAUNCH_SERIAL(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// launch with `smem` bytes of dynamic shared memory, declared inside the kernel with FGS_DYNAMIC_SMEM
+#define FGS_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define FGS_DYNAMIC_SMEM(type, name, alignment) extern __shared__ __align__(alignment) type name[]
 #endif
 
 namespace fgs {

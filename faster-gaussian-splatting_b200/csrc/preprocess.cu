@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     __shared__ __align__(16) float s_means[kPreBlock * 3];
     __shared__ __align__(16) float s_scales[kPreBlock * 3];
     __shared__ __align__(16) float s_sh0[kPreBlock * 3];
-    extern __shared__ __align__(16) float s_rest[];  // 4 warps x 32 x 45 floats (only used when total_sh_rest == 15)
+    FGS_DYNAMIC_SMEM(float, s_rest, 16);  // 4 warps x 32 x 45 floats (only used when total_sh_rest == 15)
     __shared__ __align__(16) float s_w2c[12];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -327,11 +327,11 @@ cudaError_t launch_preprocess(const float* means, const float* scales, const flo
     const int grid = (n + kPreBlock - 1) / kPreBlock;
     const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
     if (inference)
-        preprocess_kernel<true><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
+        FGS_LAUNCH_SMEM(preprocess_kernel<true>, grid, kPreBlock, smem, stream, means, scales, rotations, opacities, sh0, sh_rest,
                                                                      recs, n_touched, tile_info, depth_keys, vis_indices,
                                                                      counters, depth_hist, n, cam);
     else
-        preprocess_kernel<false><<<grid, kPreBlock, smem, stream>>>(means, scales, rotations, opacities, sh0, sh_rest,
+        FGS_LAUNCH_SMEM(preprocess_kernel<false>, grid, kPreBlock, smem, stream, means, scales, rotations, opacities, sh0, sh_rest,
                                                                       recs, n_touched, tile_info, depth_keys, vis_indices,
                                                                       counters, depth_hist, n, cam);
     return cudaGetLastError();

@@ -112,7 +112,7 @@ __device__ __forceinline__ void emit_span(const float* __restrict__ stage, float
 }
 
 __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBwdArgs a, const Cam cam) {
-    extern __shared__ __align__(16) float s_stage[];
+    FGS_DYNAMIC_SMEM(float, s_stage, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* st = s_stage + warp * kWarpFloats;
     const int wfirst = blockIdx.x * kBlock + warp * 32;
@@ -430,7 +430,7 @@ cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cuda
         if (e != cudaSuccess) return e;
         s_attr = true;
     }
-    preprocess_backward_kernel<<<div_up(a.n, kBlock), kBlock, smem, stream>>>(a, cam);
+    FGS_LAUNCH_SMEM(preprocess_backward_kernel, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
     return cudaGetLastError();
 }
 
@@ -442,7 +442,7 @@ cudaError_t launch_adam(const float* grad, float* param, float* exp_avg, float* 
     const size_t n4 = aligned ? n / 4 : 0;
     const size_t tail = n - n4 * 4;
     const size_t threads = n4 > tail ? n4 : tail;
-    adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(grad, param, exp_avg, exp_avg_sq, n, n4, step_size,
+    FGS_LAUNCH_SERIAL(adam_kernel, (unsigned)((threads + 255) / 256), 256, stream, grad, param, exp_avg, exp_avg_sq, n, n4, step_size,
                                                                       beta1, beta2, eps, bias2_sqrt_rcp);
     return cudaGetLastError();
 }

@@ -31,6 +31,10 @@ constexpr int kSortWarps = kSortBlock / 32;
 #endif
 constexpr int kLookWindow = FGS_SORT_WINDOW;
 
+#ifdef FGS_CUDA_EMU  // test-only CPU emulator (tests/cuda_emu): blocks run one after the other
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -39,6 +43,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#endif
 
 // exclusive scan of one value per thread over a 256-thread block; also returns the block total
 __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_tmp /*>= 9 words*/, uint32_t* total) {
@@ -496,7 +501,7 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
     }
     if (!pass0_hist) {
         const int hist_grid = tiles < 148 * 4 ? tiles : 148 * 4;
-        radix_hist_kernel<KeyT><<<hist_grid, kSortBlock, 0, stream>>>(keys, n_dev, hist, plan.shift[0], plan.nbits[0],
+        FGS_LAUNCH(radix_hist_kernel<KeyT>, hist_grid, kSortBlock, stream, keys, n_dev, hist, plan.shift[0], plan.nbits[0],
                                                                       (uint32_t)n_max);
     }
     KeyT* kin = keys;
@@ -505,7 +510,7 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
     uint32_t* vout = vals_alt;
     for (int p = 0; p < plan.passes; ++p) {
         const bool last = p + 1 == plan.passes;
-        onesweep_kernel<KeyT><<<grid, kSortBlock, 0, stream>>>(
+        FGS_LAUNCH(onesweep_kernel<KeyT>, grid, kSortBlock, stream,
             kin, vin, kout, vout, n_dev, p == 0 && pass0_hist ? pass0_hist : hist + p * kRadixMax,
             last ? nullptr : hist + (p + 1) * kRadixMax, lookback + (size_t)p * tiles * kRadixMax, tickets + p,
             plan.shift[p], plan.nbits[p], last ? 0 : plan.shift[p + 1], last ? 1 : plan.nbits[p + 1],
@@ -538,7 +543,7 @@ cudaError_t launch_offsets_scan(const uint32_t* sorted_idx, const uint2* tile_in
         cudaError_t e = cudaMemsetAsync(lookback, 0, sizeof(uint32_t) * offsets_scan_lookback_words(n_max), stream);
         if (e != cudaSuccess) return e;
     }
-    offsets_scan_kernel<<<div_up(n_max, kScanTile), kSortBlock, 0, stream>>>(sorted_idx, tile_info, offsets, sorted_info,
+    FGS_LAUNCH(offsets_scan_kernel, div_up(n_max, kScanTile), kSortBlock, stream, sorted_idx, tile_info, offsets, sorted_info,
                                                                            n_dev, lookback, ticket);
     return cudaGetLastError();
 }

@@ -14,20 +14,36 @@ CSRC = ROOT / 'faster-gaussian-splatting_b200' / 'csrc'
 BUILD = HERE / '_build'
 
 
+# the rasterizer proper: c_abi.cu defines fgs::report_error / fgs_last_error itself
+FULL = ['preprocess', 'sort', 'binning', 'blend_forward', 'blend_backward', 'preprocess_backward', 'aux_ops', 'c_abi']
+
+
 def build(name: str, sanitize_threads: bool = False) -> ctypes.CDLL:
-    src = CSRC / f'{name}.cu'
+    """`name`: one self-contained operator file (loss, densify, peer_adam) or 'full' = the whole rasterizer."""
+    names = FULL if name == 'full' else [name]
+    srcs = [CSRC / f'{n}.cu' for n in names]
     tag = f'{name}_tsan' if sanitize_threads else name
     out = BUILD / f'libfgs_emu_{tag}.so'
-    deps = [src, HERE / 'cuda_emu.h', HERE / 'emu_support.cpp', CSRC / 'fgs_launch.h', ROOT / 'include' / 'fgs_b200.h',
-            Path(__file__)]
+    deps = srcs + [HERE / 'cuda_emu.h', HERE / 'emu_support.cpp', CSRC / 'fgs_launch.h', CSRC / 'fgs_device.cuh', CSRC / 'fgs_host.h',
+                   ROOT / 'include' / 'fgs_b200.h', Path(__file__)]
     if not out.exists() or out.stat().st_mtime < max(p.stat().st_mtime for p in deps):
         BUILD.mkdir(exist_ok=True)
-        cmd = ['g++', '-std=c++20', '-O1', '-g', '-pthread', '-shared', '-fPIC', '-DFGS_CUDA_EMU=1',
-               '-Wno-unknown-pragmas', '-Wno-attributes', '-include', str(HERE / 'cuda_emu.h'),
-               '-x', 'c++', str(src), str(HERE / 'emu_support.cpp'), '-o', str(out)]
+        objs = []
+        extra = [] if name == 'full' else [HERE / 'emu_support.cpp']
+        for src in srcs + extra:
+            obj = BUILD / f'{tag}_{src.stem}.o'
+            cmd = ['g++', '-std=c++20', '-O1', '-g', '-pthread', '-fPIC', '-DFGS_CUDA_EMU=1', '-Wno-unknown-pragmas', '-Wno-attributes',
+                   '-include', str(HERE / 'cuda_emu.h'), '-x', 'c++', '-c', str(src), '-o', str(obj)]
+            if sanitize_threads:
+                cmd[1:1] = ['-fsanitize=thread']
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f'emulator build of {src.name} failed:\n{r.stderr[-6000:]}')
+            objs.append(str(obj))
+        cmd = ['g++', '-shared', '-pthread', '-o', str(out), *objs]
         if sanitize_threads:
             cmd[1:1] = ['-fsanitize=thread']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f'emulator build of {src.name} failed:\n{r.stderr[-4000:]}')
+            raise RuntimeError(f'emulator link failed:\n{r.stderr[-4000:]}')
     return ctypes.CDLL(str(out))

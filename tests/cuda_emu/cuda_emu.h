@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -34,7 +35,9 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
+#define __noinline__ __attribute__((noinline))
+#define __maxnreg__(n)
 #define __shared__ static
 #define __constant__ static
 
@@ -66,6 +69,18 @@ struct alignas(8) int2 {
 struct alignas(4) uchar4 {
     unsigned char x, y, z, w;
 };
+struct alignas(8) ushort4 {
+    unsigned short x, y, z, w;
+};
+struct alignas(4) ushort2 {
+    unsigned short x, y;
+};
+struct alignas(16) int4 {
+    int x, y, z, w;
+};
+struct uint3_unused;
+inline ushort4 make_ushort4(unsigned short x, unsigned short y, unsigned short z, unsigned short w) { return {x, y, z, w}; }
+inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return {x, y}; }
 inline float3 make_float3(float x, float y, float z) { return {x, y, z}; }
 inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
@@ -88,6 +103,27 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+typedef struct cuda_emu_event* cudaEvent_t;
+struct cuda_emu_event {
+    int dummy;
+};
+constexpr unsigned cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0;
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cuda_emu_event{0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::calloc(1, n); return cudaSuccess; }
+template <typename T>
+inline cudaError_t cudaMemcpyToSymbolAsync(T& symbol, const void* src, size_t n, size_t offset, cudaMemcpyKind, cudaStream_t) {
+    std::memcpy(reinterpret_cast<char*>(&symbol) + offset, src, n);
+    return cudaSuccess;
+}
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
+template <typename K>
+inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }  // a 3-SM "GPU"
@@ -117,10 +153,13 @@ inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local BlockCtx* t_block = nullptr;
 inline thread_local WarpCtx* t_warp = nullptr;
 inline thread_local int t_lane = 0;
+inline thread_local unsigned char* t_dyn_smem = nullptr;  // the running block's dynamic shared memory
 
 template <typename F>
-void launch(dim3 grid, dim3 block, F&& body) {
+void launch(dim3 grid, dim3 block, F&& body, size_t dyn_smem_bytes = 0) {
     const int threads = (int)(block.x * block.y * block.z);
+    std::vector<unsigned char> dyn(dyn_smem_bytes + 256);
+    unsigned char* dyn_base = dyn.data() + (256 - reinterpret_cast<uintptr_t>(dyn.data()) % 256) % 256;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -136,6 +175,7 @@ void launch(dim3 grid, dim3 block, F&& body) {
                         t_block = &ctx;
                         t_warp = ctx.warps[t / 32].get();
                         t_lane = t % 32;
+                        t_dyn_smem = dyn_base;
                         body();
                         t_warp->live.fetch_and(~(1u << t_lane));
                         t_warp->bar.arrive_and_drop();  // a finished thread no longer takes part in barriers
@@ -183,6 +223,41 @@ inline T exchange(T v, int src_lane) {
     return r;
 }
 
+// mbarrier state machine in the 64-bit word the kernel reserves: bit 0 phase | 15 bits arrivals left | 15 bits
+// arrival count | 32 bits pending transaction bytes (two's complement).  Copies complete at issue.
+inline std::mutex g_mbar_mutex;
+inline void mbar_settle(uint64_t& w) {
+    const uint64_t left = (w >> 1) & 0x7fff, count = (w >> 16) & 0x7fff;
+    const int32_t tx = (int32_t)(w >> 32);
+    if (left == 0 && tx == 0) w = ((w & 1) ^ 1) | (count << 1) | (count << 16);
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+    std::lock_guard<std::mutex> g(g_mbar_mutex);
+    *bar = ((uint64_t)count << 1) | ((uint64_t)count << 16);
+}
+inline void mbar_arrive(uint64_t* bar, uint32_t expect_bytes) {
+    std::lock_guard<std::mutex> g(g_mbar_mutex);
+    uint64_t w = *bar;
+    const int32_t tx = (int32_t)(w >> 32) + (int32_t)expect_bytes;
+    const uint64_t left = ((w >> 1) & 0x7fff) - 1;
+    w = (w & 0x7fff0001ull) | (left << 1) | ((uint64_t)(uint32_t)tx << 32);
+    mbar_settle(w);
+    *bar = w;
+}
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    std::lock_guard<std::mutex> g(g_mbar_mutex);
+    return (*bar & 1) != (parity & 1);
+}
+inline void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    std::memcpy(dst, src, bytes);
+    std::lock_guard<std::mutex> g(g_mbar_mutex);
+    uint64_t w = *bar;
+    const int32_t tx = (int32_t)(w >> 32) - (int32_t)bytes;
+    w = (w & 0xffffffffull) | ((uint64_t)(uint32_t)tx << 32);
+    mbar_settle(w);
+    *bar = w;
+}
+
 }  // namespace cuda_emu
 
 #define threadIdx (cuda_emu::t_threadIdx)
@@ -228,6 +303,63 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     w.bar.arrive_and_wait();
     return r;
 }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = v;
+    w.bar.arrive_and_wait();
+    const unsigned live = w.live.load();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (live >> l & 1u) r += (unsigned)w.slot[l];
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = v;
+    w.bar.arrive_and_wait();
+    const unsigned live = w.live.load();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (live >> l & 1u) r = std::max(r, (unsigned)w.slot[l]);
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = v;
+    w.bar.arrive_and_wait();
+    const unsigned live = w.live.load();
+    unsigned r = 0xffffffffu;
+    for (int l = 0; l < 32; ++l)
+        if (live >> l & 1u) r = std::min(r, (unsigned)w.slot[l]);
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = v;
+    w.bar.arrive_and_wait();
+    const unsigned live = w.live.load();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (live >> l & 1u) r |= (unsigned)w.slot[l];
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    cuda_emu::WarpCtx& w = *cuda_emu::t_warp;
+    w.slot[cuda_emu::t_lane] = v;
+    w.bar.arrive_and_wait();
+    const unsigned live = w.live.load();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((live >> l & 1u) && (unsigned)w.slot[l] == v) r |= 1u << l;
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline unsigned __activemask() { return cuda_emu::t_warp->live.load(); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
 
@@ -283,6 +415,25 @@ inline int atomicMax(int* p, int v) {
     }
     return old;
 }
+inline float4 atomicAdd(float4* p, float4 v) {  // sm_90+: one 16-byte reduction
+    float4 old;
+    old.x = atomicAdd(&p->x, v.x);
+    old.y = atomicAdd(&p->y, v.y);
+    old.z = atomicAdd(&p->z, v.z);
+    old.w = atomicAdd(&p->w, v.w);
+    return old;
+}
+inline float2 atomicAdd(float2* p, float2 v) {
+    float2 old;
+    old.x = atomicAdd(&p->x, v.x);
+    old.y = atomicAdd(&p->y, v.y);
+    return old;
+}
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return cmp;
+}
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
@@ -303,6 +454,18 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
 inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return {a.x * b.x, a.y * b.y}; }
+inline float2 __fadd2_rn(float2 a, float2 b) { return {a.x + b.x, a.y + b.y}; }
+inline float __frsqrt_rn(float a) { return 1.0f / std::sqrt(a); }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline int __float2int_rd(float a) { return (int)std::floor(a); }
+inline int __float2int_ru(float a) { return (int)std::ceil(a); }
+inline int __float2int_rn(float a) { return (int)std::nearbyint(a); }
+inline int __float2int_rz(float a) { return (int)a; }
+inline unsigned __float2uint_rd(float a) { return (unsigned)std::floor(a); }
+inline unsigned __float2uint_ru(float a) { return (unsigned)std::ceil(a); }
+inline unsigned __float2uint_rz(float a) { return (unsigned)a; }
 inline float __saturatef(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
@@ -322,3 +485,5 @@ inline unsigned min(int a, unsigned b) { return min((unsigned)a, b); }
 // kernel launch through a macro shared with the nvcc build (csrc/fgs_launch.h)
 #define FGS_LAUNCH(kernel, grid, block, stream, ...) cuda_emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
 #define FGS_LAUNCH_SERIAL(kernel, grid, block, stream, ...) cuda_emu::launch_serial((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define FGS_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) cuda_emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); }, (smem))
+#define FGS_DYNAMIC_SMEM(type, name, alignment) type* name = reinterpret_cast<type*>(cuda_emu::t_dyn_smem)

@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE ONLY: drives the emulated build of the whole rasterizer (tests/cuda_emu, `build('full')`) through
+the same C ABI as the product (include/fgs_b200.h), with numpy arrays standing in for device memory."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from fgs_b200 import _capi
+
+
+def load(sanitize_threads: bool = False):
+    from tests import cuda_emu
+    lib = cuda_emu.build('full', sanitize_threads=sanitize_threads)
+    for name, (res, args) in _capi.SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def _aligned(nbytes: int, align: int = 256) -> np.ndarray:
+    raw = np.zeros(nbytes + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + nbytes]
+
+
+class Scratch:
+    """The three caller-owned growable buffers of fgs_forward (resize callbacks)."""
+
+    def __init__(self):
+        self.buf = {}
+        self.cb = _capi.ResizeFn(self._resize)
+
+    def _resize(self, user, nbytes):
+        user = int(user)
+        if int(nbytes) == 0 and user in self.buf:
+            return self.buf[user].ctypes.data
+        self.buf[user] = _aligned(max(int(nbytes), 1))
+        self.buf[user][:] = 0xCD  # the library must not rely on zeroed scratch
+        return self.buf[user].ctypes.data
+
+
+def _f32(t) -> np.ndarray:
+    return np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy().astype(np.float32))
+
+
+def _copy_aligned(a: np.ndarray) -> np.ndarray:
+    out = _aligned(max(a.nbytes, 16)).view(np.float32)[:a.size].reshape(a.shape)
+    out[...] = a
+    return out
+
+
+def settings_struct(st, total_rest):
+    return _capi.Settings(int(st[3]), int(total_rest), int(st[4]), int(st[5]), float(st[6]), float(st[7]), float(st[8]),
+                          float(st[9]), float(st[10]), float(st[11]), int(bool(st[12])))
+
+
+def forward(lib, params, st, training=True, to_chw=True, clamp=False):
+    """params: six tensors (means, scales, rotations, opacities, sh0, sh_rest); st: RasterizerSettings tuple.
+    Returns (image, state, scratch, inputs) -- keep `scratch` and `inputs` alive for the backward."""
+    p = [_copy_aligned(_f32(t)) for t in params]
+    n = p[0].shape[0]
+    total_rest = p[5].shape[1] if p[5].ndim > 1 else 0
+    w2c, pos, bg = (_copy_aligned(_f32(t)) for t in st[:3])
+    w, h = int(st[4]), int(st[5])
+    image = _copy_aligned(np.full((3, h, w) if to_chw else (h, w, 3), np.nan, dtype=np.float32))
+    s = settings_struct(st, total_rest)
+    sc = Scratch()
+    state = _capi.ForwardState()
+    ptr = lambda a: a.ctypes.data
+    if training:
+        rc = lib.fgs_forward(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), n, C.byref(s), None,
+                             C.byref(state))
+    else:
+        rc = lib.fgs_inference(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), n, C.byref(s),
+                               int(to_chw), int(clamp), None)
+    assert rc == 0, lib.fgs_last_error()
+    return image, state, sc, dict(p=p, w2c=w2c, pos=pos, bg=bg, s=s, n=n)
+
+
+def backward(lib, image, grad_image, state, sc, inp, densification_info=None):
+    p, n = inp['p'], inp['n']
+    gi = _copy_aligned(_f32(grad_image))
+    grads = [_copy_aligned(np.full(a.shape, np.nan, dtype=np.float32)) for a in p]
+    scratch2d = _aligned(lib.fgs_grad2d_scratch_bytes(n))
+    scratch2d[:] = 0xCD
+    ptr = lambda a: a.ctypes.data
+    dens = ptr(densification_info) if densification_info is not None else None
+    rc = lib.fgs_backward(ptr(gi), ptr(image), ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[5]), ptr(inp['w2c']),
+                          ptr(inp['pos']), ptr(inp['bg']), ptr(sc.buf[1]), ptr(sc.buf[2]), ptr(sc.buf[3]),
+                          *[ptr(g) for g in grads], ptr(scratch2d), dens, n, C.byref(inp['s']), C.byref(state), None)
+    assert rc == 0, lib.fgs_last_error()
+    return [torch.from_numpy(np.array(g)) for g in grads]
