@@ -132,8 +132,10 @@ inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int,
 
 namespace cuda_emu {
 
+using Barrier = std::barrier<>;  // (a spin-then-yield barrier was tried: slower with 256 host threads on 8 cores)
+
 struct WarpCtx {
-    std::barrier<> bar;
+    Barrier bar;
     uint64_t slot[32];
     std::atomic<unsigned> live;  // lanes that have not returned yet
     explicit WarpCtx(int lanes) : bar(lanes), live(lanes >= 32 ? 0xffffffffu : ((1u << lanes) - 1u)) {
@@ -141,7 +143,7 @@ struct WarpCtx {
     }
 };
 struct BlockCtx {
-    std::barrier<> bar;
+    Barrier bar;
     std::vector<std::unique_ptr<WarpCtx>> warps;
     explicit BlockCtx(int threads) : bar(threads) {
         for (int w = 0; w * 32 < threads; ++w) warps.emplace_back(new WarpCtx(std::min(32, threads - w * 32)));

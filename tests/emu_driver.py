@@ -93,3 +93,63 @@ def backward(lib, image, grad_image, state, sc, inp, densification_info=None):
                           *[ptr(g) for g in grads], ptr(scratch2d), dens, n, C.byref(inp['s']), C.byref(state), None)
     assert rc == 0, lib.fgs_last_error()
     return [torch.from_numpy(np.array(g)) for g in grads]
+
+
+def backward_adam(lib, image, grad_image, state, sc, inp, moments_m, moments_v, steps, lrs, betas=(0.9, 0.999), eps=1e-15,
+                  densification_info=None):
+    """fgs_backward_adam: updates inp['p'] (parameters) and the moment arrays in place."""
+    p, n = inp['p'], inp['n']
+    gi = _copy_aligned(_f32(grad_image))
+    scratch2d = _aligned(lib.fgs_grad2d_scratch_bytes(n))
+    ptr = lambda a: a.ctypes.data
+    arr = lambda ts: (C.c_void_p * 6)(*[ptr(t) for t in ts])
+    dens = ptr(densification_info) if densification_info is not None else None
+    rc = lib.fgs_backward_adam(ptr(gi), ptr(image), arr(p), arr(moments_m), arr(moments_v), (C.c_int32 * 6)(*steps),
+                               (C.c_double * 6)(*lrs), betas[0], betas[1], eps, ptr(inp['w2c']), ptr(inp['pos']), ptr(inp['bg']),
+                               ptr(sc.buf[1]), ptr(sc.buf[2]), ptr(sc.buf[3]), ptr(scratch2d), dens, n, C.byref(inp['s']),
+                               C.byref(state), None)
+    assert rc == 0, lib.fgs_last_error()
+
+
+def adam_step(lib, grad, param, m, v, step, lr, betas=(0.9, 0.999), eps=1e-15):
+    ptr = lambda a: a.ctypes.data
+    rc = lib.fgs_adam_step(ptr(grad), ptr(param), ptr(m), ptr(v), param.size, int(step), float(lr), betas[0], betas[1], eps, None)
+    assert rc == 0, lib.fgs_last_error()
+
+
+def pruning_scores(lib, params, st, scores):
+    p = [_copy_aligned(_f32(t)) for t in params]
+    n = p[0].shape[0]
+    w2c, pos, bg = (_copy_aligned(_f32(t)) for t in st[:3])
+    w, h = int(st[4]), int(st[5])
+    image = _copy_aligned(np.zeros((3, h, w), dtype=np.float32))
+    s = settings_struct(st, p[5].shape[1])
+    sc = Scratch()
+    ptr = lambda a: a.ctypes.data
+    rc = lib.fgs_pruning_scores(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), ptr(scores), n,
+                                C.byref(s), None)
+    assert rc == 0, lib.fgs_last_error()
+
+
+def sort_pairs(lib, keys: np.ndarray, vals: np.ndarray, n: int, end_bit: int):
+    """keys uint32 or uint16 of length n_max >= n; returns (sorted keys[:n], sorted vals[:n])."""
+    n_max = keys.shape[0]
+    k, v = _copy_aligned_any(keys), _copy_aligned_any(vals)
+    k_alt, v_alt = _copy_aligned_any(np.zeros_like(keys)), _copy_aligned_any(np.zeros_like(vals))
+    n_dev = _copy_aligned_any(np.array([n], dtype=np.uint32))
+    sb = lib.fgs_sort_scratch_bytes(n_max, end_bit)
+    scratch = _aligned(sb)
+    scratch[:] = 0xCD
+    in_alt = C.c_int32(0)
+    fn = lib.fgs_sort_pairs_u32 if keys.dtype == np.uint32 else lib.fgs_sort_pairs_u16
+    rc = fn(k.ctypes.data, k_alt.ctypes.data, v.ctypes.data, v_alt.ctypes.data, n_dev.ctypes.data, n_max, end_bit,
+            scratch.ctypes.data, sb, C.byref(in_alt), None)
+    assert rc == 0, lib.fgs_last_error()
+    ks, vs = (k_alt, v_alt) if in_alt.value else (k, v)
+    return np.array(ks[:n]), np.array(vs[:n])
+
+
+def _copy_aligned_any(a: np.ndarray) -> np.ndarray:
+    out = _aligned(max(a.nbytes, 16)).view(a.dtype)[:a.size].reshape(a.shape)
+    out[...] = a
+    return out

@@ -1,0 +1,189 @@
+"""CPU tests of the hand-written CUDA SOURCE of the hot path: the whole rasterizer (csrc/preprocess.cu, sort.cu,
+binning.cu, blend_forward.cu, blend_backward.cu, preprocess_backward.cu, c_abi.cu) is compiled by g++ against the
+test-only thread-per-CUDA-thread emulator (tests/cuda_emu) and driven through the same C ABI as the product, with numpy
+arrays standing in for device memory.
+
+What this checks without a GPU: indexing, launch geometry, the onesweep look-back and ranking logic, the TMA ring /
+mbarrier phase logic of the persistent blend kernels (copies complete at issue), the speculative instance capacity, the
+analytic backward, fused backward + Adam -- against the golden vectors dumped from the COMPILED REFERENCE on a B200
+(tests/golden/*.npz) and against the fp64 oracle.  The emulator computes in IEEE float32 (no fast-math), so the bounds
+against the oracle are far tighter than the GPU ones.  It does not model asynchrony or performance; the GPU suite
+(tests/test_parity_gpu.py) remains the parity test proper."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+GOLDEN = Path(__file__).resolve().parent / 'golden'
+NAMES = ['means', 'scales', 'rotations', 'opacities', 'sh0', 'sh_rest']
+LRS = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]
+
+
+@pytest.fixture(scope='module')
+def emu():
+    from tests import emu_driver as E
+    lib = E.load()
+    lib.fgs_debug_set_capacity_hint(0)
+    return E, lib
+
+
+def _case(name):
+    from fgs_b200 import synthetic as syn
+    z = np.load(GOLDEN / f'{name}.npz')
+    n, w, h, seed, bases, aa = [int(v) for v in z['meta']]
+    sc = syn.make_scene(n, seed)
+    cam = syn.make_camera(seed, w, h)
+    st = (cam.w2c, cam.position, torch.from_numpy(z['bg']), bases, w, h, cam.focal_x, cam.focal_y, cam.center_x, cam.center_y,
+          cam.near_plane, cam.far_plane, bool(aa))
+    return z, sc, st, syn.make_grad_image(w, h, seed)
+
+
+@pytest.mark.parametrize('name', ['c1_deg3', 'c1_deg1', 'c1_deg0', 'c1_aa', 'ragged'])
+def test_emulated_kernels_match_reference_golden(emu, name):
+    """The kernel source against outputs of the unmodified reference backend (image, inference image, six gradients,
+    densification statistics)."""
+    if not (GOLDEN / f'{name}.npz').exists():
+        pytest.skip('golden fixture missing')
+    E, lib = emu
+    z, sc, st, gi = _case(name)
+    n = sc.means.shape[0]
+    img, state, scr, inp = E.forward(lib, list(sc), st)
+    ref_img = torch.from_numpy(z['image']).double()
+    l1 = (torch.from_numpy(np.array(img)).double() - ref_img).abs().mean().item()
+    assert l1 <= 1e-4, f'image mean-L1 vs reference {l1}'
+    dens = np.zeros((2, n), dtype=np.float32)
+    grads = E.backward(lib, img, gi, state, scr, inp, densification_info=dens)
+    for k, g in zip(NAMES, grads):
+        rg = torch.from_numpy(z[f'grad_{k}']).double()
+        e = util.rel_err(g, rg)
+        assert e <= 5e-3, f'{name}/{k}: |emulated kernels - reference|_1 / |reference|_1 = {e}'
+        assert float(g[rg.reshape(n, -1).abs().sum(1) == 0].abs().sum()) <= 1e-12 or k == 'means'  # zero rows stay zero
+    rd = torch.from_numpy(z['densification_info']).double()
+    assert torch.equal(rd[0], torch.from_numpy(dens[0]).double())
+    assert util.rel_err(torch.from_numpy(dens[1]), rd[1]) <= 5e-3
+    inf_img, _, _, _ = E.forward(lib, list(sc), st, training=False, to_chw=False, clamp=True)
+    assert (torch.from_numpy(np.array(inf_img)).double() - torch.from_numpy(z['inference_hwc']).double()).abs().mean().item() <= 1e-4
+
+
+@pytest.mark.parametrize('bases,aa', [(16, False), (4, True)])
+def test_emulated_kernels_vs_oracle_tight(emu, bases, aa):
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    E, lib = emu
+    n, w, h = 700, 112, 84
+    sc, cam = syn.make_scene(n, 3), syn.make_camera(3, w, h)
+    st = util.settings_for(cam, active_sh_bases=bases, bg=(0.1, 0.2, 0.3), aa=aa)
+    gi = syn.make_grad_image(w, h, 3)
+    img, state, scr, inp = E.forward(lib, list(sc), st)
+    dens = np.zeros((2, n), dtype=np.float32)
+    grads = E.backward(lib, img, gi, state, scr, inp, densification_info=dens)
+    dens64 = torch.zeros(2, n, dtype=torch.float64)
+    out, ograds = O.render_and_grads(list(sc), O.Settings(*st), gi, dtype=torch.float64, densification_info=dens64)
+    assert state.n_visible == int(out.proj.visible.sum())
+    assert (torch.from_numpy(np.array(img)).double() - out.image).abs().mean().item() <= 2e-6
+    for k, g, og in zip(NAMES, grads, ograds):
+        assert util.rel_err(g, og) <= 2e-4 and util.cos_sim(g, og) >= 0.999999, k
+        assert float(g[~out.proj.visible].abs().sum()) == 0.0, k
+    assert torch.equal(torch.from_numpy(dens[0]).double(), dens64[0]) and util.rel_err(torch.from_numpy(dens[1]), dens64[1]) <= 2e-4
+    # the inference path renders the same image
+    inf_img, _, _, _ = E.forward(lib, list(sc), st, training=False, to_chw=True, clamp=False)
+    assert np.abs(np.array(inf_img) - np.array(img)).max() <= 1e-6
+
+
+def test_emulated_fused_backward_adam_equals_backward_then_step_and_reference(emu):
+    E, lib = emu
+    z, sc, st, gi = _case('c1_deg3')
+    # (a) backward, then fgs_adam_step per tensor, three steps with the same gradient
+    img, state, scr, inp = E.forward(lib, list(sc), st)
+    grads = E.backward(lib, img, gi, state, scr, inp)
+    pa = [np.array(a) for a in inp['p']]
+    ma, va = [np.zeros_like(a) for a in pa], [np.zeros_like(a) for a in pa]
+    for step in (1, 2, 3):
+        for t in range(6):
+            E.adam_step(lib, np.ascontiguousarray(grads[t].numpy()), pa[t], ma[t], va[t], step, LRS[t])
+    for k, p0, a in zip(NAMES, sc.params(), pa):   # three reference FusedAdam steps on the reference's gradient
+        ref = torch.from_numpy(z[f'adam3_{k}'])
+        assert util.rel_err(torch.from_numpy(a) - p0, ref - p0) <= 2e-3, k
+    # (b) one fused backward + Adam step == one backward + adam_step
+    img2, state2, scr2, inp2 = E.forward(lib, list(sc), st)
+    mb = [E._copy_aligned(np.zeros_like(a)) for a in inp2['p']]
+    vb = [E._copy_aligned(np.zeros_like(a)) for a in inp2['p']]
+    E.backward_adam(lib, img2, gi, state2, scr2, inp2, mb, vb, [1] * 6, LRS)
+    pc = [np.array(a) for a in inp['p']]
+    mc, vc = [np.zeros_like(a) for a in pc], [np.zeros_like(a) for a in pc]
+    for t in range(6):
+        E.adam_step(lib, np.ascontiguousarray(grads[t].numpy()), pc[t], mc[t], vc[t], 1, LRS[t])
+    for t, k in enumerate(NAMES):
+        # two backward passes accumulate the 2D gradients with float atomics in different orders: last-ulp differences
+        tt = torch.from_numpy
+        assert util.rel_err(tt(np.array(inp2['p'][t])) - sc.params()[t], tt(pc[t]) - sc.params()[t]) <= 1e-4, k
+        assert util.rel_err(tt(np.array(mb[t])), tt(mc[t])) <= 1e-5 and util.rel_err(tt(np.array(vb[t])), tt(vc[t])) <= 1e-5, k
+
+
+def test_emulated_speculative_capacity_paths(emu):
+    """Cold call (no hint), a hint that is too small (checked re-run) and the normal path give the same image."""
+    from fgs_b200 import synthetic as syn
+    E, lib = emu
+    sc, cam = syn.make_scene(400, 1), syn.make_camera(1, 96, 72)
+    st = util.settings_for(cam, bg=(0.2, 0.1, 0.0))
+    lib.fgs_debug_set_capacity_hint(0)
+    cold, state, _, _ = E.forward(lib, list(sc), st)
+    assert lib.fgs_debug_get_capacity_hint() >= state.n_instances > 0
+    lib.fgs_debug_set_capacity_hint(max(state.n_instances // 3, 1))
+    redo, state2, _, _ = E.forward(lib, list(sc), st)
+    normal, state3, _, _ = E.forward(lib, list(sc), st)
+    assert state2.n_instances == state.n_instances == state3.n_instances
+    assert np.array_equal(np.array(redo), np.array(cold)) and np.array_equal(np.array(normal), np.array(cold))
+    lib.fgs_debug_set_capacity_hint(0)
+
+
+def test_emulated_empty_and_degenerate_inputs(emu):
+    from fgs_b200 import synthetic as syn
+    E, lib = emu
+    sc, cam = syn.make_scene(64, 2), syn.make_camera(2, 40, 30)
+    bg = (0.3, 0.6, 0.9)
+    st = util.settings_for(cam, bg=bg)
+    behind = [t.clone() for t in sc]
+    behind[0][:] = cam.position + (cam.position / cam.position.norm()) * 5.0  # all Gaussians behind the camera
+    img, state, scr, inp = E.forward(lib, behind, st)
+    assert state.n_visible == 0 and state.n_instances == 0
+    assert np.allclose(np.array(img), np.array(bg, dtype=np.float32)[:, None, None])
+    grads = E.backward(lib, img, torch.ones(3, 30, 40), state, scr, inp)
+    assert all(float(g.abs().sum()) == 0.0 for g in grads)
+    one = [t[:1].clone().contiguous() for t in sc]  # a single Gaussian
+    img1, state1, _, _ = E.forward(lib, one, st)
+    assert np.isfinite(np.array(img1)).all()
+
+
+@pytest.mark.parametrize('dtype,end_bit,n_max,n', [(np.uint32, 32, 5000, 5000), (np.uint32, 32, 5000, 3777), (np.uint16, 14, 9000, 9000),
+                                                  (np.uint16, 7, 300, 123), (np.uint32, 17, 2049, 2048), (np.uint32, 32, 64, 0)])
+def test_emulated_onesweep_sort_is_a_stable_sort(emu, dtype, end_bit, n_max, n):
+    E, lib = emu
+    rng = np.random.default_rng(end_bit + n)
+    hi = min(1 << end_bit, np.iinfo(dtype).max + 1)
+    keys = rng.integers(0, hi, n_max, dtype=np.uint64).astype(dtype)
+    keys[::3] //= 256  # many duplicates, empty high digits
+    vals = np.arange(n_max, dtype=np.uint32)
+    ks, vs = E.sort_pairs(lib, keys, vals, n, end_bit)
+    order = np.argsort(keys[:n].astype(np.int64), kind='stable')
+    assert np.array_equal(vs, vals[:n][order]) and np.array_equal(ks, keys[:n][order])
+
+
+def test_emulated_pruning_scores_match_reference_golden(emu):
+    f = GOLDEN / 'pruning_scores.npz'
+    if not f.exists():
+        pytest.skip('golden fixture missing')
+    from fgs_b200 import synthetic as syn
+    E, lib = emu
+    z = np.load(f)
+    n, w, h, seed = [int(v) for v in z['meta']]
+    sc, cam = syn.make_scene(n, seed), syn.make_camera(seed, w, h)
+    st = (cam.w2c, cam.position, torch.from_numpy(z['bg']), 16, w, h, cam.focal_x, cam.focal_y, cam.center_x, cam.center_y,
+          cam.near_plane, cam.far_plane, False)
+    scores = np.zeros(n, dtype=np.float32)
+    E.pruning_scores(lib, list(sc), st, scores)
+    ref = torch.from_numpy(z['scores']).double()
+    assert util.rel_err(torch.from_numpy(scores), ref) <= 5e-3
