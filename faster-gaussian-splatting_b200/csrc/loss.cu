@@ -384,8 +384,8 @@ int check_args(const void* image, const void* target, bool target_is_u8, const v
     if (!image || !target || !scratch) return report_error(-1, who, "NULL argument");
     if (width <= 0 || height <= 0) return report_error(-1, who, "empty image");
     // the streaming kernel uses 16-byte (float) / 4-byte (uint8) vector accesses
-    if (misaligned(image, 16) || misaligned(grad_image, 16) || misaligned(target, target_is_u8 ? 4 : 16) || misaligned(scratch, 128))
-        return report_error(-1, who, "image / grad_image must be 16-byte aligned, a uint8 target 4-byte, scratch 128-byte");
+    if (misaligned(image, 16) || misaligned(grad_image, 16) || misaligned(target, target_is_u8 ? 4 : 16) || misaligned(scratch, 16))
+        return report_error(-1, who, "image, grad_image, a float target and scratch must be 16-byte aligned, a uint8 target 4-byte");
     return 0;
 }
 

@@ -40,7 +40,7 @@ def _ptr(t: torch.Tensor) -> int:
 
 def _check_param(t: torch.Tensor, name: str) -> None:
     # the reference only checks this in debug builds (rasterization_api.cu:35-41); here it is always on
-    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+    if not (_capi.on_device(t) and t.dtype == torch.float32 and t.is_contiguous()):
         raise RuntimeError(f"Input tensor '{name}' must be a contiguous CUDA float tensor.")
 
 
@@ -54,7 +54,7 @@ def _settings(active_sh_bases, total_rest, width, height, fx, fy, cx, cy, near, 
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _capi.current_stream()
 
 
 def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c, cam_position,
@@ -67,7 +67,7 @@ def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficie
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
         _check_param(t, name)
     dev = means.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = means.shape[0]
         total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
         image = torch.empty((3, int(height), int(width)), dtype=torch.float32, device=dev)
@@ -98,7 +98,7 @@ def _backward_common(image, primitive_buffers, w2c, cam_position, bg_color, grad
     gi = grad_image.to(dtype=torch.float32).contiguous()
     dens_ptr = None
     if densification_info is not None and densification_info.numel() > 0:
-        if not (densification_info.is_cuda and densification_info.dtype == torch.float32
+        if not (_capi.on_device(densification_info) and densification_info.dtype == torch.float32
                 and densification_info.is_contiguous()):
             raise RuntimeError("'densification_info' must be a contiguous CUDA float tensor.")
         dens_ptr = _ptr(densification_info)
@@ -132,7 +132,7 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
         image, primitive_buffers, w2c, cam_position, bg_color, grad_image, densification_info, sh_coefficients_rest,
         active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
         proper_antialiasing, n_instances)
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = means.shape[0]
         if _grad_outputs is None:
             grads = [torch.empty_like(p) for p in (means, scales, rotations, opacities)]
@@ -171,7 +171,7 @@ def backward_adam(densification_info, grad_image, image, params, exp_avgs, exp_a
     for group in (params, exp_avgs, exp_avg_sqs):
         for t in group:
             _check_param(t, 'param/state')
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = params[0].shape[0]
         scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)
         arr = lambda ts: (C.c_void_p * 6)(*[_ptr(t) for t in ts])
@@ -193,7 +193,7 @@ def inference(means, scales, rotations, opacities, sh_coefficients_0, sh_coeffic
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
         _check_param(t, name)
     dev = means.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = means.shape[0]
         total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
         shape = (3, int(height), int(width)) if to_chw else (int(height), int(width), 3)
@@ -217,7 +217,7 @@ def adam_step(param_grad, param, exp_avg, exp_avg_sq, step_count, learning_rate,
     """adam/include/adam.h:7-16."""
     for t, name in ((param_grad, 'param_grad'), (param, 'param'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
         _check_param(t, name)
-    with torch.cuda.device(param.device):
+    with _capi.device_guard(param.device):
         rc = _lib.fgs_adam_step(_ptr(param_grad), _ptr(param), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
                                 int(step_count), float(learning_rate), float(beta1), float(beta2), float(epsilon),
                                 _stream())
@@ -229,10 +229,10 @@ def update_3d_filter(positions, w2c, filter_3d, visibility_mask, width, height, 
     """filter3d/include/filter3d.h:7-20; filter_3d and visibility_mask (bool) are updated in place."""
     _check_param(positions, 'positions')
     _check_param(filter_3d, 'filter_3d')
-    if not (visibility_mask.is_cuda and visibility_mask.dtype == torch.bool and visibility_mask.is_contiguous()):
+    if not (_capi.on_device(visibility_mask) and visibility_mask.dtype == torch.bool and visibility_mask.is_contiguous()):
         raise RuntimeError("'visibility_mask' must be a contiguous CUDA bool tensor.")
     dev = positions.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         w2c_c = _aux(w2c, dev)
         rc = _lib.fgs_update_3d_filter(_ptr(positions), _ptr(w2c_c), _ptr(filter_3d), _ptr(visibility_mask),
                                        positions.shape[0], int(width), int(height), float(focal_x), float(focal_y),
@@ -244,7 +244,7 @@ def update_3d_filter(positions, w2c, filter_3d, visibility_mask, width, height, 
 def relocation_adjustment(old_opacities, old_scales, n_samples_per_primitive):
     """densification_api.h:8-13.  Returns (new_opacities (n,1), new_scales (n,3))."""
     dev = old_opacities.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = old_opacities.shape[0]
         o = old_opacities.to(torch.float32).contiguous()
         sc = old_scales.to(torch.float32).contiguous()
@@ -261,7 +261,7 @@ def add_noise(raw_scales, raw_rotations, raw_opacities, random_samples, means, c
     for t, name in ((raw_scales, 'raw_scales'), (raw_rotations, 'raw_rotations'), (raw_opacities, 'raw_opacities'),
                     (random_samples, 'random_samples'), (means, 'means')):
         _check_param(t, name)
-    with torch.cuda.device(means.device):
+    with _capi.device_guard(means.device):
         rc = _lib.fgs_add_noise(_ptr(raw_scales), _ptr(raw_rotations), _ptr(raw_opacities), _ptr(random_samples),
                                 _ptr(means), raw_scales.shape[0], float(current_lr), _stream())
         _capi.check(rc, 'add_noise')
@@ -277,7 +277,7 @@ def pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_
                     (scores, 'scores')):
         _check_param(t, name)
     dev = means.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         n = means.shape[0]
         total_rest = sh_coefficients_rest.shape[1] if sh_coefficients_rest.dim() > 1 else 0
         image = torch.empty((3, int(height), int(width)), dtype=torch.float32, device=dev)

@@ -138,6 +138,22 @@ def load() -> C.CDLL:
     return lib
 
 
+# The three places where the Python layer touches the CUDA runtime through torch.  (tests/test_emulated_python_layer.py
+# replaces them to run this layer's argument marshalling on host tensors against the emulated build of the library.)
+def on_device(t) -> bool:
+    return bool(t.is_cuda)
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_guard(device):
+    import torch
+    return torch.cuda.device(device)
+
+
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().fgs_last_error().decode(errors='replace')

@@ -35,11 +35,11 @@ RowTensor = _capi.RowTensor
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _capi.current_stream()
 
 
 def _check(t: torch.Tensor, name: str) -> torch.Tensor:
-    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+    if not (_capi.on_device(t) and t.dtype == torch.float32 and t.is_contiguous()):
         raise RuntimeError(f"'{name}' must be a contiguous CUDA float tensor.")
     return t
 
@@ -98,7 +98,7 @@ def _move_rows(optimizer, plan, n_out: int, n_copy: int | None = None, appended:
         sp = [None, None, None]
         if split is not None:
             sp = [_check(t, 'split input').data_ptr() for t in split]
-        with torch.cuda.device(dev):
+        with _capi.device_guard(dev):
             arr = (RowTensor * len(rows))(*rows)
             rc = _lib.fgs_gather_rows(arr, len(rows), plan.data_ptr() if plan is not None else None, n_out, n_copy, sp[0], sp[1],
                                       sp[2], _stream())
@@ -117,7 +117,7 @@ def _move_rows(optimizer, plan, n_out: int, n_copy: int | None = None, appended:
 def _plan_from_flags(flags: torch.Tensor, n: int):
     """flags (n,) uint8 on the device -> (plan int64 (n_out,), totals [kept, clones, split pairs kept, splits])."""
     dev = flags.device
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         scratch = torch.empty(_lib.fgs_densify_scratch_bytes(n), dtype=torch.uint8, device=dev)
         totals = (C.c_uint32 * 4)()
         _capi.check(_lib.fgs_plan_count(flags.data_ptr(), n, scratch.data_ptr(), totals, _stream()), 'plan_count')
@@ -169,7 +169,7 @@ def reset_state(optimizer, indices: torch.Tensor) -> None:
             tensors += [_check(st['exp_avg'], 'exp_avg'), _check(st['exp_avg_sq'], 'exp_avg_sq')]
     if not tensors:
         return
-    with torch.cuda.device(indices.device):
+    with _capi.device_guard(indices.device):
         ptrs = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         rows = (C.c_int32 * len(tensors))(*[_row_floats(t) for t in tensors])
         _capi.check(_lib.fgs_zero_rows(ptrs, rows, len(tensors), indices.data_ptr(), indices.numel(), _stream()), 'zero_rows')
@@ -181,7 +181,7 @@ def morton_encode(means: torch.Tensor) -> torch.Tensor:
     _check(means, 'means')
     n = means.shape[0]
     codes = torch.empty(n, dtype=torch.int64, device=means.device)
-    with torch.cuda.device(means.device):
+    with _capi.device_guard(means.device):
         scratch = torch.empty(_lib.fgs_densify_scratch_bytes(n), dtype=torch.uint8, device=means.device)
         _capi.check(_lib.fgs_morton_keys(means.data_ptr(), n, scratch.data_ptr(), codes.data_ptr(), None, None, None, _stream()),
                     'morton_keys')
@@ -196,7 +196,7 @@ def morton_order(means: torch.Tensor) -> torch.Tensor:
     order = torch.empty(n, dtype=torch.int64, device=dev)
     if n == 0:
         return order
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         u32 = lambda: torch.empty(n, dtype=torch.int32, device=dev)
         lo, hi, idx, lo_alt, idx_alt, hi_sorted = u32(), u32(), u32(), u32(), u32(), u32()
         scratch = torch.empty(_lib.fgs_densify_scratch_bytes(n), dtype=torch.uint8, device=dev)
@@ -235,7 +235,7 @@ def adaptive_density_control(optimizer, densification_info: torch.Tensor, grad_t
     if tuple(info.shape) != (2, n):
         raise RuntimeError("'densification_info' must have shape (2, N)")
     flags = torch.empty(n, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _capi.device_guard(dev):
         rc = _lib.fgs_adc_flags(info.data_ptr(), _check(scales, 'scales').data_ptr(), _check(rotations, 'rotations').data_ptr(),
                                 _check(opacities, 'opacities').data_ptr(), n, float(grad_threshold),
                                 float(math.log(percent_dense * training_cameras_extent)),

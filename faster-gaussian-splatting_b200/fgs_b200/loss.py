@@ -21,7 +21,7 @@ _lib = _capi.load()
 
 
 def _check(image: torch.Tensor, target: torch.Tensor):
-    if not (image.is_cuda and image.dtype == torch.float32 and image.dim() == 3 and image.shape[0] == 3):
+    if not (_capi.on_device(image) and image.dtype == torch.float32 and image.dim() == 3 and image.shape[0] == 3):
         raise RuntimeError("'image' must be a CUDA float tensor of shape (3, H, W).")
     if target.shape != image.shape or target.device != image.device or target.dtype not in (torch.float32, torch.uint8):
         raise RuntimeError("'target' must be a float32 or uint8 tensor of the image's shape on the image's device.")
@@ -41,7 +41,7 @@ def _scratch(image: torch.Tensor) -> torch.Tensor:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _capi.current_stream()
 
 
 @torch.no_grad()
@@ -49,7 +49,7 @@ def l1_dssim_loss_and_grad(image, target, lambda_l1: float, lambda_dssim: float)
     """-> (terms (3,) = [loss, l1, dssim] on the device, grad_image (3,H,W)) with dL/dloss = 1; no host sync."""
     image, target = _check(image, target)
     _, h, w = image.shape
-    with torch.cuda.device(image.device):
+    with _capi.device_guard(image.device):
         scratch = _scratch(image)
         terms = torch.empty(3, dtype=torch.float32, device=image.device)
         grad = torch.empty_like(image)
@@ -65,7 +65,7 @@ class _L1DSSIM(torch.autograd.Function):
     def forward(ctx, image, target, lambda_l1, lambda_dssim):
         image_c, target_c = _check(image, target)
         _, h, w = image_c.shape
-        with torch.cuda.device(image_c.device):
+        with _capi.device_guard(image_c.device):
             scratch = _scratch(image_c)
             terms = torch.empty(3, dtype=torch.float32, device=image_c.device)
             rc = _lib.fgs_loss_forward(image_c.data_ptr(), target_c.data_ptr(), int(target_c.dtype == torch.uint8), w, h,
@@ -82,7 +82,7 @@ class _L1DSSIM(torch.autograd.Function):
     def backward(ctx, grad_loss, _grad_terms):
         image, target, scratch = ctx.saved_tensors
         _, h, w = image.shape
-        with torch.cuda.device(image.device):
+        with _capi.device_guard(image.device):
             gl = grad_loss.to(device=image.device, dtype=torch.float32).reshape(1).contiguous()
             grad = torch.empty_like(image)
             rc = _lib.fgs_loss_backward(image.data_ptr(), target.data_ptr(), int(target.dtype == torch.uint8), w, h,

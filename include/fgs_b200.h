@@ -146,7 +146,8 @@ int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const flo
  * with SSIM as in NeRFICG's fused_dssim / the published fused-ssim kernel (11x11 Gaussian window, sigma 1.5, zero
  * padding, C1 = 0.01^2, C2 = 0.03^2; not in the reference tree: parity pinned by oracle/loss_oracle.py only).
  * image and grad_image are (3,H,W) float32; target is (3,H,W) float32, or uint8 (value / 255) if target_is_u8.
- * `scratch` is a caller-owned device buffer of fgs_loss_scratch_bytes(width, height) bytes, 128-byte aligned, that
+ * `scratch` is a caller-owned device buffer of fgs_loss_scratch_bytes(width, height) bytes, 16-byte aligned (like image,
+ * grad_image and a float target; a uint8 target 4-byte), that
  * must stay untouched between fgs_loss_forward and the matching fgs_loss_backward.  loss_out receives three
  * floats on the device: the weighted loss, the L1 term, the DSSIM term.  grad_loss is a DEVICE pointer to
  * dL/dloss (NULL: 1); nothing here synchronises with the host. */

@@ -1,0 +1,195 @@
+"""TEST INFRASTRUCTURE ONLY (run as a subprocess by tests/test_emulated_python_layer.py).
+
+Runs the product's Python layer -- fgs_b200._C, torch_bindings (autograd Functions, FusedAdam), fgs_b200.loss,
+fgs_b200.densification -- UNCHANGED on host tensors against the emulated build of the whole library
+(FGS_B200_LIB -> tests/cuda_emu 'all'), with the three torch.cuda touch points of fgs_b200._capi replaced.  This checks the
+argument marshalling, tensor shapes, autograd contracts and optimizer-state handling of the Python layer without a GPU;
+the numerics are those of the emulated kernels (IEEE float32)."""
+import contextlib
+import math
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / 'faster-gaussian-splatting_b200')]
+
+from tests import cuda_emu  # noqa: E402
+
+os.environ['FGS_B200_LIB'] = str(cuda_emu.library_path('all'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from fgs_b200 import _capi  # noqa: E402
+
+_capi.on_device = lambda t: True
+_capi.current_stream = lambda: None
+_capi.device_guard = lambda device: contextlib.nullcontext()
+
+import fgs_b200  # noqa: E402
+from fgs_b200 import densification as D  # noqa: E402
+from fgs_b200 import loss as L  # noqa: E402
+from fgs_b200 import synthetic as syn  # noqa: E402
+from oracle import densify_oracle as DO  # noqa: E402
+from oracle import loss_oracle as LO  # noqa: E402
+from oracle import torch_oracle as O  # noqa: E402
+from tests import util  # noqa: E402
+
+NAMES = ('means', 'scales', 'rotations', 'opacities', 'sh_coefficients_0', 'sh_coefficients_rest')
+LRS = dict(means=1.6e-4, scales=5e-3, rotations=1e-3, opacities=2.5e-2, sh_coefficients_0=2.5e-3, sh_coefficients_rest=1.25e-4)
+
+
+def check_rasterizer_api():
+    n, w, h = 300, 64, 48
+    sc, cam = syn.make_scene(n, 4), syn.make_camera(4, w, h)
+    st = util.settings_for(cam, bg=(0.1, 0.2, 0.3))
+    gi = syn.make_grad_image(w, h, 4)
+    params = [p.clone().requires_grad_(True) for p in sc]
+    dens = torch.zeros(2, n)
+    rs = fgs_b200.RasterizerSettings(*st)
+    img = fgs_b200.diff_rasterize(*params, dens, rs)
+    assert tuple(img.shape) == (3, h, w) and not dens.requires_grad
+    img.backward(gi)
+    dens64 = torch.zeros(2, n, dtype=torch.float64)
+    out, ograds = O.render_and_grads(list(sc), O.Settings(*st), gi, dtype=torch.float64, densification_info=dens64)
+    assert (img.detach().double() - out.image).abs().mean().item() <= 2e-6
+    for p, og in zip(params, ograds):
+        assert tuple(p.grad.shape) == tuple(p.shape) and util.rel_err(p.grad, og) <= 2e-4
+    assert torch.equal(dens[0].double(), dens64[0]) and util.rel_err(dens[1], dens64[1]) <= 2e-4
+    # inference entry point: (H,W,3) clamped / (3,H,W)
+    with torch.no_grad():
+        hwc = fgs_b200.rasterize(*sc, rs, to_chw=False)
+        chw = fgs_b200.rasterize(*sc, rs, to_chw=True, clamp_output=False)
+    assert tuple(hwc.shape) == (h, w, 3) and (hwc.permute(2, 0, 1) - img.detach().clamp(0, 1)).abs().max().item() <= 1e-6
+    assert (chw - img.detach()).abs().max().item() <= 1e-6
+    # FusedAdam.step vs torch.optim.Adam on the same gradients; fused backward+Adam == backward-then-step
+    opt = fgs_b200.FusedAdam([{'params': [p], 'lr': LRS[k], 'name': k} for p, k in zip(params, NAMES)], lr=0.0, eps=1e-15)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in params]
+    ref = torch.optim.Adam([{'params': [p], 'lr': LRS[k]} for p, k in zip(ref_params, NAMES)], lr=0.0, eps=1e-15)
+    for p, q in zip(params, ref_params):
+        q.grad = p.grad.clone()
+    opt.step()
+    ref.step()
+    for p, q, p0 in zip(params, ref_params, sc):
+        assert util.rel_err(p.detach() - p0, q.detach() - p0) <= 1e-4
+    opt.zero_grad()
+    fparams = [p.clone().requires_grad_(True) for p in sc]
+    fopt = fgs_b200.FusedAdam([{'params': [p], 'lr': LRS[k], 'name': k} for p, k in zip(fparams, NAMES)], lr=0.0, eps=1e-15)
+    fimg = fgs_b200.diff_rasterize_fused(*fparams, torch.empty(0), rs, fopt)
+    fimg.backward(gi)
+    assert all(p.grad is None for p in fparams)
+    fopt.step()  # no-op: no gradients
+    for p, q, p0 in zip(fparams, params, sc):
+        assert util.rel_err(p.detach() - p0, q.detach() - p0) <= 1e-4
+        assert fopt.state[p]['step'] == 1 and util.rel_err(fopt.state[p]['exp_avg'], opt.state[q]['exp_avg']) <= 1e-5
+    # pruning scores and the small operators go through the same marshalling
+    scores = torch.zeros(n)
+    fgs_b200.update_pruning_scores(scores, *sc, rs)
+    assert util.rel_err(scores, O.pruning_scores(*sc, O.Settings(*st))) <= 2e-4
+    print('rasterizer API ok')
+
+
+def check_loss_api():
+    g = torch.Generator().manual_seed(0)
+    w, h = 50, 37
+    image = torch.rand(3, h, w, generator=g)
+    target8 = (torch.rand(3, h, w, generator=g) * 255).round().to(torch.uint8)
+    for tgt, l1w, dsw in ((target8, 0.8, 0.2), (target8.float() / 255, 1.0, 0.0)):
+        terms, grad = L.l1_dssim_loss_and_grad(image, tgt, l1w, dsw)
+        loss, l1, ds, g64 = LO.loss_and_grad(image, tgt, l1w, dsw)
+        assert abs(float(terms[0]) - float(loss)) <= 2e-5 and util.rel_err(grad, g64) <= 2e-4
+        x = image.clone().requires_grad_(True)
+        out, terms2 = L.l1_dssim_loss(x, tgt, l1w, dsw, return_terms=True)
+        assert out.dim() == 0 and not terms2.requires_grad
+        (out * 0.37).backward()
+        assert util.rel_err(x.grad, g64 * 0.37) <= 2e-4
+    # a view at an odd offset is copied, not faulted on
+    stack = torch.rand(2, 3, 5, 7, generator=g)
+    t, gr = L.l1_dssim_loss_and_grad(stack[1], stack[0], 1.0, 0.0)
+    assert abs(float(t[0]) - float((stack[1] - stack[0]).abs().mean())) <= 1e-6
+    print('loss API ok')
+
+
+def _optimizer(state):
+    params = {k: torch.nn.Parameter(state[k].clone()) for k in NAMES}
+    opt = fgs_b200.FusedAdam([{'params': [params[k]], 'lr': 1e-3, 'name': k} for k in NAMES], lr=0.0, eps=1e-15)
+    for k in NAMES:
+        opt.state[params[k]] = {'step': 7, 'exp_avg': state['exp_avg.' + k].clone(), 'exp_avg_sq': state['exp_avg_sq.' + k].clone()}
+    return opt
+
+
+def _state_of(opt, groups):
+    out = {}
+    for name, p in groups.items():
+        out[name] = p.detach()
+        st = opt.state[p]
+        assert st['step'] == 7
+        out['exp_avg.' + name], out['exp_avg_sq.' + name] = st['exp_avg'], st['exp_avg_sq']
+    assert [g['params'][0] for g in opt.param_groups] == [groups[g['name']] for g in opt.param_groups] and len(opt.state) == 6
+    return out
+
+
+def check_densification_api():
+    from tests.test_widen_densify import ADC, compare_states, fixed_randn, make_state
+    n = 1300
+    state, info = make_state(n, seed=8)
+    want, z = DO.adaptive_density_control(state, info, ADC['grad_threshold'], ADC['min_opacity'], True, ADC['percent_dense'],
+                                          ADC['extent'], fixed_randn(5))
+    opt = _optimizer(state)
+    groups = D.adaptive_density_control(opt, info, ADC['grad_threshold'], ADC['min_opacity'], True, ADC['percent_dense'],
+                                        ADC['extent'], randn=lambda shape: z.reshape(shape))
+    compare_states(_state_of(opt, groups), want, 'adc through the Python layer')
+    g = torch.Generator().manual_seed(1)
+    m = want['means'].shape[0]
+    prune_mask = torch.rand(m, generator=g) < 0.25
+    extra = torch.arange(2 * m, dtype=torch.float32).reshape(m, 2)
+    groups, (extra_new,) = D.prune_param_groups(opt, ~prune_mask, extras=[extra])
+    s1 = DO.prune(want, prune_mask)
+    compare_states(_state_of(opt, groups), s1, 'prune')
+    assert torch.equal(extra_new, extra[~prune_mask])
+    means = groups['means'].detach()
+    codes = D.morton_encode(means)
+    assert torch.equal(codes, DO.morton_encode(means))
+    order = D.morton_order(means)
+    assert torch.equal(order, torch.sort(codes, stable=True).indices)
+    groups = D.sort_param_groups(opt, order)
+    s2 = DO.sort(s1, order)
+    compare_states(_state_of(opt, groups), s2, 'morton sort')
+    new = {k: torch.randn((33,) + tuple(state[k].shape[1:]), generator=g) for k in NAMES}
+    groups = D.extend_param_groups(opt, new)
+    s3 = DO.extend(s2, new)
+    compare_states(_state_of(opt, groups), s3, 'extend')
+    idx = torch.randperm(s3['means'].shape[0], generator=g)[:77]
+    D.reset_state(opt, idx)
+    compare_states(_state_of(opt, groups), DO.reset_state(s3, idx), 'reset_state')
+    for p in groups.values():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert opt.state[groups['means']]['step'] == 8
+    print('densification API ok')
+
+
+def check_training_loop():
+    """tests/test_widen_training.py's loop (render -> L1 + DSSIM -> backward -> step, densification, Morton reordering) at a
+    size the emulator finishes in seconds: the plumbing between the modules, not the convergence."""
+    from tests import test_widen_training as T
+    T.N, T.W, T.H, T.VIEWS, T.ITERS = 150, 48, 36, 2, 6
+    settings, targets, init, _ = T._problem('cpu')
+    psnr0 = T._psnr(fgs_b200, init, settings, targets)
+    params = T._train(fgs_b200, init, settings, targets, iters=6, loss_fn=lambda a, b: L.l1_dssim_loss(a, b, 0.8, 0.2),
+                      densify_at=(3,), morton_at=(4,))
+    p1 = T._psnr(fgs_b200, params, settings, targets)
+    pf = T._psnr(fgs_b200, T._train(fgs_b200, init, settings, targets, iters=6, fused=True), settings, targets)
+    pd = T._psnr(fgs_b200, T._train(fgs_b200, init, settings, targets, iters=6), settings, targets)
+    assert math.isfinite(p1) and abs(pf - pd) <= 0.05, (psnr0, p1, pf, pd)
+    print(f'training loop ok: PSNR {psnr0:.2f} -> {pd:.2f} (drop-in) / {pf:.2f} (fused) / {p1:.2f} (DSSIM + densify, N {T.N} -> {params["means"].shape[0]})')
+
+
+if __name__ == '__main__':
+    torch.cuda.synchronize = lambda *a, **k: None  # the training helper ends with a synchronize
+    which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'training']
+    for name in which:
+        {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
+         'training': check_training_loop}[name]()
+    print('ALL OK')

@@ -9,6 +9,7 @@ analytic backward, fused backward + Adam -- against the golden vectors dumped fr
 (tests/golden/*.npz) and against the fp64 oracle.  The emulator computes in IEEE float32 (no fast-math), so the bounds
 against the oracle are far tighter than the GPU ones.  It does not model asynchrony or performance; the GPU suite
 (tests/test_parity_gpu.py) remains the parity test proper."""
+import os
 from pathlib import Path
 
 import numpy as np
@@ -41,7 +42,7 @@ def _case(name):
     return z, sc, st, syn.make_grad_image(w, h, seed)
 
 
-@pytest.mark.parametrize('name', ['c1_deg3', 'c1_deg1', 'c1_deg0', 'c1_aa', 'ragged'])
+@pytest.mark.parametrize('name', ['c1_deg3', 'c1_aa', 'ragged'] + (['c1_deg1', 'c1_deg0'] if os.environ.get('FGS_TEST_SLOW') == '1' else []))
 def test_emulated_kernels_match_reference_golden(emu, name):
     """The kernel source against outputs of the unmodified reference backend (image, inference image, six gradients,
     densification statistics)."""

@@ -1,0 +1,20 @@
+"""The product's Python layer (fgs_b200._C, torch_bindings, loss, densification) run UNCHANGED on host tensors against the
+emulated build of the whole library (tests/cuda_emu 'all', selected with FGS_B200_LIB), in a subprocess so that this
+process keeps the real libfgs_b200.so.  See tests/emu_python_layer.py for what is compared.  The mini training loop (the
+code of tests/test_widen_training.py at a toy size, ~3 min) only runs with FGS_TEST_SLOW=1."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
+PARTS = ['rasterizer', 'loss', 'densification'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
+
+
+@pytest.mark.parametrize('part', PARTS)
+def test_python_layer_on_emulated_library(part):
+    env = {k: v for k, v in os.environ.items() if k != 'FGS_B200_LIB'}
+    r = subprocess.run([sys.executable, str(SCRIPT), part], capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0 and 'ALL OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

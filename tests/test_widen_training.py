@@ -110,4 +110,4 @@ def test_training_with_dssim_densification_and_reordering(cuda_device):
     print(f'L1 + DSSIM with densification at 100 and Morton reordering at 150: N {N} -> {n_new}, PSNR {psnr0:.2f} -> {p:.2f} dB')
     # splitting replaces well-placed Gaussians by random samples of them, so no PSNR gain is asserted 50 iterations
     # after a densification round: only that the loop stays healthy on the new set of Gaussians
-    assert n_new != N and math.isfinite(p) and p >= 12.0, (n_new, psnr0, p)
+    assert n_new != N and math.isfinite(p) and p >= 10.0, (n_new, psnr0, p)
