@@ -157,34 +157,51 @@ inline thread_local WarpCtx* t_warp = nullptr;
 inline thread_local int t_lane = 0;
 inline thread_local unsigned char* t_dyn_smem = nullptr;  // the running block's dynamic shared memory
 
+// Order in which the blocks of a grid run.  Hardware promises none, so a kernel must not depend on it (kernels with
+// inter-block dependencies take their logical block id from an atomic ticket).  FGS_EMU_BLOCK_ORDER=reverse|shuffle
+// makes the emulator run the blocks in another order than 0, 1, 2, ... to check exactly that.
+inline std::vector<unsigned> block_order(unsigned n) {
+    std::vector<unsigned> order(n);
+    for (unsigned i = 0; i < n; ++i) order[i] = i;
+    const char* mode = std::getenv("FGS_EMU_BLOCK_ORDER");
+    if (mode && std::strcmp(mode, "reverse") == 0) std::reverse(order.begin(), order.end());
+    if (mode && std::strcmp(mode, "shuffle") == 0) {
+        static uint64_t state = 0x9e3779b97f4a7c15ull;
+        for (unsigned i = n; i > 1; --i) {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            std::swap(order[i - 1], order[(state >> 33) % i]);
+        }
+    }
+    return order;
+}
+
 template <typename F>
 void launch(dim3 grid, dim3 block, F&& body, size_t dyn_smem_bytes = 0) {
     const int threads = (int)(block.x * block.y * block.z);
     std::vector<unsigned char> dyn(dyn_smem_bytes + 256);
     unsigned char* dyn_base = dyn.data() + (256 - reinterpret_cast<uintptr_t>(dyn.data()) % 256) % 256;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                BlockCtx ctx(threads);
-                std::vector<std::thread> pool;
-                pool.reserve(threads);
-                for (int t = 0; t < threads; ++t)
-                    pool.emplace_back([&, t] {
-                        t_threadIdx = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-                        t_blockIdx = {bx, by, bz};
-                        t_blockDim = block;
-                        t_gridDim = grid;
-                        t_block = &ctx;
-                        t_warp = ctx.warps[t / 32].get();
-                        t_lane = t % 32;
-                        t_dyn_smem = dyn_base;
-                        body();
-                        t_warp->live.fetch_and(~(1u << t_lane));
-                        t_warp->bar.arrive_and_drop();  // a finished thread no longer takes part in barriers
-                        ctx.bar.arrive_and_drop();
-                    });
-                for (auto& th : pool) th.join();
-            }
+    for (unsigned linear : block_order(grid.x * grid.y * grid.z)) {
+        const unsigned bx = linear % grid.x, by = (linear / grid.x) % grid.y, bz = linear / (grid.x * grid.y);
+        BlockCtx ctx(threads);
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (int t = 0; t < threads; ++t)
+            pool.emplace_back([&, t] {
+                t_threadIdx = {(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+                t_blockIdx = {bx, by, bz};
+                t_blockDim = block;
+                t_gridDim = grid;
+                t_block = &ctx;
+                t_warp = ctx.warps[t / 32].get();
+                t_lane = t % 32;
+                t_dyn_smem = dyn_base;
+                body();
+                t_warp->live.fetch_and(~(1u << t_lane));
+                t_warp->bar.arrive_and_drop();  // a finished thread no longer takes part in barriers
+                ctx.bar.arrive_and_drop();
+            });
+        for (auto& th : pool) th.join();
+    }
 }
 
 // Kernels without barriers or warp collectives (declared so at the launch site with FGS_LAUNCH_SERIAL): every CUDA
@@ -196,18 +213,16 @@ void launch_serial(dim3 grid, dim3 block, F&& body) {
     t_warp = nullptr;
     t_blockDim = block;
     t_gridDim = grid;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                t_blockIdx = {bx, by, bz};
-                for (unsigned tz = 0; tz < block.z; ++tz)
-                    for (unsigned ty = 0; ty < block.y; ++ty)
-                        for (unsigned tx = 0; tx < block.x; ++tx) {
-                            t_threadIdx = {tx, ty, tz};
-                            t_lane = (int)((tx + block.x * (ty + block.y * tz)) % 32);
-                            body();
-                        }
-            }
+    for (unsigned linear : block_order(grid.x * grid.y * grid.z)) {
+        t_blockIdx = {linear % grid.x, (linear / grid.x) % grid.y, linear / (grid.x * grid.y)};
+        for (unsigned tz = 0; tz < block.z; ++tz)
+            for (unsigned ty = 0; ty < block.y; ++ty)
+                for (unsigned tx = 0; tx < block.x; ++tx) {
+                    t_threadIdx = {tx, ty, tz};
+                    t_lane = (int)((tx + block.x * (ty + block.y * tz)) % 32);
+                    body();
+                }
+    }
 }
 
 template <typename T>
