@@ -179,6 +179,9 @@ def run_gpu(args, impl):
         return (it * world + rank) % N_VIEWS
 
     use_fused = (impl == 'mine') and dist is None and not args.unfused
+    if impl == 'mine' and getattr(args, 'overlap_adam', False):
+        from fgs_b200 import _capi
+        _capi.load().fgs_debug_set_overlap_adam(1)
     fused_loss = (impl == 'mine') and getattr(args, 'fused_loss', False)
     if fused_loss:
         from fgs_b200 import loss as loss_mod
@@ -404,6 +407,7 @@ def run_gpu(args, impl):
                    'parallelism': f'view-dp{world}' if world > 1 else 'single',
                    'optimizer_path': ('fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' if use_fused
                                       else 'backward, then FusedAdam.step'),
+                   'adam_schedule': 'overlapped (side-stream Adam of invisible rows)' if getattr(args, 'overlap_adam', False) and impl == 'mine' else 'default',
                    'loss_path': 'fused L1 kernel (csrc/loss.cu)' if fused_loss else 'torch ops: (img - gt).abs().mean()',
                    'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
         'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
@@ -580,6 +584,9 @@ def main():
     ap.add_argument('--fused-loss', action='store_true',
                     help='EXPERIMENTAL (not yet measured on hardware): L1 loss and its gradient from csrc/loss.cu instead '
                          'of the seven torch kernels of (img - gt).abs().mean() + backward')
+    ap.add_argument('--overlap-adam', action='store_true',
+                    help='EXPERIMENTAL (not yet measured on hardware): fused path with the zero-gradient Adam of invisible '
+                         'Gaussians\' sh_rest rows on a side stream under the blend backward (fgs_debug_set_overlap_adam)')
     ap.add_argument('--peer-adam', action='store_true',
                     help='N > 1 only, EXPERIMENTAL: gradient reduction + Adam + parameter broadcast in one kernel over '
                          'NVLink peer memory (fgs_b200.parallel.PeerAdam) instead of NCCL all-reduce + FusedAdam.step')

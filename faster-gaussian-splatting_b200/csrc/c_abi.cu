@@ -8,6 +8,7 @@
 // work goes to the caller's stream; no bucket buffers.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fgs_b200.h"
@@ -234,6 +235,13 @@ cudaError_t ensure_readback() {
 // function-local static stream, forward.cu:47-53).
 int g_capacity_hint = 0;
 
+// Opt-in overlapped schedule of the fused backward + Adam (see backward_impl); FGS_OVERLAP_ADAM=1 in the environment or
+// fgs_debug_set_overlap_adam(1).  Off by default until it has been measured on hardware.
+bool g_overlap_adam = [] {
+    const char* e = std::getenv("FGS_OVERLAP_ADAM");
+    return e != nullptr && e[0] == '1';
+}();
+
 int next_capacity_hint(int n_instances, int current) {
     // grow with 25 % head-room, shrink only when more than half of the buffer is unused: sizes stay stable
     const long long want = (long long)n_instances + n_instances / 4 + 65536;
@@ -400,6 +408,20 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
                                ? InstanceLayout<uint16_t>(const_cast<char*>(instance_buffers), state->n_instances, end_bit).inst_recs
                                : InstanceLayout<uint32_t>(const_cast<char*>(instance_buffers), state->n_instances, end_bit).inst_recs;
     Grad2D* grad2d = reinterpret_cast<Grad2D*>(grad2d_scratch);
+    pa.n_touched = pl.n_touched;
+    pa.n = n;
+    // Overlapped schedule (opt-in): the zero-gradient Adam update of the sh_rest rows of invisible Gaussians -- pure HBM
+    // traffic that depends on nothing the blend backward produces -- runs on the side stream while the issue-bound blend
+    // backward leaves the memory system idle; the preprocess backward then skips those rows.
+    const bool overlap = g_overlap_adam && state->n_instances > 0 && preprocess_backward_can_overlap(pa, cam);
+    if (overlap) {
+        FGS_TRY(ensure_readback(), "side stream");
+        Readback& rb = readback();
+        FGS_TRY(cudaEventRecord(rb.counted, stream), "event record (overlap)");
+        FGS_TRY(cudaStreamWaitEvent(rb.stream, rb.counted, 0), "side stream wait (overlap)");
+        FGS_TRY(launch_adam_rest_invisible(pa, cam, rb.stream), "adam_rest_invisible");
+        FGS_TRY(cudaEventRecord(rb.event, rb.stream), "event record (overlap)");
+    }
     FGS_TRY(cudaMemsetAsync(grad2d, 0, sizeof(Grad2D) * (size_t)n, stream), "memset grad2d");
     if (state->n_instances > 0) {
         FGS_TRY(cudaMemsetAsync(pl.counters + kCtrTileQueueBwd, 0, sizeof(uint32_t), stream), "memset queue");
@@ -421,11 +443,10 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
     pa.rotations = rotations;
     pa.opacities = opacities;
     pa.sh_rest = sh_rest;
-    pa.n_touched = pl.n_touched;
     pa.grad2d = grad2d;
     pa.densification_info = densification_info;
-    pa.n = n;
-    FGS_KERNEL(launch_preprocess_backward(pa, cam, stream), "preprocess_backward");
+    if (overlap) FGS_TRY(cudaStreamWaitEvent(stream, readback().event, 0), "join side stream (overlap)");
+    FGS_KERNEL(launch_preprocess_backward(pa, cam, stream, overlap), "preprocess_backward");
     return 0;
 }
 
@@ -617,6 +638,9 @@ int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const flo
             "add_noise");
     return 0;
 }
+
+void fgs_debug_set_overlap_adam(int32_t on) { g_overlap_adam = on != 0; }
+int32_t fgs_debug_get_overlap_adam(void) { return g_overlap_adam ? 1 : 0; }
 
 void fgs_debug_set_capacity_hint(int32_t capacity) { g_capacity_hint = capacity > 0 ? capacity : 0; }
 int32_t fgs_debug_get_capacity_hint(void) { return g_capacity_hint; }

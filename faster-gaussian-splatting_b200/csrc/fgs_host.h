@@ -139,7 +139,12 @@ struct PreBwdArgs {
     bool fused;
     int n;
 };
-cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream);
+cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, bool skip_invisible_rest = false);
+// Overlapped schedule of the fused backward + Adam (opt-in, fgs_debug_set_overlap_adam): the zero-gradient Adam update of
+// the sh_rest rows of invisible Gaussians runs on a side stream while the blend backward runs;
+// launch_preprocess_backward(..., skip_invisible_rest = true) then leaves those rows alone.  Results are bit-identical.
+bool preprocess_backward_can_overlap(const PreBwdArgs& a, const Cam& cam);
+cudaError_t launch_adam_rest_invisible(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream);
 
 cudaError_t launch_adam(const float* grad, float* param, float* exp_avg, float* exp_avg_sq, size_t n, float step_size,
                         float beta1, float beta2, float eps, float bias2_sqrt_rcp, cudaStream_t stream);

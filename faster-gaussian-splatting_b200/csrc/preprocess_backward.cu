@@ -111,6 +111,97 @@ __device__ __forceinline__ void emit_span(const float* __restrict__ stage, float
     }
 }
 
+// Fused Adam restricted to the rows of `row_mask` (bit r = row r of the warp's 32 Gaussians; `row_floats` floats per
+// row, 9 <= row_floats <= 45 so a float4 touches at most two rows).  float4s without such a row are neither read nor
+// written; elements of other rows inside a shared float4 are written back unchanged.  `stage` == nullptr: zero
+// gradient (the dense-Adam decay of a Gaussian that was not visible).  Used by the overlapped schedule: the rows of
+// invisible Gaussians are updated by adam_rest_invisible_kernel while the blend backward runs, the visible ones here.
+template <int kU>
+__device__ __forceinline__ void emit_span_rows(const float* __restrict__ stage, float* __restrict__ p, float* __restrict__ m,
+                                               float* __restrict__ v, size_t first_elem, int n_floats, int row_floats,
+                                               uint32_t row_mask, float step_size, float beta1, float beta2, float eps,
+                                               float b2, int lane) {
+    float* pp = p + first_elem;
+    float* mm = m + first_elem;
+    float* vv = v + first_elem;
+    const uint32_t magic = (65536u + (uint32_t)row_floats - 1u) / (uint32_t)row_floats;  // e / row_floats == (e * magic) >> 16, e < 32 * 45
+    const bool vec = (n_floats & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(mm) | reinterpret_cast<uintptr_t>(vv)) & 15u) == 0;
+    if (vec) {
+        const int n4 = n_floats >> 2;
+        for (int i0 = lane; i0 < n4; i0 += 32 * kU) {
+            float4 p4[kU], m4[kU], v4[kU];
+            uint32_t sel[kU];  // bit c: element c of the float4 belongs to a row of the mask
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + 32 * u;
+                sel[u] = 0u;
+                if (i < n4) {
+                    const uint32_t e0 = 4u * (uint32_t)i;
+                    const uint32_t r0 = (e0 * magic) >> 16, r1 = ((e0 + 3u) * magic) >> 16;
+                    const uint32_t first_of_r1 = r1 * (uint32_t)row_floats;  // elements >= this index belong to row r1
+#pragma unroll
+                    for (uint32_t c = 0; c < 4u; ++c) sel[u] |= ((row_mask >> (e0 + c >= first_of_r1 ? r1 : r0)) & 1u) << c;
+                    if (sel[u]) {
+                        p4[u] = reinterpret_cast<const float4*>(pp)[i];
+                        m4[u] = reinterpret_cast<const float4*>(mm)[i];
+                        v4[u] = reinterpret_cast<const float4*>(vv)[i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int i = i0 + 32 * u;
+                if (sel[u]) {
+                    const float4 g4 = stage ? reinterpret_cast<const float4*>(stage)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sel[u] & 1u) adam_update(g4.x, p4[u].x, m4[u].x, v4[u].x, step_size, beta1, beta2, eps, b2);
+                    if (sel[u] & 2u) adam_update(g4.y, p4[u].y, m4[u].y, v4[u].y, step_size, beta1, beta2, eps, b2);
+                    if (sel[u] & 4u) adam_update(g4.z, p4[u].z, m4[u].z, v4[u].z, step_size, beta1, beta2, eps, b2);
+                    if (sel[u] & 8u) adam_update(g4.w, p4[u].w, m4[u].w, v4[u].w, step_size, beta1, beta2, eps, b2);
+                    reinterpret_cast<float4*>(pp)[i] = p4[u];
+                    reinterpret_cast<float4*>(mm)[i] = m4[u];
+                    reinterpret_cast<float4*>(vv)[i] = v4[u];
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < n_floats; i += 32) {
+            if ((row_mask >> (((uint32_t)i * magic) >> 16)) & 1u) {
+                float pe = pp[i], me = mm[i], ve = vv[i];
+                adam_update(stage ? stage[i] : 0.0f, pe, me, ve, step_size, beta1, beta2, eps, b2);
+                pp[i] = pe;
+                mm[i] = me;
+                vv[i] = ve;
+            }
+        }
+    }
+}
+
+// Overlapped schedule, part 1 (side stream, while the blend backward runs): dense Adam with zero gradient on the
+// sh_rest rows of the Gaussians that were not visible in this view -- 76 % of the parameter bytes of 39 % of the
+// Gaussians at C2.  At most one small CTA per SM (<= 32 registers, no shared memory) so that it fits next to the
+// three resident CTAs of the blend backward.
+__global__ void __launch_bounds__(128, 16) adam_rest_invisible_kernel(const uint32_t* __restrict__ n_touched, float* __restrict__ p,
+                                                                      float* __restrict__ m, float* __restrict__ v, const int n,
+                                                                      const int row_floats, const float step_size,
+                                                                      const float beta1, const float beta2, const float eps,
+                                                                      const float b2) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = (n + 31) >> 5;
+    for (int group = blockIdx.x * 4 + warp; group < groups; group += gridDim.x * 4) {
+        const int wfirst = group << 5;
+        const int rows = min(32, n - wfirst);
+        const bool invisible = lane < rows && __ldg(n_touched + wfirst + lane) == 0u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, invisible);
+        if (mask == 0u) continue;
+        emit_span_rows<1>(nullptr, p, m, v, (size_t)wfirst * row_floats, rows * row_floats, row_floats, mask, step_size, beta1,
+                          beta2, eps, b2, lane);
+    }
+}
+
+// kSkipInvisibleRest: the sh_rest rows of invisible Gaussians have already been updated by adam_rest_invisible_kernel
+// (fused mode only); everything else is identical.
+template <bool kSkipInvisibleRest>
 __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBwdArgs a, const Cam cam) {
     FGS_DYNAMIC_SMEM(float, s_stage, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -384,9 +475,16 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
               h.eps, h.bias2_sqrt_rcp[3], lane);
     emit_span(st + kOffSh0, a.g_sh0, a.p[4], a.m[4], a.v[4], w0 * 3, rows * 3, a.fused, h.step_size[4], h.beta1, h.beta2,
               h.eps, h.bias2_sqrt_rcp[4], lane);
-    if (rest_floats > 0)
-        emit_span(rest, a.g_sh_rest, a.p[5], a.m[5], a.v[5], w0 * rest_floats, rows * rest_floats, a.fused,
-                  h.step_size[5], h.beta1, h.beta2, h.eps, h.bias2_sqrt_rcp[5], lane);
+    if (rest_floats > 0) {
+        if (kSkipInvisibleRest) {
+            if (vis_mask != 0u)
+                emit_span_rows<4>(rest, a.p[5], a.m[5], a.v[5], w0 * rest_floats, rows * rest_floats, rest_floats, vis_mask,
+                                  h.step_size[5], h.beta1, h.beta2, h.eps, h.bias2_sqrt_rcp[5], lane);
+        } else {
+            emit_span(rest, a.g_sh_rest, a.p[5], a.m[5], a.v[5], w0 * rest_floats, rows * rest_floats, a.fused,
+                      h.step_size[5], h.beta1, h.beta2, h.eps, h.bias2_sqrt_rcp[5], lane);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const float* __restrict__ grad, float* __restrict__ param,
@@ -421,16 +519,43 @@ __global__ void __launch_bounds__(256) adam_kernel(const float* __restrict__ gra
 
 }  // namespace
 
-cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream) {
+cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, bool skip_invisible_rest) {
     if (a.n <= 0) return cudaSuccess;
     static bool s_attr = false;
     const size_t smem = (size_t)kWarps * kWarpFloats * sizeof(float);
     if (!s_attr) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(preprocess_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         s_attr = true;
     }
-    FGS_LAUNCH_SMEM(preprocess_backward_kernel, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
+    if (skip_invisible_rest && a.fused)
+        FGS_LAUNCH_SMEM(preprocess_backward_kernel<true>, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
+    else
+        FGS_LAUNCH_SMEM(preprocess_backward_kernel<false>, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
+    return cudaGetLastError();
+}
+
+bool preprocess_backward_can_overlap(const PreBwdArgs& a, const Cam& cam) {
+    const int rest_floats = cam.total_sh_rest * 3;
+    return a.fused && a.n > 0 && rest_floats >= 9 && rest_floats <= 45;
+}
+
+cudaError_t launch_adam_rest_invisible(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream) {
+    if (!preprocess_backward_can_overlap(a, cam)) return cudaSuccess;
+    static int s_sms = 0;
+    if (s_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (s_sms < 1) s_sms = 1;
+    }
+    const int groups = (a.n + 31) / 32;
+    const int grid = (groups + 3) / 4 < s_sms ? (groups + 3) / 4 : s_sms;  // at most one CTA per SM
+    const AdamHyper& h = a.hyper;
+    FGS_LAUNCH(adam_rest_invisible_kernel, grid, 128, stream, a.n_touched, a.p[5], a.m[5], a.v[5], a.n, cam.total_sh_rest * 3,
+               h.step_size[5], h.beta1, h.beta2, h.eps, h.bias2_sqrt_rcp[5]);
     return cudaGetLastError();
 }
 

@@ -93,6 +93,8 @@ SIGNATURES = {
     'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),
     'fgs_peer_adam_slice': (C.c_int, [_U64Arr6, C.c_int32, C.c_int32, _U64Arr6, _U64Arr6, _U64Arr6]),
     'fgs_peer_last_error': (C.c_char_p, []),
+    'fgs_debug_set_overlap_adam': (None, [C.c_int32]),
+    'fgs_debug_get_overlap_adam': (C.c_int32, []),
     'fgs_debug_set_capacity_hint': (None, [C.c_int32]),
     'fgs_debug_get_capacity_hint': (C.c_int32, []),
     'fgs_profile_enable': (None, [C.c_int32]),

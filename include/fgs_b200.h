@@ -259,6 +259,12 @@ int fgs_profile_read(char* out, size_t out_bytes);
 void fgs_debug_set_capacity_hint(int32_t capacity);
 int32_t fgs_debug_get_capacity_hint(void);
 
+/* EXPERIMENTAL schedule of fgs_backward_adam (default off; also FGS_OVERLAP_ADAM=1 in the environment): the
+ * zero-gradient Adam update of the sh_rest rows of Gaussians that were not visible runs on a private side stream
+ * concurrently with the blend backward.  Results are bit-identical to the default schedule. */
+void fgs_debug_set_overlap_adam(int32_t on);
+int32_t fgs_debug_get_overlap_adam(void);
+
 /* Building blocks exported for the unit tests (each is one stage of fgs_forward). */
 int fgs_sort_pairs_u32(uint32_t* keys, uint32_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
                        const uint32_t* n_dev, int32_t n_max, int32_t end_bit, void* scratch,

@@ -22,3 +22,6 @@ timeout 600 python profiles/bench_widen.py > $O/r2_widen_bench.json 2> $O/r2_wid
 # per-launch list of the widened kernels (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'ssim|l1_kernel|gather_rows|plan_|adc_|morton|bbox' \
   -c 60 --csv --log-file $O/r2_widen_launches.csv python profiles/bench_widen.py > /dev/null 2>&1
+timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --overlap-adam > $O/r2_bench_overlap.json 2> $O/r2_bench_overlap.err
+timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --overlap-adam --fused-loss > $O/r2_bench_overlap_fusedloss.json 2> $O/r2_bench_overlap_fusedloss.err
+timeout 600 python -m pytest tests/test_widen_overlap_gpu.py -m gpu -q -s > $O/r2_overlap_test.txt 2>&1

@@ -188,3 +188,57 @@ def test_emulated_pruning_scores_match_reference_golden(emu):
     E.pruning_scores(lib, list(sc), st, scores)
     ref = torch.from_numpy(z['scores']).double()
     assert util.rel_err(torch.from_numpy(scores), ref) <= 5e-3
+
+
+@pytest.mark.parametrize('n,rest_bases', [(333, 15), (97, 3)] + ([(200, 8)] if os.environ.get('FGS_TEST_SLOW') == '1' else []))
+def test_emulated_overlapped_adam_schedule_matches_default(emu, n, rest_bases):
+    """fgs_debug_set_overlap_adam(1): the zero-gradient Adam of the sh_rest rows of invisible Gaussians moves to a side
+    stream kernel, the preprocess backward skips those rows.  Two fused steps under both schedules: rows of invisible
+    Gaussians bit-identical, the rest equal up to the float-atomic order of the 2D gradients; no float4 shared by a
+    visible and an invisible row may be lost or applied twice."""
+    from fgs_b200 import synthetic as syn
+    E, lib = emu
+    w, h = 48, 36
+    sc, cam = syn.make_scene(n, 6), syn.make_camera(6, w, h)
+    params = list(sc)
+    params[5] = params[5][:, :rest_bases].contiguous()
+    params[0] = params[0].clone()
+    params[0][::3] += 40.0  # a third of the Gaussians far outside the frustum: invisible rows interleaved with visible ones
+    st = util.settings_for(cam, active_sh_bases={15: 16, 8: 9, 3: 4}[rest_bases], bg=(0.1, 0.1, 0.1))
+    gi = syn.make_grad_image(w, h, 6)
+
+    def two_steps(overlap):
+        lib.fgs_debug_set_overlap_adam(int(overlap))
+        assert lib.fgs_debug_get_overlap_adam() == int(overlap)
+        cur = [p.clone() for p in params]
+        mom_m = mom_v = None
+        vis = None
+        for step in (1, 2):
+            img, state, scr, inp = E.forward(lib, cur, st)
+            if mom_m is None:  # non-zero moments: the zero-gradient update of an invisible row must be observable
+                rng = np.random.default_rng(11)
+                mom_m = [E._copy_aligned((rng.standard_normal(a.shape) * 1e-3).astype(np.float32)) for a in inp['p']]
+                mom_v = [E._copy_aligned((rng.random(a.shape) * 1e-6 + 1e-9).astype(np.float32)) for a in inp['p']]
+            E.backward_adam(lib, img, gi, state, scr, inp, mom_m, mom_v, [step + 4] * 6, LRS)
+            cur = [torch.from_numpy(np.array(a)) for a in inp['p']]
+            vis = state.n_visible
+        lib.fgs_debug_set_overlap_adam(0)
+        return cur, [np.array(a) for a in mom_m], [np.array(a) for a in mom_v], vis
+
+    pa, ma, va, vis_a = two_steps(False)
+    pb, mb, vb, vis_b = two_steps(True)
+    assert vis_a == vis_b and 0 < vis_a < n
+    # Gaussians that were never visible (every third one): identical bits in every tensor
+    never = torch.zeros(n, dtype=torch.bool)
+    never[::3] = True
+    for t, k in enumerate(NAMES):
+        assert torch.equal(pa[t][never], pb[t][never]), k
+        assert np.array_equal(ma[t][never.numpy()], mb[t][never.numpy()]) and np.array_equal(va[t][never.numpy()], vb[t][never.numpy()]), k
+        assert util.rel_err(pb[t] - params[t], pa[t] - params[t]) <= 1e-4, k
+        assert util.rel_err(torch.from_numpy(mb[t]), torch.from_numpy(ma[t])) <= 1e-5, k
+        assert util.rel_err(torch.from_numpy(vb[t]), torch.from_numpy(va[t])) <= 1e-5, k
+    # dense Adam semantics: the never-visible rows DID move (momentum applies to them too), by exactly two decayed steps
+    assert all(torch.isfinite(p).all() for p in pb)
+    moved = (pb[5][never] - params[5][never]).abs()
+    assert float(moved.min()) > 0.0, 'an sh_rest row of an invisible Gaussian was skipped by both kernels'
+    assert not np.array_equal(mb[5][never.numpy()], np.zeros_like(mb[5][never.numpy()]))
