@@ -332,8 +332,9 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // empty tiles keep the range (0, 0); tile_max_n is written for every item by the blend forward
     FGS_TRY(cudaMemsetAsync(tl.ranges, 0, sizeof(uint2) * n_tiles, stream), "memset ranges");
 
+    // rotations == NULL: covariance-input mode, `scales` holds (N,6) 3D covariances (include/fgs_b200.h)
     FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_info, pl.keys[0],
-                              pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream),
+                              pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream, rotations ? nullptr : scales),
             "preprocess");
     Readback& rb = readback();
     FGS_TRY(cudaEventRecord(rb.counted, stream), "event record");
@@ -440,6 +441,7 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
     }
     pa.means = means;
     pa.scales = scales;
+    pa.cov3d = rotations == nullptr;  // covariance-input mode: scales holds (N,6), g_scales receives (N,6)
     pa.rotations = rotations;
     pa.opacities = opacities;
     pa.sh_rest = sh_rest;

@@ -37,7 +37,8 @@ cudaError_t launch_preprocess(const float* means, const float* scales, const flo
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
                               uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices,
                               uint32_t* counters, uint32_t* depth_hist,
-                              int n, const Cam& cam, bool inference, cudaStream_t stream);
+                              int n, const Cam& cam, bool inference, cudaStream_t stream,
+                              const float* cov3d = nullptr /* (N,6): 3D covariances given directly, scales/rotations unused */);
 
 // LSD radix sort of (key, value) pairs, onesweep style (one read + one write of the data per pass).
 // `n_dev` points at the element count on the device, `n_max` bounds it on the host (grid sizing).
@@ -131,6 +132,10 @@ struct PreBwdArgs {
     float* g_opacities;
     float* g_sh0;
     float* g_sh_rest;
+    // covariance-input mode (unfused only): `scales` holds the (N,6) covariances, g_scales receives their (N,6) gradient
+    // (xx, xy, xz, yy, yz, zz; an off-diagonal entry counts once, i.e. twice the per-entry matrix gradient),
+    // rotations / g_rotations are unused
+    bool cov3d;
     // fused backward + Adam: parameters and moments updated in place, no gradient tensors
     float* p[6];
     float* m[6];

@@ -75,7 +75,10 @@ __device__ __forceinline__ float3 eval_sh(const float3 sh0, const float* __restr
     return r;
 }
 
-template <bool kInference>
+// kCov3d: `scales` points at (N,6) rows (xx, xy, xz, yy, yz, zz) of the 3D covariance and `rotations` is not read -- the
+// input mode of Gaussians whose covariance does not come from (scale, rotation), e.g. 4D Gaussians sliced at a time t
+// (csrc/slice4d.cu).  Everything downstream of the covariance is identical.
+template <bool kInference, bool kCov3d>
 __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ sh0, const float* __restrict__ sh_rest,
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     uint32_t* __restrict__ vis_indices, uint32_t* __restrict__ counters, uint32_t* __restrict__ depth_hist, const int n,
     const Cam cam) {
     __shared__ __align__(16) float s_means[kPreBlock * 3];
-    __shared__ __align__(16) float s_scales[kPreBlock * 3];
+    __shared__ __align__(16) float s_scales[kPreBlock * (kCov3d ? 6 : 3)];
     __shared__ __align__(16) float s_sh0[kPreBlock * 3];
     FGS_DYNAMIC_SMEM(float, s_rest, 16);  // 4 warps x 32 x 45 floats (only used when total_sh_rest == 15)
     __shared__ __align__(16) float s_w2c[12];
@@ -110,9 +113,12 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     // overlaps the staged loads (measured: two exposed DRAM round trips after the barrier otherwise)
     const int idx = first + tid;
     const float raw_opacity = __ldg(opacities + (idx < n ? idx : first));
-    const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + (idx < n ? idx : first));
+    const float4 q = kCov3d ? make_float4(1.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(rotations) + (idx < n ? idx : first));
     stage_rows<3>(s_means, means + (size_t)first * 3, rows * 3, tid, kPreBlock);
-    stage_rows<3>(s_scales, scales + (size_t)first * 3, rows * 3, tid, kPreBlock);
+    if (kCov3d)
+        stage_rows<6>(s_scales, scales + (size_t)first * 6, rows * 6, tid, kPreBlock);
+    else
+        stage_rows<3>(s_scales, scales + (size_t)first * 3, rows * 3, tid, kPreBlock);
     stage_rows<3>(s_sh0, sh0 + (size_t)first * 3, rows * 3, tid, kPreBlock);
     __syncthreads();
     if (cam_bulk) mbar_wait(&s_bar, 0u);
@@ -133,8 +139,9 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     if (opacity < kMinAlpha) active = false;
 
     // P3: covariance from exp(2 s) and the unnormalised quaternion (r, x, y, z)
-    const float3 var = make_float3(__expf(2.0f * s_scales[3 * r]), __expf(2.0f * s_scales[3 * r + 1]),
-                                   __expf(2.0f * s_scales[3 * r + 2]));
+    const float3 var = kCov3d ? make_float3(1.f, 1.f, 1.f)
+                              : make_float3(__expf(2.0f * s_scales[3 * r]), __expf(2.0f * s_scales[3 * r + 1]),
+                                            __expf(2.0f * s_scales[3 * r + 2]));
     const float qxx = q.y * q.y, qyy = q.z * q.z, qzz = q.w * q.w;
     const float qxy = q.y * q.z, qxz = q.y * q.w, qyz = q.z * q.w;
     const float qrx = q.x * q.y, qry = q.x * q.z, qrz = q.x * q.w;
@@ -147,12 +154,16 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float S11 = R11 * var.x, S12 = R12 * var.y, S13 = R13 * var.z;
     const float S21 = R21 * var.x, S22 = R22 * var.y, S23 = R23 * var.z;
     const float S31 = R31 * var.x, S32 = R32 * var.y, S33 = R33 * var.z;
-    const float c11 = S11 * R11 + S12 * R12 + S13 * R13;
-    const float c12 = S11 * R21 + S12 * R22 + S13 * R23;
-    const float c13 = S11 * R31 + S12 * R32 + S13 * R33;
-    const float c22 = S21 * R21 + S22 * R22 + S23 * R23;
-    const float c23 = S21 * R31 + S22 * R32 + S23 * R33;
-    const float c33 = S31 * R31 + S32 * R32 + S33 * R33;
+    float c11 = S11 * R11 + S12 * R12 + S13 * R13;
+    float c12 = S11 * R21 + S12 * R22 + S13 * R23;
+    float c13 = S11 * R31 + S12 * R32 + S13 * R33;
+    float c22 = S21 * R21 + S22 * R22 + S23 * R23;
+    float c23 = S21 * R31 + S22 * R32 + S23 * R33;
+    float c33 = S31 * R31 + S32 * R32 + S33 * R33;
+    if (kCov3d) {
+        c11 = s_scales[6 * r], c12 = s_scales[6 * r + 1], c13 = s_scales[6 * r + 2];
+        c22 = s_scales[6 * r + 3], c23 = s_scales[6 * r + 4], c33 = s_scales[6 * r + 5];
+    }
 
     // P4: normalised image coordinates, clipped copy for the Jacobian only
     const float x = (W[0] * mean.x + W[1] * mean.y + W[2] * mean.z + W[3]) / depth;
@@ -322,18 +333,25 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
                               uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
-                              uint32_t* depth_hist, int n, const Cam& cam, bool inference, cudaStream_t stream) {
+                              uint32_t* depth_hist, int n, const Cam& cam, bool inference, cudaStream_t stream,
+                              const float* cov3d) {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + kPreBlock - 1) / kPreBlock;
     const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
-    if (inference)
-        FGS_LAUNCH_SMEM(preprocess_kernel<true>, grid, kPreBlock, smem, stream, means, scales, rotations, opacities, sh0, sh_rest,
-                                                                     recs, n_touched, tile_info, depth_keys, vis_indices,
-                                                                     counters, depth_hist, n, cam);
-    else
-        FGS_LAUNCH_SMEM(preprocess_kernel<false>, grid, kPreBlock, smem, stream, means, scales, rotations, opacities, sh0, sh_rest,
-                                                                      recs, n_touched, tile_info, depth_keys, vis_indices,
-                                                                      counters, depth_hist, n, cam);
+#define FGS_PRE_LAUNCH(INF, COV, SCALES)                                                                               \
+    do {                                                                                                               \
+        auto kernel = preprocess_kernel<INF, COV>;                                                                     \
+        FGS_LAUNCH_SMEM(kernel, grid, kPreBlock, smem, stream, means, SCALES, rotations, opacities, sh0, sh_rest, recs, \
+                        n_touched, tile_info, depth_keys, vis_indices, counters, depth_hist, n, cam);                  \
+    } while (0)
+    if (cov3d) {
+        if (inference) FGS_PRE_LAUNCH(true, true, cov3d);
+        else FGS_PRE_LAUNCH(false, true, cov3d);
+    } else {
+        if (inference) FGS_PRE_LAUNCH(true, false, scales);
+        else FGS_PRE_LAUNCH(false, false, scales);
+    }
+#undef FGS_PRE_LAUNCH
     return cudaGetLastError();
 }
 

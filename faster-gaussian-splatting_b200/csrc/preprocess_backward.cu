@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(128, 16) adam_rest_invisible_kernel(const uint
 
 // kSkipInvisibleRest: the sh_rest rows of invisible Gaussians have already been updated by adam_rest_invisible_kernel
 // (fused mode only); everything else is identical.
-template <bool kSkipInvisibleRest>
+// kCov3d: covariance-input mode (see preprocess.cu): a.scales holds (N,6) covariances, a.g_scales receives their (N,6)
+// gradient, rotations are not touched (unfused only).
+template <bool kSkipInvisibleRest, bool kCov3d>
 __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBwdArgs a, const Cam cam) {
     FGS_DYNAMIC_SMEM(float, s_stage, 16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,10 +310,11 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         const float inv_z = 1.0f / depth;
         const float x = (W[0] * mean.x + W[1] * mean.y + W[2] * mean.z + W[3]) * inv_z;
         const float y = (W[4] * mean.x + W[5] * mean.y + W[6] * mean.z + W[7]) * inv_z;
-        const float3 var = make_float3(__expf(2.0f * __ldg(a.scales + 3 * (size_t)idx)),
-                                       __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 1)),
-                                       __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 2)));
-        const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+        const float3 var = kCov3d ? make_float3(1.f, 1.f, 1.f)
+                                  : make_float3(__expf(2.0f * __ldg(a.scales + 3 * (size_t)idx)),
+                                                __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 1)),
+                                                __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 2)));
+        const float4 q = kCov3d ? make_float4(1.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
         const float qxx = q.y * q.y, qyy = q.z * q.z, qzz = q.w * q.w;
         const float qxy = q.y * q.z, qxz = q.y * q.w, qyz = q.z * q.w;
         const float qrx = q.x * q.y, qry = q.x * q.z, qrz = q.x * q.w;
@@ -327,12 +330,16 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         const float V11 = R11 * var.x, V12 = R12 * var.y, V13 = R13 * var.z;
         const float V21 = R21 * var.x, V22 = R22 * var.y, V23 = R23 * var.z;
         const float V31 = R31 * var.x, V32 = R32 * var.y, V33 = R33 * var.z;
-        const float c11 = V11 * R11 + V12 * R12 + V13 * R13;
-        const float c12 = V11 * R21 + V12 * R22 + V13 * R23;
-        const float c13 = V11 * R31 + V12 * R32 + V13 * R33;
-        const float c22 = V21 * R21 + V22 * R22 + V23 * R23;
-        const float c23 = V21 * R31 + V22 * R32 + V23 * R33;
-        const float c33 = V31 * R31 + V32 * R32 + V33 * R33;
+        float c11 = V11 * R11 + V12 * R12 + V13 * R13;
+        float c12 = V11 * R21 + V12 * R22 + V13 * R23;
+        float c13 = V11 * R31 + V12 * R32 + V13 * R33;
+        float c22 = V21 * R21 + V22 * R22 + V23 * R23;
+        float c23 = V21 * R31 + V22 * R32 + V23 * R33;
+        float c33 = V31 * R31 + V32 * R32 + V33 * R33;
+        if (kCov3d) {
+            const float* cv = a.scales + 6 * (size_t)idx;
+            c11 = __ldg(cv), c12 = __ldg(cv + 1), c13 = __ldg(cv + 2), c22 = __ldg(cv + 3), c23 = __ldg(cv + 4), c33 = __ldg(cv + 5);
+        }
 
         const float clip_l = (-0.15f * cam.width - cam.center_x) / cam.focal_x;
         const float clip_r = (1.15f * cam.width - cam.center_x) / cam.focal_x;
@@ -440,6 +447,10 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         gq[1] = s2 * (ex - st_ * q.y);
         gq[2] = s2 * (ey - st_ * q.z);
         gq[3] = s2 * (ez - st_ * q.w);
+        if (kCov3d) {  // gradient of the six covariance entries: an off-diagonal entry stands for two matrix entries
+            gs[0] = S11, gs[1] = 2.0f * S12, gs[2] = 2.0f * S13;
+            gq[0] = S22, gq[1] = 2.0f * S23, gq[2] = S33;
+        }
     } else if (in_range) {
         for (int k = 0; k < rest_floats; ++k) my_rest[k] = 0.f;
     }
@@ -449,13 +460,22 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         st[kOffMeans + 3 * lane] = gm[0];
         st[kOffMeans + 3 * lane + 1] = gm[1];
         st[kOffMeans + 3 * lane + 2] = gm[2];
-        st[kOffScales + 3 * lane] = gs[0];
-        st[kOffScales + 3 * lane + 1] = gs[1];
-        st[kOffScales + 3 * lane + 2] = gs[2];
-        st[kOffRot + 4 * lane] = gq[0];
-        st[kOffRot + 4 * lane + 1] = gq[1];
-        st[kOffRot + 4 * lane + 2] = gq[2];
-        st[kOffRot + 4 * lane + 3] = gq[3];
+        if (kCov3d) {  // 32 x 6 floats from kOffScales on (the scales and rotations areas are adjacent)
+            st[kOffScales + 6 * lane] = gs[0];
+            st[kOffScales + 6 * lane + 1] = gs[1];
+            st[kOffScales + 6 * lane + 2] = gs[2];
+            st[kOffScales + 6 * lane + 3] = gq[0];
+            st[kOffScales + 6 * lane + 4] = gq[1];
+            st[kOffScales + 6 * lane + 5] = gq[2];
+        } else {
+            st[kOffScales + 3 * lane] = gs[0];
+            st[kOffScales + 3 * lane + 1] = gs[1];
+            st[kOffScales + 3 * lane + 2] = gs[2];
+            st[kOffRot + 4 * lane] = gq[0];
+            st[kOffRot + 4 * lane + 1] = gq[1];
+            st[kOffRot + 4 * lane + 2] = gq[2];
+            st[kOffRot + 4 * lane + 3] = gq[3];
+        }
         st[kOffOpac + lane] = gop;
         st[kOffSh0 + 3 * lane] = gsh0[0];
         st[kOffSh0 + 3 * lane + 1] = gsh0[1];
@@ -467,10 +487,14 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
     // tensor order: 0 means, 1 scales, 2 rotations, 3 opacities, 4 sh0, 5 sh_rest
     emit_span(st + kOffMeans, a.g_means, a.p[0], a.m[0], a.v[0], w0 * 3, rows * 3, a.fused, h.step_size[0], h.beta1,
               h.beta2, h.eps, h.bias2_sqrt_rcp[0], lane);
-    emit_span(st + kOffScales, a.g_scales, a.p[1], a.m[1], a.v[1], w0 * 3, rows * 3, a.fused, h.step_size[1], h.beta1,
-              h.beta2, h.eps, h.bias2_sqrt_rcp[1], lane);
-    emit_span(st + kOffRot, a.g_rotations, a.p[2], a.m[2], a.v[2], w0 * 4, rows * 4, a.fused, h.step_size[2], h.beta1,
-              h.beta2, h.eps, h.bias2_sqrt_rcp[2], lane);
+    if (kCov3d) {
+        emit_span(st + kOffScales, a.g_scales, nullptr, nullptr, nullptr, w0 * 6, rows * 6, false, 0.f, 0.f, 0.f, 0.f, 0.f, lane);
+    } else {
+        emit_span(st + kOffScales, a.g_scales, a.p[1], a.m[1], a.v[1], w0 * 3, rows * 3, a.fused, h.step_size[1], h.beta1,
+                  h.beta2, h.eps, h.bias2_sqrt_rcp[1], lane);
+        emit_span(st + kOffRot, a.g_rotations, a.p[2], a.m[2], a.v[2], w0 * 4, rows * 4, a.fused, h.step_size[2], h.beta1,
+                  h.beta2, h.eps, h.bias2_sqrt_rcp[2], lane);
+    }
     emit_span(st + kOffOpac, a.g_opacities, a.p[3], a.m[3], a.v[3], w0, rows, a.fused, h.step_size[3], h.beta1, h.beta2,
               h.eps, h.bias2_sqrt_rcp[3], lane);
     emit_span(st + kOffSh0, a.g_sh0, a.p[4], a.m[4], a.v[4], w0 * 3, rows * 3, a.fused, h.step_size[4], h.beta1, h.beta2,
@@ -524,16 +548,21 @@ cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cuda
     static bool s_attr = false;
     const size_t smem = (size_t)kWarps * kWarpFloats * sizeof(float);
     if (!s_attr) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto k00 = preprocess_backward_kernel<false, false>;
+        auto k10 = preprocess_backward_kernel<true, false>;
+        auto k01 = preprocess_backward_kernel<false, true>;
+        cudaError_t e = cudaFuncSetAttribute(k00, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(preprocess_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k10, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k01, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         s_attr = true;
     }
-    if (skip_invisible_rest && a.fused)
-        FGS_LAUNCH_SMEM(preprocess_backward_kernel<true>, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
-    else
-        FGS_LAUNCH_SMEM(preprocess_backward_kernel<false>, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
+    if (a.cov3d && a.fused) return cudaErrorInvalidValue;  // the covariance-input mode has no fused Adam
+    auto kernel = a.cov3d ? preprocess_backward_kernel<false, true>
+                          : (skip_invisible_rest && a.fused) ? preprocess_backward_kernel<true, false> : preprocess_backward_kernel<false, false>;
+    FGS_LAUNCH_SMEM(kernel, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,12 @@ typedef struct fgs_forward_state {
 int fgs_abi_version(void);
 const char* fgs_last_error(void);
 
+/* Covariance-input mode (no reference counterpart on `main`; what the FasterGS4D branch, README.md:39, needs from the
+ * rasterizer): fgs_forward / fgs_inference / fgs_backward called with rotations == NULL read `scales` as (N,6) rows
+ * (xx, xy, xz, yy, yz, zz) of the 3D covariance, and fgs_backward (grad_rotations == NULL) writes the (N,6) gradient of
+ * those six entries to grad_scales (an off-diagonal entry counts once).  Everything else is unchanged.  Not available
+ * for fgs_backward_adam. */
+
 /* forward.h:10-36 -- differentiable forward.  Writes image (3,H,W). */
 int fgs_forward(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance,
                 const float* means, const float* scales, const float* rotations, const float* opacities,

@@ -172,8 +172,15 @@ class Projected(NamedTuple):
     n_touched_tiles: torch.Tensor  # (N,) int
 
 
-def preprocess(means, scales, rotations, opacities, sh0, sh_rest, s: Settings) -> Projected:
-    """kernels_forward.cuh:14-209 (P1-P12 in SURVEY.md §8.1)."""
+def cov3d_from_six(c6):
+    """(N,6) = (xx, xy, xz, yy, yz, zz) -> (N,3,3) symmetric."""
+    xx, xy, xz, yy, yz, zz = c6.unbind(1)
+    return torch.stack([xx, xy, xz, xy, yy, yz, xz, yz, zz], dim=1).reshape(-1, 3, 3)
+
+
+def preprocess(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, cov3d=None) -> Projected:
+    """kernels_forward.cuh:14-209 (P1-P12 in SURVEY.md §8.1).  `cov3d` (N,6): the 3D covariance is given directly
+    (scales / rotations are ignored) -- the input mode of the time-sliced 4D Gaussians (oracle/fourd_oracle.py)."""
     dt = means.dtype
     W = s.w2c[:3, :3].to(dt)
     t = s.w2c[:3, 3].to(dt)
@@ -184,10 +191,13 @@ def preprocess(means, scales, rotations, opacities, sh0, sh_rest, s: Settings) -
     opacity = torch.sigmoid(opacities[:, 0])
     active = active & (opacity >= MIN_ALPHA)
 
-    variance = torch.exp(2.0 * scales)
-    R, norm_sq = quaternion_to_rotation(rotations)
-    active = active & (norm_sq >= 1e-8)
-    cov3d = R @ torch.diag_embed(variance) @ R.transpose(1, 2)
+    if cov3d is None:
+        variance = torch.exp(2.0 * scales)
+        R, norm_sq = quaternion_to_rotation(rotations)
+        active = active & (norm_sq >= 1e-8)
+        cov3d = R @ torch.diag_embed(variance) @ R.transpose(1, 2)
+    else:
+        cov3d = cov3d_from_six(cov3d)
 
     safe_depth = torch.where(active, depth, torch.ones_like(depth))
     x = cam[:, 0] / safe_depth
@@ -318,14 +328,14 @@ class RenderOut(NamedTuple):
 
 
 def render(means, scales, rotations, opacities, sh0, sh_rest, s: Settings, pixel_chunk: int = 16384,
-           window=None) -> RenderOut:
+           window=None, cov3d=None) -> RenderOut:
     """Forward of diff_rasterize: preprocess + depth order + dense front-to-back blend
     (kernels_forward.cuh:362-498, B1-B8 in SURVEY.md §8.1).  Differentiable.
 
     `window=(x0, y0, x1, y1)` renders only that pixel rectangle (exactly: Gaussians whose
     opacity-aware bounding box misses the window have alpha < 1/255 on all of its pixels); the
     returned image is (3, y1-y0, x1-x0).  Used to time a bounded sample of a large workload."""
-    proj = preprocess(means, scales, rotations, opacities, sh0, sh_rest, s)
+    proj = preprocess(means, scales, rotations, opacities, sh0, sh_rest, s, cov3d=cov3d)
     vis_mask = proj.visible
     if window is not None:
         wx0, wy0, wx1, wy1 = window

@@ -90,7 +90,7 @@ inline int2 make_int2(int x, int y) { return {x, y}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
-constexpr cudaError_t cudaSuccess = 0;
+constexpr cudaError_t cudaSuccess = 0, cudaErrorInvalidValue = 1;
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {

@@ -60,7 +60,7 @@ def settings_struct(st, total_rest):
 def forward(lib, params, st, training=True, to_chw=True, clamp=False):
     """params: six tensors (means, scales, rotations, opacities, sh0, sh_rest); st: RasterizerSettings tuple.
     Returns (image, state, scratch, inputs) -- keep `scratch` and `inputs` alive for the backward."""
-    p = [_copy_aligned(_f32(t)) for t in params]
+    p = [None if t is None else _copy_aligned(_f32(t)) for t in params]  # rotations None: covariance-input mode
     n = p[0].shape[0]
     total_rest = p[5].shape[1] if p[5].ndim > 1 else 0
     w2c, pos, bg = (_copy_aligned(_f32(t)) for t in st[:3])
@@ -69,7 +69,7 @@ def forward(lib, params, st, training=True, to_chw=True, clamp=False):
     s = settings_struct(st, total_rest)
     sc = Scratch()
     state = _capi.ForwardState()
-    ptr = lambda a: a.ctypes.data
+    ptr = lambda a: None if a is None else a.ctypes.data
     if training:
         rc = lib.fgs_forward(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), n, C.byref(s), None,
                              C.byref(state))
@@ -83,16 +83,16 @@ def forward(lib, params, st, training=True, to_chw=True, clamp=False):
 def backward(lib, image, grad_image, state, sc, inp, densification_info=None):
     p, n = inp['p'], inp['n']
     gi = _copy_aligned(_f32(grad_image))
-    grads = [_copy_aligned(np.full(a.shape, np.nan, dtype=np.float32)) for a in p]
+    grads = [None if a is None else _copy_aligned(np.full(a.shape, np.nan, dtype=np.float32)) for a in p]
     scratch2d = _aligned(lib.fgs_grad2d_scratch_bytes(n))
     scratch2d[:] = 0xCD
-    ptr = lambda a: a.ctypes.data
+    ptr = lambda a: None if a is None else a.ctypes.data
     dens = ptr(densification_info) if densification_info is not None else None
     rc = lib.fgs_backward(ptr(gi), ptr(image), ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[5]), ptr(inp['w2c']),
                           ptr(inp['pos']), ptr(inp['bg']), ptr(sc.buf[1]), ptr(sc.buf[2]), ptr(sc.buf[3]),
                           *[ptr(g) for g in grads], ptr(scratch2d), dens, n, C.byref(inp['s']), C.byref(state), None)
     assert rc == 0, lib.fgs_last_error()
-    return [torch.from_numpy(np.array(g)) for g in grads]
+    return [None if g is None else torch.from_numpy(np.array(g)) for g in grads]
 
 
 def backward_adam(lib, image, grad_image, state, sc, inp, moments_m, moments_v, steps, lrs, betas=(0.9, 0.999), eps=1e-15,
