@@ -22,7 +22,7 @@ LIB = OUT_DIR / 'libfgs_b200.so'
 OBJ_DIR = HERE / 'build' / 'obj'
 
 SOURCES = ['preprocess.cu', 'sort.cu', 'binning.cu', 'blend_forward.cu', 'blend_backward.cu',
-           'preprocess_backward.cu', 'aux_ops.cu', 'peer_adam.cu', 'loss.cu', 'densify.cu', 'c_abi.cu']
+           'preprocess_backward.cu', 'aux_ops.cu', 'peer_adam.cu', 'loss.cu', 'densify.cu', 'slice4d.cu', 'c_abi.cu']
 HEADERS = ['fgs_device.cuh', 'fgs_host.h', 'fgs_launch.h', '../../include/fgs_b200.h']
 
 NVCC_FLAGS = [

@@ -34,12 +34,14 @@ def _resize(user, nbytes):
 _resize_cb = _capi.ResizeFn(_resize)
 
 
-def _ptr(t: torch.Tensor) -> int:
-    return t.data_ptr()
+def _ptr(t):
+    return None if t is None else t.data_ptr()
 
 
-def _check_param(t: torch.Tensor, name: str) -> None:
+def _check_param(t, name: str) -> None:
     # the reference only checks this in debug builds (rasterization_api.cu:35-41); here it is always on
+    if t is None and name == 'rotations':  # covariance-input mode: `scales` holds (N,6) covariances (include/fgs_b200.h)
+        return
     if not (_capi.on_device(t) and t.dtype == torch.float32 and t.is_contiguous()):
         raise RuntimeError(f"Input tensor '{name}' must be a contiguous CUDA float tensor.")
 
@@ -135,7 +137,7 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
     with _capi.device_guard(dev):
         n = means.shape[0]
         if _grad_outputs is None:
-            grads = [torch.empty_like(p) for p in (means, scales, rotations, opacities)]
+            grads = [None if p is None else torch.empty_like(p) for p in (means, scales, rotations, opacities)]
             g_sh0 = torch.empty((n, 1, 3), dtype=torch.float32, device=dev)
             g_rest = torch.empty_like(sh_coefficients_rest)
         else:
@@ -143,6 +145,8 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
             # nobody else holds a reference to the object it was handed
             outs = [t.view(t.shape) for t in _grad_outputs]
             grads, g_sh0, g_rest = outs[:4], outs[4], outs[5]
+            if rotations is None:
+                raise RuntimeError('set_gradient_outputs is not available in covariance-input mode')
             shapes = [tuple(p.shape) for p in (means, scales, rotations, opacities)] + [(n, 1, 3), tuple(sh_coefficients_rest.shape)]
             for t, shape in zip(_grad_outputs, shapes):
                 if tuple(t.shape) != shape or t.device != dev:

@@ -19,6 +19,6 @@ def __getattr__(name):
     if name in __all__:
         tb = importlib.import_module('.torch_bindings', __name__)
         return getattr(tb, name)
-    if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel', 'loss', 'densification'):
+    if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel', 'loss', 'densification', 'fourd'):
         return importlib.import_module('.' + name, __name__)
     raise AttributeError(f'module {__name__!r} has no attribute {name!r}')

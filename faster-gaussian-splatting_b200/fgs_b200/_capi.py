@@ -88,6 +88,8 @@ SIGNATURES = {
     'fgs_adc_flags': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, _P, _P]),
     'fgs_morton_keys': (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     'fgs_gather_u32': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P]),
+    'fgs_slice4d_forward': (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int32, _P, _P, _P, _P]),
+    'fgs_slice4d_backward': (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'fgs_peer_adam_step': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _U64Arr6, _U64Arr6, _I32Arr6, _F64Arr6,
                                       C.c_double, C.c_double, C.c_double, _P]),
     'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),

@@ -230,6 +230,20 @@ int fgs_morton_keys(const float* means, int32_t n_primitives, void* scratch, int
 int fgs_gather_u32(const uint32_t* src, const uint32_t* index, uint32_t* dst, int64_t* index_as_i64, int32_t n,
                    void* stream);
 
+/* ---- time slice of 4D Gaussians (csrc/slice4d.cu; the FasterGS4D branch, README.md:39, is not in the reference tree:
+ * restated from Yang et al., ICLR 2024 -- parity unpinned, oracle/fourd_oracle.py).  means4 (N,4) = (x, y, z, t), scales4
+ * (N,4) log-scales, rot_l / rot_r (N,4) unnormalised quaternions of the left / right isoclinic rotation, opacities (N,1)
+ * logits.  Forward: the 3D Gaussians at time t as means3 (N,3), cov3 (N,6) = (xx, xy, xz, yy, yz, zz) and opacity
+ * logits (N,1) including the temporal marginal -- the inputs of fgs_forward in covariance-input mode.  Backward: the
+ * gradients of the five 4D tensors from those of the three outputs. */
+int fgs_slice4d_forward(const float* means4, const float* scales4, const float* rot_l, const float* rot_r,
+                        const float* opacities, float t, int32_t n_primitives, float* means3, float* cov3,
+                        float* opacity_logits, void* stream);
+int fgs_slice4d_backward(const float* means4, const float* scales4, const float* rot_l, const float* rot_r,
+                         const float* opacities, float t, int32_t n_primitives, const float* grad_means3,
+                         const float* grad_cov3, const float* grad_opacity_logits, float* grad_means4,
+                         float* grad_scales4, float* grad_rot_l, float* grad_rot_r, float* grad_opacities, void* stream);
+
 /* ---- view-parallel training over NVLink peer memory (no reference counterpart: the reference is single-GPU,
  * Renderer.py:58-61).  EXPERIMENTAL: compiled and host-tested, not yet run on hardware (see csrc/peer_adam.cu).
  *

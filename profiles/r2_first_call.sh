@@ -25,3 +25,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --overlap-adam > $O/r2_bench_overlap.json 2> $O/r2_bench_overlap.err
 timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --overlap-adam --fused-loss > $O/r2_bench_overlap_fusedloss.json 2> $O/r2_bench_overlap_fusedloss.err
 timeout 600 python -m pytest tests/test_widen_overlap_gpu.py -m gpu -q -s > $O/r2_overlap_test.txt 2>&1
+timeout 900 python -m pytest tests/test_widen_fourd.py -m gpu -q -s > $O/r2_fourd_test.txt 2>&1
+timeout 600 python profiles/bench_fourd.py > $O/r2_fourd_bench.json 2> $O/r2_fourd_bench.err

@@ -36,7 +36,7 @@ def build(name: str, sanitize_threads: bool = False) -> ctypes.CDLL:
     """`name`: one self-contained operator file (loss, densify, peer_adam), 'full' = the whole rasterizer, or 'all' =
     every symbol of include/fgs_b200.h in one library (what FGS_B200_LIB can point the Python layer at)."""
     from concurrent.futures import ThreadPoolExecutor
-    names = FULL if name == 'full' else FULL + ['loss', 'densify', 'peer_adam'] if name == 'all' else [name]
+    names = FULL if name == 'full' else FULL + ['loss', 'densify', 'peer_adam', 'slice4d'] if name == 'all' else [name]
     srcs = [CSRC / f'{n}.cu' for n in names] + ([] if name in ('full', 'all') else [HERE / 'emu_support.cpp'])
     tag = f'{name}_tsan' if sanitize_threads else name
     out = BUILD / f'libfgs_emu_{tag}.so'

@@ -186,10 +186,53 @@ def check_training_loop():
     print(f'training loop ok: PSNR {psnr0:.2f} -> {pd:.2f} (drop-in) / {pf:.2f} (fused) / {p1:.2f} (DSSIM + densify, N {T.N} -> {params["means"].shape[0]})')
 
 
+def make_scene_4d(n, seed, width):
+    sc = syn.make_scene(n, seed, width=width)
+    g = torch.Generator().manual_seed(seed + 77)
+    means4 = torch.cat([sc.means, torch.rand(n, 1, generator=g)], dim=1).contiguous()
+    scales4 = torch.cat([sc.scales, torch.randn(n, 1, generator=g) * 0.3 - 1.2], dim=1).contiguous()
+    rot_l = torch.randn(n, 4, generator=g)
+    rot_r = torch.randn(n, 4, generator=g) * 0.3 + torch.tensor([1.0, 0.0, 0.0, 0.0])  # near the identity: mild space-time coupling
+    return means4, scales4, rot_l.contiguous(), rot_r.contiguous(), sc.opacities, sc.sh_coefficients_0, sc.sh_coefficients_rest
+
+
+def check_fourd_api():
+    from fgs_b200 import fourd as F4
+    from oracle import fourd_oracle as FO
+    n, w, h, t = 250, 64, 48, 0.4
+    params = make_scene_4d(n, 5, w)
+    cam = syn.make_camera(5, w, h)
+    st = util.settings_for(cam, bg=(0.05, 0.1, 0.15))
+    gi = syn.make_grad_image(w, h, 5)
+    leaves = [p.clone().requires_grad_(True) for p in params]
+    dens = torch.zeros(2, n)
+    img = F4.diff_rasterize_4d(*leaves, t, dens, fgs_b200.RasterizerSettings(*st))
+    img.backward(gi)
+    o_leaves = [p.double().clone().requires_grad_(True) for p in params]
+    s = O.Settings(*st)
+    s = s._replace(w2c=s.w2c.double(), cam_position=s.cam_position.double(), bg_color=s.bg_color.double())
+    out = FO.render_4d(*o_leaves, t, s)
+    out.image.backward(gi.double())
+    vis = int(out.proj.visible.sum())
+    assert 0 < vis < n and float(dens[0].sum()) == vis
+    assert (img.detach().double() - out.image.detach()).abs().mean().item() <= 2e-6
+    names = ('means4', 'scales4', 'rot_l', 'rot_r', 'opacities', 'sh0', 'sh_rest')
+    for name, a, b in zip(names, leaves, o_leaves):
+        assert a.grad is not None and util.rel_err(a.grad, b.grad) <= 5e-4, (name, util.rel_err(a.grad, b.grad))
+    with torch.no_grad():
+        inf = F4.rasterize_4d(*params, t, fgs_b200.RasterizerSettings(*st), to_chw=True, clamp_output=False)
+    assert (inf - img.detach()).abs().max().item() <= 1e-6
+    # another time slice renders a different image (the Gaussians move and fade)
+    with torch.no_grad():
+        other = F4.rasterize_4d(*params, 0.9, fgs_b200.RasterizerSettings(*st), to_chw=True, clamp_output=False)
+    assert (other - inf).abs().mean().item() > 1e-4
+    print(f'4D API ok: {vis} of {n} Gaussians visible at t = {t}')
+
+
 if __name__ == '__main__':
     torch.cuda.synchronize = lambda *a, **k: None  # the training helper ends with a synchronize
-    which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'training']
+    which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'fourd', 'training']
     for name in which:
         {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
-         'training': check_training_loop}[name]()
+         'fourd': check_fourd_api, 'training': check_training_loop}[name]()
     print('ALL OK')

@@ -10,7 +10,7 @@ from pathlib import Path
 import pytest
 
 SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
-PARTS = ['rasterizer', 'loss', 'densification'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
+PARTS = ['rasterizer', 'loss', 'densification', 'fourd'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
 
 
 @pytest.mark.parametrize('part', PARTS)
