@@ -229,10 +229,27 @@ def check_fourd_api():
     print(f'4D API ok: {vis} of {n} Gaussians visible at t = {t}')
 
 
+def check_gpu_test_code():
+    """The bodies of the `-m gpu` tests of the widened rows, executed here with device 'cpu' (and smaller sizes where the
+    test takes them as parameters): validates the TEST code that will first meet a GPU at the end of the round."""
+    from tests import test_widen_densify as TD
+    from tests import test_widen_fourd as TF
+    from tests import test_widen_loss as TL
+    from tests import test_widen_overlap_gpu as TO
+    dev = torch.device('cpu')
+    TL.test_loss_gpu_vs_oracle(dev, 70, 45, False, 0.8, 0.2)
+    TL.test_loss_gpu_vs_oracle(dev, 16, 12, True, 1.0, 0.0)
+    TD.test_adc_gpu_vs_oracle(dev, 2500, True)
+    TD.test_prune_sort_extend_reset_morton_gpu(dev)
+    TO.test_overlapped_adam_schedule_matches_default(dev, 400, 64, 48)
+    TF.test_fourd_forward_backward_vs_oracle(dev)
+    print('GPU test code ok')
+
+
 if __name__ == '__main__':
     torch.cuda.synchronize = lambda *a, **k: None  # the training helper ends with a synchronize
     which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'fourd', 'training']
     for name in which:
         {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
-         'fourd': check_fourd_api, 'training': check_training_loop}[name]()
+         'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code}[name]()
     print('ALL OK')

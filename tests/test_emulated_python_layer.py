@@ -1,6 +1,7 @@
 """The product's Python layer (fgs_b200._C, torch_bindings, loss, densification) run UNCHANGED on host tensors against the
 emulated build of the whole library (tests/cuda_emu 'all', selected with FGS_B200_LIB), in a subprocess so that this
-process keeps the real libfgs_b200.so.  See tests/emu_python_layer.py for what is compared.  The mini training loop (the
+process keeps the real libfgs_b200.so.  See tests/emu_python_layer.py for what is compared; part "gpu_tests" executes the
+bodies of the `-m gpu` tests of the widened rows with device "cpu".  The mini training loop (the
 code of tests/test_widen_training.py at a toy size, ~3 min) only runs with FGS_TEST_SLOW=1."""
 import os
 import subprocess
@@ -10,7 +11,7 @@ from pathlib import Path
 import pytest
 
 SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
-PARTS = ['rasterizer', 'loss', 'densification', 'fourd'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
+PARTS = ['rasterizer', 'loss', 'densification', 'fourd', 'gpu_tests'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
 
 
 @pytest.mark.parametrize('part', PARTS)
