@@ -11,6 +11,7 @@ argument meaning as the NeRFICG helpers it calls (``Optim.adam_utils``: Model.py
     morton_encode(means) -> int64 codes                                    Model.py:461
     morton_order(means)  -> int64 ordering (== torch.argsort(morton_encode(means)), stable)
     adaptive_density_control(optimizer, densification_info, ...)           Model.py:312-366, fused
+    mcmc_densification(optimizer, min_opacity, cap_max)                    Model.py:368-457 (3DGS-MCMC relocation + growth)
 
 The optimizer is a ``torch.optim.Adam`` with ONE tensor per param group and a ``'name'`` per group (Model.py:238-245);
 state keys ``step`` / ``exp_avg`` / ``exp_avg_sq`` are preserved.  Each call moves every parameter tensor and both
@@ -249,3 +250,57 @@ def adaptive_density_control(optimizer, densification_info: torch.Tensor, grad_t
         raise RuntimeError(f'randn must return a tensor of shape {shape}')
     out, ex = _move_rows(optimizer, plan, kept + clones + 2 * pairs, split=(scales, rotations, z), extras=extras)
     return (out, ex) if extras else out
+
+
+def mcmc_densification(optimizer, min_opacity: float, cap_max: int, multinomial=None):
+    """Model.py:368-457 (3DGS-MCMC): dead Gaussians (opacity <= min_opacity or a degenerate quaternion) are relocated
+    onto samples of the live ones drawn with probability proportional to opacity, then the set grows by 5 % up to
+    `cap_max` the same way; sampled Gaussians share their opacity / scale with their copies (relocation_adjustment,
+    Eq. 9) and get a fresh Adam state.  The sampling and the index assignments are torch ops as in the reference; the
+    adjustment, the state reset and the growth run through the C ABI (fgs_relocation_adjustment, fgs_zero_rows,
+    fgs_gather_rows).  `multinomial(weights, n)` defaults to torch.multinomial(weights, n, replacement=True).
+    Returns {name: Parameter}."""
+    from . import _C
+    if multinomial is None:
+        multinomial = lambda weights, n: torch.multinomial(weights, n, replacement=True)
+    logit_min = math.log(min_opacity / (1 - min_opacity))
+    eps = torch.finfo(torch.float32).eps
+
+    def adjusted(groups, sampled):  # Model.py:384-391
+        opacities = torch.sigmoid(groups['opacities'].data).flatten()
+        _, inverse, counts_per_unique = sampled.unique(sorted=False, return_inverse=True, return_counts=True)
+        counts = counts_per_unique[inverse] + 1  # +1 for the original Gaussian
+        new_o, new_s = _C.relocation_adjustment(opacities[sampled], groups['scales'].data[sampled].exp(), counts)
+        return new_o.clamp(min_opacity, 1.0 - eps).logit(), new_s.log()
+
+    groups = {name: param for name, _, param in _groups(optimizer)}
+    with torch.no_grad():
+        dead_mask = groups['opacities'].data.flatten() <= logit_min
+        dead_mask |= groups['rotations'].data.mul(groups['rotations'].data).sum(dim=1) < 1e-8
+        n_dead = int(dead_mask.sum().item())
+        if n_dead > 0:
+            dead_indices = torch.where(dead_mask)[0]
+            alive_indices = torch.where(~dead_mask)[0]
+            opacities = torch.sigmoid(groups['opacities'].data).flatten()
+            sampled = alive_indices[multinomial(opacities[alive_indices], n_dead)]
+            adj_o, adj_s = adjusted(groups, sampled)
+            groups['opacities'].data[sampled] = adj_o
+            groups['scales'].data[sampled] = adj_s
+            for name in ('means', 'sh_coefficients_0', 'sh_coefficients_rest', 'rotations'):
+                groups[name].data[dead_indices] = groups[name].data[sampled]
+            groups['opacities'].data[dead_indices] = adj_o
+            groups['scales'].data[dead_indices] = adj_s
+            reset_state(optimizer, sampled)
+        n = groups['means'].shape[0]
+        n_added = max(0, min(int(cap_max), int(1.05 * n)) - n)
+        if n_added > 0:
+            opacities = torch.sigmoid(groups['opacities'].data).flatten()
+            sampled = multinomial(opacities, n_added)
+            adj_o, adj_s = adjusted(groups, sampled)
+            groups['opacities'].data[sampled] = adj_o
+            groups['scales'].data[sampled] = adj_s
+            new = {name: groups[name].data[sampled] for name in ('means', 'sh_coefficients_0', 'sh_coefficients_rest', 'rotations')}
+            new['opacities'], new['scales'] = adj_o, adj_s
+            groups = extend_param_groups(optimizer, new)
+            reset_state(optimizer, sampled)
+    return groups

@@ -116,3 +116,48 @@ def morton_encode(means: torch.Tensor) -> torch.Tensor:
         for c in range(3):
             code |= ((q[:, c] >> bit) & 1) << (3 * bit + (2 - c))
     return code
+
+
+def mcmc_densification(state: dict, min_opacity: float, cap_max: int, multinomial):
+    """Model.py:368-457 on the dict of tensors; `multinomial(weights, n)` is the sampler (shared with the code under
+    test so that both draw the same indices).  relocation_adjustment is oracle/aux_oracle.py's restatement."""
+    from oracle import aux_oracle as A
+    st = {k: v.clone() for k, v in state.items()}
+    logit_min = math.log(min_opacity / (1 - min_opacity))
+    eps = torch.finfo(torch.float32).eps
+
+    def adjusted(sampled):
+        opacities = torch.sigmoid(st['opacities']).flatten()
+        _, inverse, counts_per_unique = sampled.unique(sorted=False, return_inverse=True, return_counts=True)
+        counts = counts_per_unique[inverse] + 1
+        new_o, new_s = A.relocation_adjustment(opacities[sampled], st['scales'][sampled].exp(), counts)
+        return new_o.reshape(-1, 1).clamp(min_opacity, 1.0 - eps).logit(), new_s.log()
+
+    dead = st['opacities'].flatten() <= logit_min
+    dead |= st['rotations'].mul(st['rotations']).sum(dim=1) < 1e-8
+    n_dead = int(dead.sum())
+    if n_dead > 0:
+        dead_idx, alive_idx = torch.where(dead)[0], torch.where(~dead)[0]
+        opacities = torch.sigmoid(st['opacities']).flatten()
+        sampled = alive_idx[multinomial(opacities[alive_idx], n_dead)]
+        adj_o, adj_s = adjusted(sampled)
+        st['opacities'][sampled] = adj_o
+        st['scales'][sampled] = adj_s
+        for name in ('means', 'sh_coefficients_0', 'sh_coefficients_rest', 'rotations'):
+            st[name][dead_idx] = st[name][sampled]
+        st['opacities'][dead_idx] = adj_o
+        st['scales'][dead_idx] = adj_s
+        st = reset_state(st, sampled)
+    n = st['means'].shape[0]
+    n_added = max(0, min(int(cap_max), int(1.05 * n)) - n)
+    if n_added > 0:
+        opacities = torch.sigmoid(st['opacities']).flatten()
+        sampled = multinomial(opacities, n_added)
+        adj_o, adj_s = adjusted(sampled)
+        st['opacities'][sampled] = adj_o
+        st['scales'][sampled] = adj_s
+        new = {name: st[name][sampled] for name in ('means', 'sh_coefficients_0', 'sh_coefficients_rest', 'rotations')}
+        new['opacities'], new['scales'] = adj_o, adj_s
+        st = extend(st, new)
+        st = reset_state(st, sampled)
+    return st

@@ -167,6 +167,24 @@ def check_densification_api():
         p.grad = torch.ones_like(p)
     opt.step()
     assert opt.state[groups['means']]['step'] == 8
+    # 3DGS-MCMC relocation + growth (Model.py:368-457) with a shared deterministic sampler
+    state2, _ = make_state(900, seed=21)
+    state2['opacities'][::7] = -9.0  # dead Gaussians
+
+    def sampler():
+        gen = torch.Generator().manual_seed(3)
+        return lambda weights, k: torch.multinomial(weights, k, replacement=True, generator=gen)
+    want2 = DO.mcmc_densification(state2, 0.005, 930, sampler())
+    opt2 = _optimizer(state2)
+    groups2 = D.mcmc_densification(opt2, 0.005, 930, multinomial=sampler())
+    got2 = _state_of(opt2, groups2)
+    assert got2['means'].shape[0] == 930 == want2['means'].shape[0]
+    for k in want2:
+        if k in ('opacities', 'scales'):  # relocation_adjustment: alternating series, compared like tests/test_aux_ops.py
+            rel = ((got2[k] - want2[k]).abs() / want2[k].abs().clamp_min(1e-12)).reshape(-1)
+            assert float(rel.median()) <= 1e-5 and float((rel <= 5e-2).float().mean()) >= 0.97, k
+        else:
+            assert torch.equal(got2[k], want2[k]), k
     print('densification API ok')
 
 
