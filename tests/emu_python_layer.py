@@ -87,6 +87,16 @@ def check_rasterizer_api():
     scores = torch.zeros(n)
     fgs_b200.update_pruning_scores(scores, *sc, rs)
     assert util.rel_err(scores, O.pruning_scores(*sc, O.Settings(*st))) <= 2e-4
+    # the three small operators (3D filter, MCMC relocation, noise) against the compiled reference's golden and the oracle
+    from tests import test_aux_ops as TA
+    from fgs_b200 import _C
+    d, filt = TA._inputs('cpu')
+    got = TA._run(fgs_b200, d, filt, _C.add_noise)
+    TA._compare(got, TA._oracle_run(TA._inputs('cpu')[0], filt), 'emulated kernels vs oracle')
+    if TA.GOLDEN.exists():
+        z = np.load(TA.GOLDEN)
+        TA._compare(got, (z['filter_3d'], z['visibility'], z['new_opacities'], z['new_scales'], z['means']),
+                    'emulated kernels vs reference golden')
     print('rasterizer API ok')
 
 
