@@ -268,7 +268,7 @@ def check_gpu_test_code():
     TL.test_loss_gpu_vs_oracle(dev, 70, 45, False, 0.8, 0.2)
     TL.test_loss_gpu_vs_oracle(dev, 16, 12, True, 1.0, 0.0)
     TD.test_adc_gpu_vs_oracle(dev, 2500, True)
-    TD.test_prune_sort_extend_reset_morton_gpu(dev)
+    TD.test_prune_sort_extend_reset_morton_gpu(dev, n=4000)
     TO.test_overlapped_adam_schedule_matches_default(dev, 400, 64, 48)
     TF.test_fourd_forward_backward_vs_oracle(dev)
     print('GPU test code ok')

@@ -232,9 +232,8 @@ def test_adc_gpu_vs_oracle(cuda_device, n, prune_large):
 
 
 @pytest.mark.gpu
-def test_prune_sort_extend_reset_morton_gpu(cuda_device):
+def test_prune_sort_extend_reset_morton_gpu(cuda_device, n=50_000):
     from fgs_b200 import densification as D
-    n = 50_000
     state, info = make_state(n, seed=3)
     g = torch.Generator().manual_seed(11)
     prune_mask = torch.rand(n, generator=g) < 0.3
