@@ -160,7 +160,7 @@ class PeerAdam:
             if p.grad.data_ptr() != g.data_ptr():  # gradient produced elsewhere (e.g. a regulariser): bring it in
                 g.copy_(p.grad)
         self.steps += 1
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = self._capi.current_stream()
         self._gh.barrier()  # stream-ordered: every rank's gradients are complete
         rc = self._lib.fgs_peer_adam_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),

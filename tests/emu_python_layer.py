@@ -257,6 +257,60 @@ def check_fourd_api():
     print(f'4D API ok: {vis} of {n} Gaussians visible at t = {t}')
 
 
+def check_peer_adam_class():
+    """fgs_b200.parallel.PeerAdam in a world of ONE rank (gloo), with torch's symmetric memory replaced by plain host
+    tensors: the Python side of the class -- flat layout, parameter / gradient views, the rasterizer's backward writing
+    its gradients straight into the symmetric gradient buffer (set_gradient_outputs), step / zero_grad / reset / close --
+    against diff_rasterize + FusedAdam.step.  (The multi-rank slicing of the kernel is covered by
+    tests/test_peer_adam.py::test_peer_adam_kernel_emulated_ranks.)"""
+    import types
+    import torch.distributed as dist
+    from fgs_b200 import parallel
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('gloo', rank=0, world_size=1)
+    fake = types.ModuleType('torch.distributed._symmetric_memory')
+    fake.empty = lambda n, dtype, device: torch.empty(n, dtype=dtype, device=device)
+
+    class Handle:
+        def __init__(self, t):
+            self.buffer_ptrs = [t.data_ptr()]
+
+        def barrier(self):
+            pass
+    fake.rendezvous = lambda t, group_name: Handle(t)
+    sys.modules['torch.distributed._symmetric_memory'] = fake
+    dist._symmetric_memory = fake
+    n, w, h = 200, 48, 36
+    sc, cam = syn.make_scene(n, 9), syn.make_camera(9, w, h)
+    rs = fgs_b200.RasterizerSettings(*util.settings_for(cam))
+    gis = [syn.make_grad_image(w, h, k) for k in range(2)]
+    lrs = [LRS[k] for k in NAMES]
+    pa = [p.clone().requires_grad_(True) for p in sc]
+    oa = fgs_b200.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15)
+    for it in range(2):
+        fgs_b200.diff_rasterize(*pa, torch.empty(0), rs).backward(gis[it])
+        oa.step()
+        oa.zero_grad()
+    ob = parallel.PeerAdam([p.clone() for p in sc], lrs)
+    for it in range(2):
+        fgs_b200.diff_rasterize(*ob.params, torch.empty(0), rs).backward(gis[it])
+        assert all(p.grad.data_ptr() == g.data_ptr() for p, g in zip(ob.params, ob.grads)), 'gradient was copied, not adopted'
+        ob.step()
+        ob.zero_grad()
+    ob.close()
+    for a, b, p0 in zip(pa, ob.params, sc):
+        assert util.rel_err(b.detach() - p0, a.detach() - p0) <= 2e-3
+    ob.reset()
+    assert ob.steps == 0 and float(ob.exp_avg.abs().sum()) == 0.0
+    # after close() the backward allocates its own gradient tensors again
+    q = [p.clone().requires_grad_(True) for p in sc]
+    fgs_b200.diff_rasterize(*q, torch.empty(0), rs).backward(gis[0])
+    assert q[0].grad.data_ptr() != ob.grads[0].data_ptr()
+    dist.destroy_process_group()
+    print('PeerAdam class ok')
+
+
 def check_gpu_test_code():
     """The bodies of the `-m gpu` tests of the widened rows, executed here with device 'cpu' (and smaller sizes where the
     test takes them as parameters): validates the TEST code that will first meet a GPU at the end of the round."""
@@ -279,5 +333,5 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'fourd', 'training']
     for name in which:
         {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
-         'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code}[name]()
+         'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code, 'peer_adam': check_peer_adam_class}[name]()
     print('ALL OK')

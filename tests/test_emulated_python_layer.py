@@ -11,7 +11,7 @@ from pathlib import Path
 import pytest
 
 SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
-PARTS = ['rasterizer', 'loss', 'densification', 'fourd', 'gpu_tests'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
+PARTS = ['rasterizer', 'loss', 'densification', 'fourd', 'gpu_tests', 'peer_adam'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
 
 
 @pytest.mark.parametrize('part', PARTS)
