@@ -54,19 +54,20 @@ def test_emulated_kernels_match_reference_golden(emu, name):
     img, state, scr, inp = E.forward(lib, list(sc), st)
     ref_img = torch.from_numpy(z['image']).double()
     l1 = (torch.from_numpy(np.array(img)).double() - ref_img).abs().mean().item()
-    assert l1 <= 1e-4, f'image mean-L1 vs reference {l1}'
+    assert l1 <= 1e-6, f'image mean-L1 vs reference {l1}'  # north_star: 1e-4; measured 6e-8 ... 1.1e-7
     dens = np.zeros((2, n), dtype=np.float32)
     grads = E.backward(lib, img, gi, state, scr, inp, densification_info=dens)
     for k, g in zip(NAMES, grads):
         rg = torch.from_numpy(z[f'grad_{k}']).double()
         e = util.rel_err(g, rg)
-        assert e <= 5e-3, f'{name}/{k}: |emulated kernels - reference|_1 / |reference|_1 = {e}'
+        # north_star: rtol 1e-3; measured 5e-7 ... 1.8e-5 (the reference's fast-math is the larger part of it)
+        assert e <= 1e-4, f'{name}/{k}: |emulated kernels - reference|_1 / |reference|_1 = {e}'
         assert float(g[rg.reshape(n, -1).abs().sum(1) == 0].abs().sum()) <= 1e-12 or k == 'means'  # zero rows stay zero
     rd = torch.from_numpy(z['densification_info']).double()
     assert torch.equal(rd[0], torch.from_numpy(dens[0]).double())
-    assert util.rel_err(torch.from_numpy(dens[1]), rd[1]) <= 5e-3
+    assert util.rel_err(torch.from_numpy(dens[1]), rd[1]) <= 1e-4
     inf_img, _, _, _ = E.forward(lib, list(sc), st, training=False, to_chw=False, clamp=True)
-    assert (torch.from_numpy(np.array(inf_img)).double() - torch.from_numpy(z['inference_hwc']).double()).abs().mean().item() <= 1e-4
+    assert (torch.from_numpy(np.array(inf_img)).double() - torch.from_numpy(z['inference_hwc']).double()).abs().mean().item() <= 1e-6
 
 
 @pytest.mark.parametrize('bases,aa', [(16, False), (4, True)])
