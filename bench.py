@@ -165,6 +165,9 @@ def run_gpu(args, impl):
     else:
         params = [p.to(dev).contiguous().requires_grad_(True) for p in sc]
         opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
+    flat = None
+    if getattr(args, 'flat_allreduce', False) and dist is not None and impl == 'mine' and peer is None:
+        flat = parallel.FlatGradients(params)
     bg = torch.zeros(3, device=dev)
     st_dev = [settings_tuple(c, dev, bg) for c in cams]
     gt_dev = [t.to(dev).float().div_(255.0) for t in targets]
@@ -204,7 +207,10 @@ def run_gpu(args, impl):
         if dist is not None and peer is None:
             # (parallel.allreduce_and_step pipelines the per-tensor Adam behind the all-reduces; it is covered by the
             # gloo tests but has no NCCL measurement yet, so the benchmark stays on the path that was measured)
-            parallel.allreduce_gradients(params)
+            if flat is not None:
+                flat.allreduce(params)
+            else:
+                parallel.allreduce_gradients(params)
         opt.step()
         opt.zero_grad()
         return loss
@@ -587,6 +593,9 @@ def main():
     ap.add_argument('--overlap-adam', action='store_true',
                     help='EXPERIMENTAL (not yet measured on hardware): fused path with the zero-gradient Adam of invisible '
                          'Gaussians\' sh_rest rows on a side stream under the blend backward (fgs_debug_set_overlap_adam)')
+    ap.add_argument('--flat-allreduce', action='store_true',
+                    help='N > 1 only, EXPERIMENTAL: the backward writes the six gradients into one flat buffer and ONE NCCL '
+                         'all-reduce sums it (fgs_b200.parallel.FlatGradients) instead of six collectives')
     ap.add_argument('--peer-adam', action='store_true',
                     help='N > 1 only, EXPERIMENTAL: gradient reduction + Adam + parameter broadcast in one kernel over '
                          'NVLink peer memory (fgs_b200.parallel.PeerAdam) instead of NCCL all-reduce + FusedAdam.step')

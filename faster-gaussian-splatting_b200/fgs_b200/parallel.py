@@ -103,6 +103,53 @@ def peer_layout(shapes: Sequence[Sequence[int]]) -> tuple[list[int], list[int], 
     return offsets, counts, off
 
 
+class FlatGradients:
+    """One contiguous buffer behind the six gradient tensors, so that the view-parallel reduction is ONE all-reduce of
+    236 N bytes instead of six collectives (five of them latency-bound).  While the object is alive the rasterizer's
+    backward writes its gradients straight into views of the buffer (`_C.set_gradient_outputs`; autograd adopts them as
+    `.grad` without a copy), so nothing is gathered or scattered.  One backward per rank and step: a second backward before
+    `zero_grad()` would overwrite the buffer the first one's `.grad` lives in (accumulate views with separate tensors).
+
+        flat = FlatGradients(params)                       # every rank
+        loss.backward(); flat.allreduce(params, dens); optimizer.step(); optimizer.zero_grad()
+
+    EXPERIMENTAL: covered by the gloo tests, not yet measured over NCCL (bench.py --flat-allreduce)."""
+
+    def __init__(self, params: Sequence[torch.Tensor], register: bool = True) -> None:
+        self.shapes = [tuple(p.shape) for p in params]
+        self.offsets, self.counts, total = peer_layout(self.shapes)
+        self.buffer = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        self.views = [self.buffer[o:o + c].view(shape) for o, c, shape in zip(self.offsets, self.counts, self.shapes)]
+        self._registered = False
+        if register:
+            from . import _C
+            _C.set_gradient_outputs(self.views)
+            self._registered = True
+
+    def allreduce(self, params: Sequence[torch.Tensor], densification_info: torch.Tensor | None = None, group=None) -> None:
+        """Sum the gradients (and densification_info) over the group; afterwards every p.grad is a view of the buffer."""
+        import torch.distributed as dist
+        for p, v in zip(params, self.views):
+            if p.grad is None:
+                raise RuntimeError('FlatGradients.allreduce: parameter without gradient (every rank must render a view)')
+            if p.grad.data_ptr() != v.data_ptr():  # produced elsewhere (another loss term, the CPU tests): bring it in
+                v.copy_(p.grad)
+                p.grad = v
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        works = [dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+        if densification_info is not None and densification_info.numel() > 0:
+            works.append(dist.all_reduce(densification_info, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def close(self) -> None:
+        if self._registered:
+            from . import _C
+            _C.set_gradient_outputs(None)
+            self._registered = False
+
+
 class PeerAdam:
     """Dense Adam over a view-parallel group without an all-reduce: gradients and parameters live in symmetric memory
     (`torch.distributed._symmetric_memory`), one kernel per step (csrc/peer_adam.cu) sums this rank's slice of every

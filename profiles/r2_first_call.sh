@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 if [ "${NGPU:-1}" -gt 1 ]; then
   FGS_TEST_PEER_ADAM=1 timeout 600 python -m pytest tests/test_peer_adam.py -m gpu -x -q -s > $O/r2_peer_adam_test.txt 2>&1
-  for flag in "" "--peer-adam"; do
+  for flag in "" "--flat-allreduce" "--peer-adam"; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $NGPU --steps 100 --warmup 10 $flag > "$O/r2_bench_${NGPU}gpu${flag}.json" 2> "$O/r2_bench_${NGPU}gpu${flag}.err"
   done

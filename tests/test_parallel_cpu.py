@@ -144,3 +144,44 @@ def test_allreduce_is_noop_without_process_group():
     p.grad = torch.full((3,), 2.0)
     parallel.allreduce_gradients([p])
     assert torch.equal(p.grad, torch.full((3,), 2.0))
+
+
+def _worker_flat(rank, world, port, out_dict):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from fgs_b200 import parallel
+    shapes = [(41, 3), (41, 3), (41, 4), (41, 1), (41, 1, 3), (41, 15, 3)]  # 41 * 3 = 123: regions need padding to float4s
+
+    def grads():
+        return [torch.randn(s, generator=torch.Generator().manual_seed(10 * rank + i)) for i, s in enumerate(shapes)]
+    pa = [torch.zeros(s, requires_grad=True) for s in shapes]
+    pb = [torch.zeros(s, requires_grad=True) for s in shapes]
+    for p, g in zip(pa, grads()):
+        p.grad = g
+    for p, g in zip(pb, grads()):
+        p.grad = g
+    dens_a, dens_b = torch.full((2, 41), float(rank + 1)), torch.full((2, 41), float(rank + 1))
+    flat = parallel.FlatGradients(pa, register=False)  # register=True hands the views to the CUDA backward: not on CPU
+    flat.allreduce(pa, densification_info=dens_a)
+    parallel.allreduce_gradients(pb, densification_info=dens_b)
+    same_memory = all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(pa, flat.views))
+    padding_zero = all(float(flat.buffer[o + c:o + (c + 3) // 4 * 4].abs().sum()) == 0.0 for o, c in zip(flat.offsets, flat.counts))
+    out_dict[rank] = ([p.grad.clone() for p in pa], [p.grad.clone() for p in pb], dens_a, dens_b, same_memory, padding_zero)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradients_single_allreduce_equals_six():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_flat, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        ga, gb, da, db, same_memory, padding_zero = out[rank]
+        assert same_memory and padding_zero
+        for a, b in zip(ga, gb):
+            assert torch.equal(a, b), 'one flat all-reduce differs from six all-reduces'
+        assert torch.equal(da, db) and float(da[0, 0]) == 3.0
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b), 'ranks diverged'
