@@ -27,3 +27,6 @@ timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu-baseline --overlap-
 timeout 600 python -m pytest tests/test_widen_overlap_gpu.py -m gpu -q -s > $O/r2_overlap_test.txt 2>&1
 timeout 900 python -m pytest tests/test_widen_fourd.py -m gpu -q -s > $O/r2_fourd_test.txt 2>&1
 timeout 600 python profiles/bench_fourd.py > $O/r2_fourd_bench.json 2> $O/r2_fourd_bench.err
+# one --set full capture of the two heaviest new kernels (read here with ncu -i ... --page raw --csv)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ssim_stats|ssim_grad|gather_rows' -c 6 -o $O/r2_widen_full \
+  python profiles/bench_widen.py > /dev/null 2>&1
