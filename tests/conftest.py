@@ -19,3 +19,13 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     return torch.device('cuda:0')
+
+
+def pytest_collection_modifyitems(config, items):
+    """A per-test time limit (pytest-timeout, if installed): the emulated-kernel tests run hundreds of host threads with
+    barriers -- a deadlock must fail the test, not hang the suite."""
+    if not config.pluginmanager.hasplugin('timeout'):
+        return
+    for item in items:
+        if item.get_closest_marker('timeout') is None:
+            item.add_marker(pytest.mark.timeout(1800))
