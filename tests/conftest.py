@@ -28,4 +28,6 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker('timeout') is None:
-            item.add_marker(pytest.mark.timeout(1800))
+            # method 'thread': the main thread sits inside a ctypes call while the emulator runs, where a signal handler
+            # would never get to run
+            item.add_marker(pytest.mark.timeout(1800, method='thread'))
