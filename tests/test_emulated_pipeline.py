@@ -246,3 +246,33 @@ def test_emulated_overlapped_adam_schedule_matches_default(emu, n, rest_bases):
     moved = (pb[5][never] - params[5][never]).abs()
     assert float(moved.min()) > 0.0, 'an sh_rest row of an invisible Gaussian was skipped by both kernels'
     assert not np.array_equal(mb[5][never.numpy()], np.zeros_like(mb[5][never.numpy()]))
+
+
+@pytest.mark.skipif(os.environ.get('FGS_TEST_SLOW') != '1', reason='~5 min on the emulator (12.6 M pixels); FGS_TEST_SLOW=1')
+def test_emulated_more_than_65536_tiles_uses_32bit_tile_keys(emu):
+    """257 x 256 tiles: the tile sort, create_instances and ranges_gather run their uint32 key instantiations.  Image and
+    gradients inside a 640 x 480 window against the oracle rendering that window (gradient zero outside it)."""
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    E, lib = emu
+    w, h, n = 16 * 257, 12 * 256, 40
+    sc, cam = syn.make_scene(n, 1, width=256), syn.make_camera(1, w, h)
+    st = util.settings_for(cam, bg=(0.2, 0.3, 0.4))
+    x0, y0, x1, y1 = w // 2 - 320, h // 2 - 240, w // 2 + 320, h // 2 + 240
+    gwin = syn.make_grad_image(x1 - x0, y1 - y0, 3)
+    gi = torch.zeros(3, h, w)
+    gi[:, y0:y1, x0:x1] = gwin
+    img, state, scr, inp = E.forward(lib, list(sc), st)
+    assert state.n_instances > 0
+    grads = E.backward(lib, img, gi, state, scr, inp)
+    leaves = [p.double().clone().requires_grad_(True) for p in sc]
+    s = O.Settings(*st)
+    s = s._replace(w2c=s.w2c.double(), cam_position=s.cam_position.double(), bg_color=s.bg_color.double())
+    out = O.render(*leaves, s, window=(x0, y0, x1, y1))
+    out.image.backward(gwin.double())
+    crop = torch.from_numpy(np.array(img))[:, y0:y1, x0:x1].double()
+    assert (crop - out.image.detach()).abs().mean().item() <= 2e-6
+    assert float(out.image.detach().sub(torch.tensor([0.2, 0.3, 0.4], dtype=torch.float64)[:, None, None]).abs().max()) > 0.05  # not just background
+    for k, g, leaf in zip(NAMES, grads, leaves):
+        ref = torch.zeros_like(leaf) if leaf.grad is None else leaf.grad
+        assert util.rel_err(g, ref) <= 5e-4, k
