@@ -41,7 +41,7 @@ LRS = dict(means=1.6e-4, scales=5e-3, rotations=1e-3, opacities=2.5e-2, sh_coeff
 
 
 def check_rasterizer_api():
-    n, w, h = 300, 64, 48
+    n, w, h = 200, 48, 36
     sc, cam = syn.make_scene(n, 4), syn.make_camera(4, w, h)
     st = util.settings_for(cam, bg=(0.1, 0.2, 0.3))
     gi = syn.make_grad_image(w, h, 4)
@@ -323,7 +323,7 @@ def check_gpu_test_code():
     TL.test_loss_gpu_vs_oracle(dev, 16, 12, True, 1.0, 0.0)
     TD.test_adc_gpu_vs_oracle(dev, 2500, True)
     TD.test_prune_sort_extend_reset_morton_gpu(dev, n=4000)
-    TO.test_overlapped_adam_schedule_matches_default(dev, 400, 64, 48)
+    TO.test_overlapped_adam_schedule_matches_default(dev, 300, 48, 36)
     TF.test_fourd_forward_backward_vs_oracle(dev)
     print('GPU test code ok')
 

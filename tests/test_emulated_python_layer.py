@@ -11,11 +11,13 @@ from pathlib import Path
 import pytest
 
 SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
-PARTS = ['rasterizer', 'loss', 'densification', 'fourd', 'gpu_tests', 'peer_adam'] + (['training'] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
+# two subprocesses (each pays the interpreter + torch start-up once)
+PARTS = [('rasterizer', 'loss', 'peer_adam'), ('densification', 'fourd', 'gpu_tests')] + \
+    ([('training',)] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
 
 
-@pytest.mark.parametrize('part', PARTS)
-def test_python_layer_on_emulated_library(part):
+@pytest.mark.parametrize('parts', PARTS, ids=lambda p: '+'.join(p))
+def test_python_layer_on_emulated_library(parts):
     env = {k: v for k, v in os.environ.items() if k != 'FGS_B200_LIB'}
-    r = subprocess.run([sys.executable, str(SCRIPT), part], capture_output=True, text=True, timeout=1500, env=env)
+    r = subprocess.run([sys.executable, str(SCRIPT), *parts], capture_output=True, text=True, timeout=1700, env=env)
     assert r.returncode == 0 and 'ALL OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
