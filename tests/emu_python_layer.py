@@ -87,6 +87,18 @@ def check_rasterizer_api():
     scores = torch.zeros(n)
     fgs_b200.update_pruning_scores(scores, *sc, rs)
     assert util.rel_err(scores, O.pruning_scores(*sc, O.Settings(*st))) <= 2e-4
+    # two forwards before their backwards (multi-view accumulation): the opaque per-call buffers must not interfere
+    rs2 = fgs_b200.RasterizerSettings(*util.settings_for(syn.make_camera(1, w, h), bg=(0.1, 0.2, 0.3)))
+    gi2 = syn.make_grad_image(w, h, 1)
+
+    def accumulated(views):
+        ps = [p.clone().requires_grad_(True) for p in sc]
+        imgs = [fgs_b200.diff_rasterize(*ps, torch.empty(0), r) for r, _ in views]
+        sum((im * g).sum() for im, (_, g) in zip(imgs, views)).backward()
+        return [p.grad for p in ps]
+    both, first, second = accumulated([(rs, gi), (rs2, gi2)]), accumulated([(rs, gi)]), accumulated([(rs2, gi2)])
+    for x, y, z in zip(both, first, second):
+        assert util.rel_err(x, y + z) <= 1e-5
     # the three small operators (3D filter, MCMC relocation, noise) against the compiled reference's golden and the oracle
     from tests import test_aux_ops as TA
     from fgs_b200 import _C
