@@ -323,6 +323,66 @@ def check_peer_adam_class():
     print('PeerAdam class ok')
 
 
+def check_reference_bindings():
+    """INTEGRATION.md option B, executed: the REFERENCE's own torch_bindings/*.py (autograd Function, FusedAdam, the small
+    operators; read from /root/reference, which only exists in the development container) import `_C` from a package
+    named FasterGSCudaBackend -- here that `_C` is this repo's fgs_b200._C over the emulated library.  Their unmodified
+    Python then renders, back-propagates and steps; results against the oracle."""
+    import types
+    ref_pkg = Path('/root/reference/FasterGSCudaBackend/FasterGSCudaBackend')
+    if not (ref_pkg / 'torch_bindings' / 'rasterization.py').exists():
+        print('reference bindings: /root/reference not present, skipped')
+        return
+    from fgs_b200 import _C
+    for k in [k for k in sys.modules if k == 'FasterGSCudaBackend' or k.startswith('FasterGSCudaBackend.')]:
+        del sys.modules[k]
+    pkg = types.ModuleType('FasterGSCudaBackend')
+    pkg.__path__ = [str(ref_pkg)]
+    pkg._C = _C
+    sys.modules['FasterGSCudaBackend'] = pkg
+    sys.modules['FasterGSCudaBackend._C'] = _C
+    import importlib
+    tb = importlib.import_module('FasterGSCudaBackend.torch_bindings')
+    assert str(ref_pkg) in tb.__file__ and str(ref_pkg) in sys.modules['FasterGSCudaBackend.torch_bindings.rasterization'].__file__
+    n, w, h = 200, 48, 36
+    sc, cam = syn.make_scene(n, 7), syn.make_camera(7, w, h)
+    st = util.settings_for(cam, bg=(0.3, 0.2, 0.1))
+    gi = syn.make_grad_image(w, h, 7)
+    params = [p.clone().requires_grad_(True) for p in sc]
+    dens = torch.zeros(2, n)
+    img = tb.diff_rasterize(*params, dens, tb.RasterizerSettings(*st))
+    img.backward(gi)
+    dens64 = torch.zeros(2, n, dtype=torch.float64)
+    out, ograds = O.render_and_grads(list(sc), O.Settings(*st), gi, dtype=torch.float64, densification_info=dens64)
+    assert (img.detach().double() - out.image).abs().mean().item() <= 2e-6
+    for p, og in zip(params, ograds):
+        assert util.rel_err(p.grad, og) <= 2e-4
+    assert util.rel_err(dens[1], dens64[1]) <= 2e-4
+    opt = tb.FusedAdam([{'params': [p], 'lr': LRS[k]} for p, k in zip(params, NAMES)], lr=0.0, eps=1e-15)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in params]
+    ref_opt = torch.optim.Adam([{'params': [p], 'lr': LRS[k]} for p, k in zip(ref_params, NAMES)], lr=0.0, eps=1e-15)
+    for p, q in zip(params, ref_params):
+        q.grad = p.grad.clone()
+    opt.step()
+    ref_opt.step()
+    for p, q, p0 in zip(params, ref_params, sc):
+        assert util.rel_err(p.detach() - p0, q.detach() - p0) <= 2e-3
+    with torch.no_grad():
+        hwc = tb.rasterize(*sc, tb.RasterizerSettings(*st), to_chw=False)
+    assert tuple(hwc.shape) == (h, w, 3) and (hwc.permute(2, 0, 1) - img.detach().clamp(0, 1)).abs().max().item() <= 1e-6
+    scores = torch.zeros(n)
+    tb.update_pruning_scores(scores, *sc, tb.RasterizerSettings(*st))
+    assert util.rel_err(scores, O.pruning_scores(*sc, O.Settings(*st))) <= 2e-4
+    # the small operators through the reference's own wrappers
+    from tests import test_aux_ops as TA
+    d, filt = TA._inputs('cpu')
+    got = TA._run(tb, d, filt, _C.add_noise)
+    TA._compare(got, TA._oracle_run(TA._inputs('cpu')[0], filt), "reference's bindings over this repo's _C vs oracle")
+    for k in [k for k in sys.modules if k == 'FasterGSCudaBackend' or k.startswith('FasterGSCudaBackend.')]:
+        del sys.modules[k]
+    print("reference's own torch_bindings over fgs_b200._C ok")
+
+
 def check_gpu_test_code():
     """The bodies of the `-m gpu` tests of the widened rows, executed here with device 'cpu' (and smaller sizes where the
     test takes them as parameters): validates the TEST code that will first meet a GPU at the end of the round."""
@@ -345,5 +405,6 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['rasterizer', 'loss', 'densification', 'fourd', 'training']
     for name in which:
         {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
-         'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code, 'peer_adam': check_peer_adam_class}[name]()
+         'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code, 'peer_adam': check_peer_adam_class,
+         'reference_bindings': check_reference_bindings}[name]()
     print('ALL OK')
