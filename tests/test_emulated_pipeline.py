@@ -276,3 +276,23 @@ def test_emulated_more_than_65536_tiles_uses_32bit_tile_keys(emu):
     for k, g, leaf in zip(NAMES, grads, leaves):
         ref = torch.zeros_like(leaf) if leaf.grad is None else leaf.grad
         assert util.rel_err(g, ref) <= 5e-4, k
+
+
+@pytest.mark.skipif(os.environ.get('FGS_TEST_SLOW') != '1', reason='~1.5 min (12 000 Gaussians); FGS_TEST_SLOW=1')
+def test_emulated_mid_size_scene_multi_block_sorts(emu):
+    """8 000 visible Gaussians, 31 000 instances: several 2048-key tiles per sort pass (chunked onesweep with look-back), a
+    multi-block offsets scan, hundreds of blend items -- against the fp64 oracle."""
+    from fgs_b200 import synthetic as syn
+    from oracle import torch_oracle as O
+    E, lib = emu
+    n, w, h = 12000, 256, 144
+    sc, cam = syn.make_scene(n, 4, width=w), syn.make_camera(4, w, h)
+    st = util.settings_for(cam, bg=(0.1, 0.2, 0.3))
+    gi = syn.make_grad_image(w, h, 4)
+    img, state, scr, inp = E.forward(lib, list(sc), st)
+    grads = E.backward(lib, img, gi, state, scr, inp)
+    out, ograds = O.render_and_grads(list(sc), O.Settings(*st), gi, dtype=torch.float64)
+    assert state.n_visible == int(out.proj.visible.sum()) > 4096 and state.n_instances > 3 * 2048
+    assert (torch.from_numpy(np.array(img)).double() - out.image.detach()).abs().mean().item() <= 2e-6
+    for k, g, og in zip(NAMES, grads, ograds):
+        assert util.rel_err(g, og) <= 2e-4, k
