@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json: train iters/s @ 1M Gaussians, 1080p).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mine|reference] [--config c2|c3|c5] [--batch B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one training iteration of the reference's Trainer loop (Trainer.py:170-201) on one view:
-diff_rasterize forward + L1 loss + backward + FusedAdam.step + zero_grad, through the public Python
-operator API (the call a user of the reference makes).  Synthetic scene of the named shape
-(fgs_b200/synthetic.py), random-init parameters, fp32 arithmetic.
+One step = one training iteration of the reference's Trainer loop (Trainer.py:170-201): forward + loss + backward +
+Adam per view, through the public Python operator API (the call a user of the reference makes).  Synthetic scene
+of the named shape (fgs_b200/synthetic.py), random-init parameters, fp32 arithmetic.
 
-Prints ONE JSON line on rank 0.  Keys: see DESIGN.md "Measurement".  With N > 1 every rank renders its
-own view of an N-view batch (weak scaling), gradients are summed with one NCCL all-reduce per tensor
-and every rank applies the identical Adam step; value = views trained per second over all ranks.
-`--impl reference` runs the UNMODIFIED reference CUDA backend from baseline/_ref through the same loop
-(north_star: "next to the reference's own CUDA path"); if it is not installed, the CPU oracle port
-is timed instead and the line says so.
+Configs (BASELINE.json):  c2 (default) = configs[1], 1 M Gaussians at 1920x1080;  c3 = configs[2], 3 M Gaussians at
+1600x1063, FasterGSFused path;  c5 = configs[4], 500 k 4D Gaussians x 150 time steps at 1080p (no reference source).
+configs[3] (8-view batches on 1/2/4/8 GPUs) = `--batch 8` with `--gpus N`: the 8 views of a batch are split over the
+ranks (strong scaling); without --batch every rank trains one view per step (weak scaling, batch = N).
+
+Prints ONE JSON line on rank 0.  Keys: see DESIGN.md "Measurement".  With N > 1 every rank renders its own views,
+the gradients are summed over the ranks and every rank ends the step with identical parameters (--dp-mode selects how:
+one kernel over NVLink peer / multicast memory, NCCL reduce-scatter + sharded Adam + all-gather, or NCCL all-reduce +
+dense Adam); value = views trained per second over all ranks.  `--impl reference` runs the UNMODIFIED reference CUDA
+backend from baseline/_ref through the same loop (north_star: "next to the reference's own CUDA path"); if it is not
+installed, the CPU oracle port is timed instead and the line says so.
 """
 from __future__ import annotations
 
@@ -34,10 +38,17 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / 'faster-gaussian-splatting_b200'))
 sys.path.insert(0, str(ROOT))
 
-N_GAUSSIANS, WIDTH, HEIGHT, SH_BASES, N_VIEWS = 1_000_000, 1920, 1080, 16, 8
+SH_BASES, N_VIEWS = 16, 8
 LRS = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]  # means, scales, rotations, opacities, sh0, sh_rest (Trainer.py:56-66)
-METRIC = 'train_iters_per_sec_1M_gaussians_1080p'
-T_TILES = math.ceil(WIDTH / 16) * math.ceil(HEIGHT / 12)
+CONFIGS = {
+    'c2': dict(n=1_000_000, w=1920, h=1080, metric='train_iters_per_sec_1M_gaussians_1080p',
+               workload='configs[1]: fastergs_garden shape, 1M Gaussians, 1920x1080, 16 SH bases'),
+    'c3': dict(n=3_000_000, w=1600, h=1063, metric='train_iters_per_sec_3M_gaussians_1600p',
+               workload='configs[2]: bicycle shape, 3M Gaussians, 1600x1063, 16 SH bases, FasterGSFused backward+Adam'),
+    'c5': dict(n=500_000, w=1920, h=1080, metric='train_iters_per_sec_500k_4d_gaussians_1080p',
+               workload='configs[4]: FasterGS4D shape, 500k 4D Gaussians x 150 time steps, 1920x1080, 16 SH bases'),
+}
+DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc')
 
 
 def peak_hbm_gbs():
@@ -92,7 +103,7 @@ class ClockSampler:
 
 
 def algorithmic_bytes(N, V, I, P, T, S=45):
-    """compulsory bytes per stage and per unfused training iteration."""
+    """compulsory bytes per stage and per training iteration."""
     st = {
         'preprocess': 44 * N + (12 + 4 * S) * V + 4 * N + 56 * V,
         'depth sort': 16 * V,
@@ -106,12 +117,14 @@ def algorithmic_bytes(N, V, I, P, T, S=45):
     }
     st['iteration'] = 1940 * N + (408 + 12 * S) * V + 28 * I + 52 * P + 16 * T
     st['iteration_fused'] = 1468 * N + (352 + 8 * S) * V + 28 * I + 52 * P + 16 * T
+    st['preprocess_backward_fused'] = st['iteration_fused'] - (st['iteration'] - st['preprocess_backward'] - st['adam_step'])
     return st
 
 
-def make_problem(device, n=N_GAUSSIANS, w=WIDTH, h=HEIGHT, views=N_VIEWS):
+def make_problem(cfg, views=N_VIEWS):
     from fgs_b200 import synthetic as syn
-    sc = syn.make_scene(n, 0)
+    n, w, h = cfg['n'], cfg['w'], cfg['h']
+    sc = syn.make_scene(n, 0, width=w)
     cams = [syn.make_camera(k, w, h, n_views=views) for k in range(views)]
     # ground-truth images are 8-bit (as image datasets are): the e2e path ships them over PCIe as uint8 and
     # converts on the device; the resident path trains on the very same (quantised) float targets
@@ -127,22 +140,48 @@ def settings_tuple(cam, device, bg):
 def load_backend(impl):
     if impl == 'reference':
         from tests import util
-        ref = util.load_reference()
-        return ref
+        return util.load_reference()
     import fgs_b200
     return fgs_b200
 
 
+_WINDOW = {}
+
+
+def torch_dssim(x, y):
+    """1 - mean SSIM with the 11x11 Gaussian window (sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2): plain torch ops
+    for the arms that do not use the fused loss kernel."""
+    key = (x.device, x.dtype)
+    if key not in _WINDOW:
+        g = torch.exp(-((torch.arange(11, dtype=x.dtype, device=x.device) - 5.0) ** 2) / (2 * 1.5 ** 2))
+        g = g / g.sum()
+        _WINDOW[key] = (g[:, None] * g[None, :]).expand(3, 1, 11, 11).contiguous()
+    w = _WINDOW[key]
+    conv = lambda t: torch.nn.functional.conv2d(t[None], w, padding=5, groups=3)[0]
+    mx, my = conv(x), conv(y)
+    sxx, syy, sxy = conv(x * x) - mx * mx, conv(y * y) - my * my, conv(x * y) - mx * my
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ssim = ((2 * mx * my + c1) * (2 * sxy + c2)) / ((mx * mx + my * my + c1) * (sxx + syy + c2))
+    return 1.0 - ssim.mean()
+
+
 def run_gpu(args, impl):
+    cfg = CONFIGS[args.config]
+    n_gauss, width, height = cfg['n'], cfg['w'], cfg['h']
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    n_ranks = world  # ranks of the job as launched (the reference arm folds them into one process below)
+    batch = args.batch if args.batch else n_ranks  # views per optimizer step over the whole job
+    if batch % n_ranks:
+        raise SystemExit(f'bench.py: --batch {batch} is not a multiple of the {n_ranks} ranks')
     if impl == 'reference' and world > 1:
-        # the reference has no multi-GPU mode (Renderer.py:58-61): its semantics for an N-view batch is
+        # the reference has no multi-GPU mode (Renderer.py:58-61): its semantics for a B-view batch is
         # gradient accumulation on one GPU; rank 0 runs that alone, the other ranks leave
         if rank != 0:
             return None
-        args.accumulate_views, world = world, 1
+        world = 1
+    vpr = batch // world  # views per rank and step
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist = None
@@ -157,91 +196,109 @@ def run_gpu(args, impl):
             return run_cpu_port(args, reason='baseline/_ref not installed on this box')
         return None
 
-    sc, cams, targets = make_problem(dev)
-    peer = None
-    if getattr(args, 'peer_adam', False) and dist is not None and impl == 'mine':
-        peer = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS)
-        params, opt = peer.params, peer
+    sc, cams, targets = make_problem(cfg)
+    mine = impl == 'mine'
+    # ---- how the step ends: who sums the gradients and who applies Adam ------------------------------------------
+    dp_mode = args.dp_mode if (dist is not None and mine) else 'none'
+    if dp_mode == 'auto':
+        dp_mode = 'peer-mc'
+    opt_obj = None  # PeerAdam / ShardedAdam own flat parameter + gradient buffers
+    if dp_mode in ('peer', 'peer-mc'):
+        try:
+            opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=(dp_mode == 'peer-mc'))
+        except Exception as e:  # no symmetric memory / no NVLS on this box: NCCL collectives instead, and say so
+            if args.dp_mode != 'auto':
+                raise
+            print(f'[bench] PeerAdam unavailable ({e!r}); falling back to --dp-mode sharded', file=sys.stderr)
+            dp_mode = 'sharded'
+    if dp_mode == 'sharded':
+        opt_obj = parallel.ShardedAdam([p.to(dev).contiguous() for p in sc], LRS)
+    if opt_obj is not None:
+        params, opt = opt_obj.params, opt_obj
     else:
         params = [p.to(dev).contiguous().requires_grad_(True) for p in sc]
         opt = be.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, LRS)], lr=0.0, eps=1e-15)
-    flat = None
-    if getattr(args, 'flat_allreduce', False) and dist is not None and impl == 'mine' and peer is None:
-        flat = parallel.FlatGradients(params)
+    flat = parallel.FlatGradients(params) if dp_mode == 'flat' else None
+    registered = opt_obj if opt_obj is not None else flat  # object whose flat gradient buffer the backward writes into
     bg = torch.zeros(3, device=dev)
     st_dev = [settings_tuple(c, dev, bg) for c in cams]
     gt_dev = [t.to(dev).float().div_(255.0) for t in targets]
+    gt8_dev = [t.to(dev) for t in targets]
     gt_pin = [t.pin_memory() for t in targets]
     w2c_pin = [c.w2c.pin_memory() for c in cams]
     pos_pin = [c.position.pin_memory() for c in cams]
     empty = torch.empty(0)
 
-    acc = max(int(getattr(args, 'accumulate_views', 1)), 1)
+    def view_of(mi):  # micro-step mi of rank r trains view (mi * world + r) of the 8-view ring
+        return (mi * world + rank) % N_VIEWS
 
-    def view_of(it):  # rank r trains view (it * world + r) of the 8-view ring
-        return (it * world + rank) % N_VIEWS
-
-    use_fused = (impl == 'mine') and dist is None and not args.unfused
-    if impl == 'mine' and getattr(args, 'overlap_adam', False):
+    # FasterGSFused semantics (backward applies Adam in the same kernel) needs the whole batch in one backward
+    use_fused = mine and dist is None and vpr == 1 and not args.unfused
+    fused_loss = mine and not args.torch_loss
+    if mine and args.overlap_adam:
         from fgs_b200 import _capi
         _capi.load().fgs_debug_set_overlap_adam(1)
-    fused_loss = (impl == 'mine') and getattr(args, 'fused_loss', False)
-    if fused_loss:
-        from fgs_b200 import loss as loss_mod
+    if mine:
+        from fgs_b200 import _C as mine_C, loss as loss_mod
+    lam = (0.8, 0.2) if args.yaml_loss else (1.0, 0.0)
+    dens_info = torch.zeros(2, n_gauss, device=dev) if args.yaml_loss else empty
 
-    def train_view(st, gt, fused):
+    def train_view(st, gt, fused, j=0):
+        """forward + loss + backward of one view; gt is uint8 or float on the device."""
         rs = be.RasterizerSettings(*st)
+        if registered is not None and vpr > 1:
+            # the first view of the step writes its gradients straight into the flat buffer, the following views
+            # into fresh tensors that autograd adds onto it
+            mine_C.set_gradient_outputs(registered.grads if opt_obj is not None else registered.views) if j == 0 else mine_C.set_gradient_outputs(None)
         if fused:  # backward applies the Adam update in the same kernel; opt.step() is then a no-op
-            img = be.diff_rasterize_fused(*params, empty, rs, opt)
+            img = be.diff_rasterize_fused(*params, dens_info, rs, opt)
         else:
-            img = be.diff_rasterize(*params, empty, rs)
+            img = be.diff_rasterize(*params, dens_info, rs)
         if fused_loss:  # csrc/loss.cu: loss value and d loss / d image in one kernel, uint8 or float target
-            terms, grad_image = loss_mod.l1_dssim_loss_and_grad(img.detach(), gt, 1.0, 0.0)
+            terms, grad_image = loss_mod.l1_dssim_loss_and_grad(img.detach(), gt, lam[0], lam[1])
             img.backward(grad_image)
-            loss = terms[0]
+            return terms[0]
+        if gt.dtype == torch.uint8:
+            gt = gt.float().div_(255.0)  # uint8 -> float on the device
+        if args.yaml_loss:  # torch L1 + a torch conv2d DSSIM (NeRFICG's fused_dssim is not in the reference tree)
+            loss = lam[0] * (img - gt).abs().mean() + lam[1] * torch_dssim(img, gt)
         else:
-            if gt.dtype == torch.uint8:
-                gt = gt.float().div_(255.0)  # uint8 -> float on the device
             loss = (img - gt).abs().mean()
-            loss.backward()
-        if dist is not None and peer is None:
-            # (parallel.allreduce_and_step pipelines the per-tensor Adam behind the all-reduces; it is covered by the
-            # gloo tests but has no NCCL measurement yet, so the benchmark stays on the path that was measured)
-            if flat is not None:
+        loss.backward()
+        return loss
+
+    def finish_step():
+        if dist is not None and opt_obj is None:
+            if dp_mode == 'flat':
                 flat.allreduce(params)
+            elif dp_mode == 'pipelined':
+                parallel.allreduce_and_step(params, opt)
+                opt.zero_grad()
+                return
             else:
                 parallel.allreduce_gradients(params)
         opt.step()
         opt.zero_grad()
-        return loss
-
-    def accumulate_step(it):  # reference arm at N > 1: N views accumulated on one GPU, one optimizer step
-        loss = None
-        for j in range(acc):
-            k = (it * acc + j) % N_VIEWS
-            img = be.diff_rasterize(*params, empty, be.RasterizerSettings(*st_dev[k]))
-            loss = (img - gt_dev[k]).abs().mean()
-            loss.backward()
-        opt.step()
-        opt.zero_grad()
-        return loss
 
     def step_resident(it, fused=None):
-        if acc > 1:
-            return accumulate_step(it)
-        k = view_of(it)
-        return train_view(st_dev[k], gt_dev[k], use_fused if fused is None else fused)
+        f = use_fused if fused is None else fused
+        loss = None
+        for j in range(vpr):
+            k = view_of(it * vpr + j)
+            loss = train_view(st_dev[k], gt8_dev[k] if fused_loss else gt_dev[k], f, j)
+        finish_step()
+        return loss
 
-    # end to end: host buffers in, loss out.  The view's target image and camera are copied from pinned
-    # host memory every step (double-buffered on a copy stream so the transfer overlaps the previous
-    # step's kernels -- an input pipeline, as in any trainer), the loss is read back every step.
+    # end to end: host buffers in, loss out.  Every view's target image and camera are copied from pinned
+    # host memory (double-buffered on a copy stream so the transfer overlaps the previous view's kernels -- an input
+    # pipeline, as in any trainer), the loss is read back every step.
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [{'gt8': torch.empty_like(gt_dev[0], dtype=torch.uint8), 'w2c': torch.empty(4, 4, device=dev), 'pos': torch.empty(3, device=dev),
+    bufs = [{'gt8': torch.empty_like(gt8_dev[0]), 'w2c': torch.empty(4, 4, device=dev), 'pos': torch.empty(3, device=dev),
              'ready': torch.cuda.Event(), 'free': torch.cuda.Event()} for _ in range(2)]
 
-    def prefetch(it):
-        b = bufs[it % 2]
-        k = view_of(it)
+    def prefetch(mi):
+        b = bufs[mi % 2]
+        k = view_of(mi)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(b['free'])
             b['gt8'].copy_(gt_pin[k], non_blocking=True)
@@ -255,9 +312,8 @@ def run_gpu(args, impl):
     # drained by the synchronize that closes the timed region
     loss_pin = [torch.zeros(1).pin_memory() for _ in range(2)]
     loss_evt = [torch.cuda.Event() for _ in range(2)]
-    loss_log = []
-
     loss_ready = [torch.cuda.Event() for _ in range(2)]
+    loss_log = []
 
     def read_loss(it, loss):
         slot = it % 2
@@ -277,29 +333,31 @@ def run_gpu(args, impl):
     diag = {'h2d': True, 'd2h': True}  # FGS_BENCH_DIAG switches the two halves of the e2e path off in turn
 
     def step_e2e(it, fused=None):
-        if acc > 1:
-            return read_loss(it, accumulate_step(it))
+        f = use_fused if fused is None else fused
         if not diag['h2d']:
-            k = view_of(it)
-            loss = train_view(st_dev[k], gt_dev[k], use_fused if fused is None else fused)
+            loss = step_resident(it, fused)
             return read_loss(it, loss) if diag['d2h'] else loss
-        if e2e_state['primed'] < it:
-            for b in bufs:
+        loss = None
+        for j in range(vpr):
+            mi = it * vpr + j
+            if e2e_state['primed'] < mi:
+                for b in bufs:
+                    b['free'].record(torch.cuda.current_stream())
+                prefetch(mi)
+            prefetch(mi + 1)
+            e2e_state['primed'] = mi + 1
+            b = bufs[mi % 2]
+            k = view_of(mi)
+            torch.cuda.current_stream().wait_event(b['ready'])
+            st = (b['w2c'], b['pos']) + st_dev[k][2:]
+            if fused_loss:  # the loss kernel reads the uint8 staging buffer itself: released after the view
+                loss = train_view(st, b['gt8'], f, j)
                 b['free'].record(torch.cuda.current_stream())
-            prefetch(it)
-        prefetch(it + 1)
-        e2e_state['primed'] = it + 1
-        b = bufs[it % 2]
-        k = view_of(it)
-        torch.cuda.current_stream().wait_event(b['ready'])
-        st = (b['w2c'], b['pos']) + st_dev[k][2:]
-        if fused_loss:  # the loss kernel reads the uint8 staging buffer itself: released after the step
-            loss = train_view(st, b['gt8'], use_fused if fused is None else fused)
-            b['free'].record(torch.cuda.current_stream())
-        else:
-            gt = b['gt8'].float().div_(255.0)  # uint8 -> float on the device
-            b['free'].record(torch.cuda.current_stream())
-            loss = train_view(st, gt, use_fused if fused is None else fused)
+            else:
+                gt = b['gt8'].float().div_(255.0)  # uint8 -> float on the device
+                b['free'].record(torch.cuda.current_stream())
+                loss = train_view(st, gt, f, j)
+        finish_step()
         return read_loss(it, loss) if diag['d2h'] else loss
 
     init_params = [p.detach().clone() for p in params]
@@ -311,10 +369,12 @@ def run_gpu(args, impl):
             for p, p0 in zip(params, init_params):
                 p.copy_(p0)
                 p.grad = None
-        if peer is not None:
-            peer.reset()
+        if opt_obj is not None:
+            opt_obj.reset()
         else:
             opt.state.clear()
+        if dens_info.numel():
+            dens_info.zero_()
 
     def timed(fn, steps, warmup, sample_clocks=False):
         reset_state()
@@ -362,7 +422,7 @@ def run_gpu(args, impl):
     steps, warmup = args.steps, max(args.warmup, 3)
     # untimed pre-warm, both arms alike: every one of the 8 views three times, so that the caching
     # allocator has seen every scratch size and the clocks have ramped before the W warm-up steps
-    for it in range(3 * N_VIEWS):
+    for it in range(max(3 * N_VIEWS // vpr, 3)):
         step_resident(it)
     torch.cuda.synchronize()
     reset_state()
@@ -377,50 +437,63 @@ def run_gpu(args, impl):
             print(f'[diag] e2e h2d={h2d} d2h={d2h}: {ms_d / steps:.4f} ms/step', file=sys.stderr)
         diag['h2d'] = diag['d2h'] = True
     ms_total, clocks = timed(step_resident, steps, warmup, sample_clocks=True)
-    ms_e2e, _ = timed(step_e2e, steps, max(warmup, 10))
+    ms_e2e = float('nan') if args.quick else timed(step_e2e, steps, max(warmup, 10))[0]
     extra = {}
-    if use_fused:  # also report the strict drop-in path: diff_rasterize backward + separate FusedAdam.step
+    if use_fused and not args.quick:  # also report the strict drop-in path: diff_rasterize backward + separate FusedAdam.step
         ms_u, _ = timed(lambda it: step_resident(it, fused=False), steps, 3)
         ms_ue, _ = timed(lambda it: step_e2e(it, fused=False), steps, 3)
-        extra['dropin_unfused'] = {'value': round(world * 1000.0 * steps / ms_u, 3), 'ms_per_step': round(ms_u / steps, 4),
-                                   'e2e': round(world * 1000.0 * steps / ms_ue, 3), 'unit': 'iters/s',
-                                   'note': 'diff_rasterize + FusedAdam.step, the API the reference Trainer.py calls'}
+        extra['dropin_unfused'] = {'value': round(batch * 1000.0 * steps / ms_u, 3), 'ms_per_step': round(ms_u / steps, 4),
+                                   'e2e': round(batch * 1000.0 * steps / ms_ue, 3), 'unit': 'iters/s',
+                                   'note': 'diff_rasterize + FusedAdam.step, the API the reference Trainer.py calls '
+                                           '(loss as in `loss_path`)'}
     # second BASELINE.json metric: render ms (inference path, rasterize(..., to_chw=True)), inputs resident
     reset_state()
     with torch.no_grad():
         det = [p.detach() for p in params]
-        for it in range(5):
+        for it in range(0 if args.quick else 5):
             be.rasterize(*det, be.RasterizerSettings(*st_dev[it % N_VIEWS]), to_chw=True)
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        for it in range(50):
+        for it in range(1 if args.quick else 50):
             be.rasterize(*det, be.RasterizerSettings(*st_dev[it % N_VIEWS]), to_chw=True)
         r1.record()
         torch.cuda.synchronize()
-        render_ms = r0.elapsed_time(r1) / 50
+        render_ms = r0.elapsed_time(r1) / (1 if args.quick else 50)
     ms_step = ms_total / steps
-    value = world * acc * 1000.0 / ms_step
-    e2e_value = world * acc * 1000.0 / (ms_e2e / steps)
+    value = batch * 1000.0 / ms_step
+    e2e_value = batch * 1000.0 / (ms_e2e / steps)
 
+    if use_fused:
+        opt_path = 'fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)'
+    elif dp_mode in ('peer', 'peer-mc'):
+        opt_path = ('backward into a symmetric-memory gradient buffer, then ONE kernel: gradient sum over the ranks + Adam on the '
+                    'rank\'s 1/W slice + parameter broadcast (' + ('NVLS multimem.ld_reduce / multimem.st' if opt_obj.multicast else 'NVLink peer loads / stores') + ')')
+    elif dp_mode == 'sharded':
+        opt_path = 'backward, NCCL reduce-scatter, Adam on the rank\'s 1/W shard, NCCL all-gather'
+    elif dp_mode in ('allreduce', 'flat', 'pipelined'):
+        opt_path = f'backward, NCCL all-reduce ({dp_mode}), dense FusedAdam.step on every rank'
+    else:
+        opt_path = 'backward' + (f' x{vpr} (gradient accumulation)' if vpr > 1 else '') + ', then FusedAdam.step'
+    loss_desc = ('0.8 L1 + 0.2 DSSIM' if args.yaml_loss else 'L1') + (': fused loss+gradient kernel (csrc/loss.cu, fgs_b200.loss)' if fused_loss else ': torch ops')
     out = {
-        'metric': METRIC, 'value': round(value, 3), 'unit': 'iters/s', 'n_gpus': world if acc == 1 else acc, 'steps': steps,
-        'warmup': warmup, 'ms_per_step': round(ms_step, 4), 'higher_is_better': True, 'scaling': 'weak',
+        'metric': cfg['metric'], 'value': round(value, 3), 'unit': 'iters/s', 'n_gpus': n_ranks, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': round(ms_step, 4), 'higher_is_better': True,
+        'scaling': 'strong' if args.batch else 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: fastergs_garden shape, 1M Gaussians, 1920x1080, 16 SH bases, '
-                               'fwd + L1 + bwd + FusedAdam.step per view',
-                   'n_gaussians': N_GAUSSIANS, 'width': WIDTH, 'height': HEIGHT, 'views_per_step': world * acc,
+        'config': {'workload': cfg['workload'] + f'; fwd + loss + bwd + Adam per view, {batch} view(s) per optimizer step',
+                   'n_gaussians': n_gauss, 'width': width, 'height': height, 'views_per_step': batch,
                    'parallelism': f'view-dp{world}' if world > 1 else 'single',
-                   'optimizer_path': ('fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' if use_fused
-                                      else 'backward, then FusedAdam.step'),
-                   'adam_schedule': 'overlapped (side-stream Adam of invisible rows)' if getattr(args, 'overlap_adam', False) and impl == 'mine' else 'default',
-                   'loss_path': 'fused L1 kernel (csrc/loss.cu)' if fused_loss else 'torch ops: (img - gt).abs().mean()',
-                   'l2_policy': 'inputs_larger_than_L2 (params+moments+grads = 944 MB per step vs 126 MB L2)'},
-        'e2e': {'value': round(e2e_value, 3), 'unit': 'iters/s',
-                'h2d_bytes_per_step': 3 * WIDTH * HEIGHT + 64 + 12, 'd2h_bytes_per_step': 4,
-                'note': 'per step: uint8 target image + camera (w2c, position) from pinned host memory, loss scalar back'},
+                   'optimizer_path': opt_path,
+                   'adam_schedule': 'overlapped (side-stream Adam of invisible rows)' if (args.overlap_adam and mine) else 'default',
+                   'loss_path': loss_desc,
+                   'densification_info': 'accumulated every step' if args.yaml_loss else 'not collected',
+                   'l2_policy': f'inputs_larger_than_L2 (params+moments+grads = {944 * n_gauss // 1_000_000} MB per step vs 126 MB L2)'},
+        'e2e': {'value': None if args.quick else round(e2e_value, 3), 'unit': 'iters/s',
+                'h2d_bytes_per_step': vpr * (3 * width * height + 64 + 12), 'd2h_bytes_per_step': 4,
+                'note': 'per view: uint8 target image + camera (w2c, position) from pinned host memory; per step: loss scalar back'},
         'clocks': clocks,
-        'render_ms_1080p': round(render_ms, 4),
+        'render_ms_1080p' if args.config != 'c3' else 'render_ms': round(render_ms, 4),
     }
     out.update(extra)
     if impl == 'reference':
@@ -428,105 +501,152 @@ def run_gpu(args, impl):
         out['cpu_baseline'] = None
         out['config']['reference'] = 'unmodified FasterGSCudaBackend (baseline/_ref) CUDA path on the same GPU'
     else:
-        out.update(profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use_fused))
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_baseline()
+        out.update(profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, use_fused, fused_loss, step_resident,
+                                opt_obj is not None or dist is not None, vpr))
+        if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline and not args.quick:
+            out['cpu_baseline'] = cpu_baseline(with_c2_estimate=args.config == 'c2')
+    if registered is not None:
+        registered.close()
     if dist is not None:
         dist.destroy_process_group()
     return out if rank == 0 else None
 
 
-def profile_mine(be, params, opt, st_dev, gt_dev, empty, dev, ms_step, rank, use_fused=False):
+def profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, use_fused, fused_loss, step_fn, distributed, vpr):
     """Per-kernel CUDA-event timing of a few extra (untimed) iterations -> roofline of the dominant
     kernel, launch count, scene statistics."""
     from fgs_b200 import _capi
+    n_gauss, width, height = cfg['n'], cfg['w'], cfg['h']
+    t_tiles = math.ceil(width / 16) * math.ceil(height / 12)
     reps = 5
     _capi.profile_enable(True)
     per = {}
     launches = 0
     for it in range(reps):
-        rs = be.RasterizerSettings(*st_dev[it % N_VIEWS])
-        img = be.diff_rasterize_fused(*params, empty, rs, opt) if use_fused else be.diff_rasterize(*params, empty, rs)
-        loss = (img - gt_dev[it % N_VIEWS]).abs().mean()
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
+        step_fn(it)
         recs = _capi.profile_read()
         # kernels per profiled group: a sort = one onesweep kernel per 8-bit digit place (the first-digit histograms
         # are accumulated by the kernels that produce the keys); create_instances = main + large-footprint kernel
-        per_group = {'depth sort': 4, 'tile sort': math.ceil(math.ceil(math.log2(max(T_TILES, 2))) / 8), 'create_instances': 2}
+        per_group = {'depth sort': 4, 'tile sort': math.ceil(math.ceil(math.log2(max(t_tiles, 2))) / 8), 'create_instances': 2}
         launches = sum(per_group.get(name, 1) for name, _ in recs)
+        sums = {}
         for name, ms in recs:
+            sums[name] = sums.get(name, 0.0) + ms
+        for name, ms in sums.items():
             per.setdefault(name, []).append(ms)
     _capi.profile_enable(False)
-    kern = {k: sum(v) / reps for k, v in per.items()}  # ms per iteration per kernel group
+    kern = {k: sum(v) / reps / vpr for k, v in per.items()}  # ms per view per kernel group
     # scene statistics of view 0 (V, I) from the forward state
     from fgs_b200 import _C
-    st = st_dev[0]
     with torch.no_grad():
-        r = _C.forward(*[p.detach() for p in params], *st)
+        r = _C.forward(*[p.detach() for p in params], *st_dev[0])
     I = int(r[5])
-    from fgs_b200 import _capi as cap
     V = None
     try:
         V = int(torch.frombuffer(bytearray(r[1][:8].cpu().numpy().tobytes()), dtype=torch.int32)[0])
     except Exception:
         pass
-    P, T = WIDTH * HEIGHT, math.ceil(WIDTH / 16) * math.ceil(HEIGHT / 12)
-    N = N_GAUSSIANS
+    P, T = width * height, t_tiles
+    N = n_gauss
     alg = algorithmic_bytes(N, V or 0, I, P, T)
     dom = max(kern, key=kern.get)
     peak, peak_src = peak_hbm_gbs()
-    dom_bytes = alg.get(dom, 0)
+    dom_bytes = alg.get(dom + '_fused' if (use_fused and dom == 'preprocess_backward') else dom, alg.get(dom, 0))
     traffic = None
     try:  # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/)
-        traffic = json.loads((ROOT / 'profiles' / 'r1_traffic.json').read_text())['bytes_per_launch'].get(dom)
+        tj = ROOT / 'profiles' / ('r2_traffic.json' if (ROOT / 'profiles' / 'r2_traffic.json').exists() else 'r1_traffic.json')
+        traffic = json.loads(tj.read_text())['bytes_per_launch'].get(dom)
     except Exception:
         pass
     dom_ms = kern[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_bytes = alg['iteration_fused'] if use_fused else alg['iteration']
-    iter_achieved = iter_bytes / (ms_step * 1e-3) / 1e9
-    kernel_ms_sum = sum(kern.values())
-    return {
-        'gpu_launches': launches,
+    iter_achieved = iter_bytes * vpr / (ms_step * 1e-3) / 1e9
+    kernel_ms_sum = sum(kern.values()) * vpr
+    out = {
+        'gpu_launches': launches + (1 if fused_loss else 0) * vpr,
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
                      'frac': round(achieved / peak, 4), 'traffic': traffic, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': dom_bytes, 'ms_per_launch': round(dom_ms, 4),
-                     'share_of_step': round(dom_ms / ms_step, 3),
-                     'note': 'blend kernels are FP32-issue bound, not HBM bound; see DESIGN.md'},
-        'roofline_iteration': {'algorithmic_bytes': iter_bytes, 'achieved': round(iter_achieved, 2),
+                     'share_of_step': round(dom_ms * vpr / ms_step, 3),
+                     'note': 'blend kernels are FP32-issue bound, not HBM bound; see DESIGN.md (issue roofline in profiles/)'},
+        'roofline_iteration': {'algorithmic_bytes': iter_bytes * vpr, 'achieved': round(iter_achieved, 2),
                                'peak': peak, 'unit': 'GB/s', 'frac': round(iter_achieved / peak, 4)},
         'kernels_ms': {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
         'kernels_ms_sum': round(kernel_ms_sum, 4),
         'scene': {'N': N, 'V': V, 'I': I, 'P': P, 'T': T},
     }
+    if distributed:
+        # what the step spends outside the rasterizer's own kernels: loss, gradient exchange + Adam, host gaps
+        out['exposed_outside_rasterizer_ms'] = round(ms_step - kernel_ms_sum, 4)
+    return out
 
 
-def cpu_baseline():
-    """Oracle port timed on the host cores on a BOUNDED, shape-preserving sample of the workload.
-
-    The benchmark scene scales Gaussian size with sqrt(1e6 / N) (fgs_b200/synthetic.py), so
-    N/16 Gaussians rendered at 480x270 (1/16 of the pixels) have the same footprint in pixels, the
-    same instances per Gaussian and the same depth complexity per pixel as the full 1M / 1080p
-    workload: per-Gaussian work and per-pixel work are both 1/16.  Measured: preprocess (+SH) forward
-    and backward on the 62.5k Gaussians, blend forward+backward on a 96x72 window of the 480x270 image,
-    Adam on the full 59 M parameters.  Estimate = 16 * preprocess + 16 * (480*270)/(96*72) * blend + Adam."""
+def cpu_baseline(with_c2_estimate=True):
+    """The oracle port (oracle/torch_oracle.py) timed on the host cores.  SURVEY.md §8(d): the reference has no CPU
+    path (Renderer.py:58-59), so the reported CPU number is the pure-PyTorch oracle on C1 (1 k Gaussians, 128x128:
+    forward + L1 + autograd backward + Adam), NOT extrapolated.  `c2_estimate` is a separate, clearly labelled extra:
+    a bounded shape-preserving sample of the benchmark workload scaled to the full size."""
     from oracle import torch_oracle as O
     from fgs_b200 import synthetic as syn
+    host_cores = os.cpu_count() or 1
     # the oracle is many small vectorised torch ops: beyond ~16 threads the fork/join overhead dominates
     # (measured: 128 threads are 100x slower than 8 on this workload), so at most 16 host threads are used
-    cores = min(os.cpu_count() or 1, 16)
-    torch.set_num_threads(cores)
+    threads = min(host_cores, 16)
+    torch.set_num_threads(threads)
+    t_start = time.perf_counter()
+    sc = syn.make_scene(1000, 0)
+    cam = syn.make_camera(0, 128, 128)
+    s = O.Settings(cam.w2c, cam.position, torch.zeros(3), SH_BASES, 128, 128, cam.focal_x, cam.focal_y,
+                   cam.center_x, cam.center_y, cam.near_plane, cam.far_plane, False)
+    gt = syn.make_target(128, 128)
+    leaves = [p.clone().requires_grad_(True) for p in sc]
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in leaves]
+
+    def c1_iteration(step):
+        out = O.render(*leaves, s)
+        (out.image - gt).abs().mean().backward()
+        with torch.no_grad():
+            for p, (m, v), lr in zip(leaves, state, LRS):
+                O.adam_step(p, p.grad, m, v, step, lr)
+                p.grad = None
+
+    c1_iteration(1)
+    ts = []
+    step = 2
+    while len(ts) < 50 and (time.perf_counter() - t_start < 12.0 or len(ts) < 5):
+        t0 = time.perf_counter()
+        c1_iteration(step)
+        ts.append(time.perf_counter() - t0)
+        step += 1
+    med = sorted(ts)[len(ts) // 2]
+    out = {'value': round(1.0 / med, 4), 'unit': 'iters/s on C1 (1k Gaussians, 128x128)', 'cores': host_cores, 'threads': threads,
+           'kind': 'port',
+           'sample': f'oracle/torch_oracle.py fp32 on configs[0] (1 k Gaussians, 128x128 single view): forward + L1 + autograd '
+                     f'backward + Adam, median of {len(ts)} iterations = {med * 1e3:.1f} ms, not extrapolated; '
+                     f'{host_cores} host cores on this box, {threads} torch threads used'}
+    if with_c2_estimate:
+        out['c2_estimate'] = cpu_c2_estimate(threads)
+    return out
+
+
+def cpu_c2_estimate(threads):
+    """EXTRA (an estimate, not the reported baseline): the benchmark scene scales Gaussian size with sqrt(1e6 / N)
+    (fgs_b200/synthetic.py), so N/16 Gaussians rendered at 480x270 have the same footprint in pixels and the same depth
+    complexity per pixel as the full 1M / 1080p workload.  Measured: preprocess forward+backward on the 62.5k Gaussians,
+    blend forward+backward on a 96x72 window, Adam on the full 59 M parameters; scaled by 16, 16 x pixel ratio, 1."""
+    from oracle import torch_oracle as O
+    from fgs_b200 import synthetic as syn
+    cfg = CONFIGS['c2']
     shrink = 16
-    n, w, h = N_GAUSSIANS // shrink, WIDTH // 4, HEIGHT // 4
+    n, w, h = cfg['n'] // shrink, cfg['w'] // 4, cfg['h'] // 4
     sc = syn.make_scene(n, 0)
     cam = syn.make_camera(0, w, h)
     s = O.Settings(cam.w2c, cam.position, torch.zeros(3), SH_BASES, w, h, cam.focal_x, cam.focal_y,
                    cam.center_x, cam.center_y, cam.near_plane, cam.far_plane, False)
     win = (w // 2 - 48, h // 2 - 36, w // 2 + 48, h // 2 + 36)
     t_start = time.perf_counter()
-    reps = 5  # every part is timed `reps` times, the median counts (the dense oracle's memory bounds the sample size)
+    reps = 3
 
     def median_time(fn):
         ts = []
@@ -536,13 +656,11 @@ def cpu_baseline():
             ts.append(time.perf_counter() - t0)
         return sorted(ts)[len(ts) // 2]
 
-    # (a) preprocess forward + backward alone
     def run_pre():
         leaves = [p.clone().requires_grad_(True) for p in sc]
         pr = O.preprocess(*leaves, s)
         (pr.mean2d.sum() + pr.conic.sum() + pr.opacity.sum() + pr.color.sum()).backward()
     t_pre = median_time(run_pre)
-    # (b) windowed render forward + backward (contains one more preprocess pass)
     gt = syn.make_target(w, h)[:, win[1]:win[3], win[0]:win[2]]
 
     def run_all():
@@ -551,8 +669,7 @@ def cpu_baseline():
         (out.image - gt).abs().mean().backward()
     t_all = median_time(run_all)
     t_blend = max(t_all - t_pre, 0.0)
-    # (c) Adam on the full-size parameter set
-    full = [torch.zeros(N_GAUSSIANS, k) for k in (3, 3, 4, 1, 3, 45)]
+    full = [torch.zeros(cfg['n'], k) for k in (3, 3, 4, 1, 3, 45)]
     state = [(torch.ones_like(p), torch.zeros_like(p), torch.zeros_like(p)) for p in full]
 
     def run_adam():
@@ -562,21 +679,102 @@ def cpu_baseline():
     t_adam = median_time(run_adam)
     ratio = (w * h) / ((win[2] - win[0]) * (win[3] - win[1]))
     est = shrink * t_pre + shrink * ratio * t_blend + t_adam
-    return {'value': round(1.0 / est, 6), 'unit': 'iters/s', 'cores': cores, 'kind': 'port',
-            'sample': f'oracle/torch_oracle.py fp32, shape-preserving 1/{shrink} sample: {n} Gaussians at {w}x{h}; '
-                      f'preprocess fwd+bwd {t_pre:.1f} s (x{shrink}), blend fwd+bwd on a 96x72 window {t_blend:.1f} s '
-                      f'(x{shrink * ratio:.0f}), Adam on 59M params {t_adam:.1f} s (medians of {reps}); measured '
-                      f'{time.perf_counter() - t_start:.0f} s of CPU work, estimated {est:.0f} s per full iteration'}
+    return {'iters_per_s': round(1.0 / est, 6), 'kind': 'ESTIMATE (scaled bounded sample; not the reported baseline)',
+            'sample': f'1/{shrink} shape-preserving sample: {n} Gaussians at {w}x{h}; preprocess fwd+bwd {t_pre:.1f} s (x{shrink}), '
+                      f'blend fwd+bwd on a 96x72 window {t_blend:.1f} s (x{shrink * ratio:.0f}), Adam on 59M params {t_adam:.1f} s '
+                      f'(medians of {reps}); {time.perf_counter() - t_start:.0f} s of CPU work, estimated {est:.0f} s per iteration'}
 
 
 def run_cpu_port(args, reason):
-    cb = cpu_baseline()
-    return {'metric': METRIC, 'value': cb['value'], 'unit': 'iters/s', 'n_gpus': 0, 'steps': 1, 'warmup': 0,
+    cb = cpu_baseline(with_c2_estimate=False)
+    return {'metric': CONFIGS[args.config]['metric'], 'value': cb['value'], 'unit': 'iters/s', 'n_gpus': 0, 'steps': 1, 'warmup': 0,
             'ms_per_step': round(1000.0 / cb['value'], 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': 'configs[1] (bounded sample, see cpu_baseline.sample)', 'note': reason},
+            'config': {'workload': 'configs[0] (C1: the CPU oracle port; the reference has no CPU path)', 'note': reason},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def run_fourd(args):
+    """configs[4]: FasterGS4D shape.  One step = time slice + forward + L1 + backward + Adam on the seven 4D tensors at a
+    random time stamp; render ms = inference over the 150 time steps.  THIS repo only (the reference's FasterGS4D branch
+    is not in the tree)."""
+    import fgs_b200
+    from fgs_b200 import fourd as F4, loss as loss_mod, synthetic as syn
+    from tests.test_widen_fourd import make_scene_4d
+    cfg = CONFIGS['c5']
+    dev = torch.device('cuda', 0)
+    n, w, h, n_t = cfg['n'], cfg['w'], cfg['h'], 150
+    params = [p.to(dev).requires_grad_(True) for p in make_scene_4d(n, 0, w)]
+    lrs4 = [1.6e-4, 5e-3, 1e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]
+    opt = fgs_b200.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, lrs4)], lr=0.0, eps=1e-15)
+    cams = [syn.make_camera(k, w, h) for k in range(N_VIEWS)]
+    bg = torch.zeros(3, device=dev)
+    rs = [fgs_b200.RasterizerSettings(*settings_tuple(c, dev, bg)) for c in cams]
+    targets8 = [(syn.make_target(w, h, seed=k) * 255.0).round().clamp(0, 255).to(torch.uint8) for k in range(N_VIEWS)]
+    gt8 = [t.to(dev) for t in targets8]
+    gt_pin = [t.pin_memory() for t in targets8]
+    times = [i / (n_t - 1) for i in range(n_t)]
+    empty = torch.empty(0)
+
+    def step(i, gt):
+        img = F4.diff_rasterize_4d(*params, times[(37 * i) % n_t], empty, rs[i % N_VIEWS])
+        terms, g = loss_mod.l1_dssim_loss_and_grad(img.detach(), gt, 1.0, 0.0)
+        img.backward(g)
+        opt.step()
+        opt.zero_grad()
+        return terms[0]
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_step = timed(lambda i: step(i, gt8[i % N_VIEWS]), steps, warmup)
+    stage = [torch.empty_like(gt8[0]) for _ in range(2)]
+    loss_pin = torch.zeros(1).pin_memory()
+
+    def step_e2e(i):
+        b = stage[i % 2]
+        b.copy_(gt_pin[i % N_VIEWS], non_blocking=True)
+        loss = step(i, b)
+        loss_pin.copy_(loss.reshape(1), non_blocking=True)
+    ms_e2e = timed(step_e2e, steps, warmup)
+    with torch.no_grad():
+        det = [p.detach() for p in params]
+        ms_render = timed(lambda i: F4.rasterize_4d(*det, times[i % n_t], rs[i % N_VIEWS], to_chw=True), n_t, 10)
+    t_end = time.time() + 3.0
+    while len(sampler.lines) < 5 and time.time() < t_end:
+        for i in range(20):
+            step(i, gt8[i % N_VIEWS])
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    peak, peak_src = peak_hbm_gbs()
+    # algorithmic bytes of the 4D iteration: the 3D iteration on the sliced Gaussians (unfused: SURVEY §8d) with the slice
+    # forward (25 floats in, 10 out per Gaussian) and backward (25 + 10 in, 25 out) and Adam on 4+4+4+4+1+3+45 floats
+    adam_floats = 4 + 4 + 4 + 4 + 1 + 3 + 45
+    return {'metric': cfg['metric'], 'value': round(1000.0 / ms_step, 3), 'unit': 'iters/s', 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': round(ms_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': cfg['workload'] + '; slice + fwd + fused L1 + bwd + FusedAdam.step on the seven 4D tensors, random time stamp',
+                       'n_gaussians': n, 'width': w, 'height': h, 'time_steps': n_t,
+                       'reference': 'none: the FasterGS4D branch is not in /root/reference (parity unpinned, oracle/fourd_oracle.py)',
+                       'l2_policy': f'inputs_larger_than_L2 (params+moments+grads = {adam_floats * 16 * n // 1_000_000} MB per step vs 126 MB L2)'},
+            'e2e': {'value': round(1000.0 / ms_e2e, 3), 'unit': 'iters/s', 'h2d_bytes_per_step': 3 * w * h, 'd2h_bytes_per_step': 4},
+            'render_ms_per_timestep': round(ms_render, 4), 'clocks': clocks, 'gpu_launches': 22,
+            'roofline': {'bound': 'hbm', 'kernel': 'whole iteration (no per-kernel split for the 4D path)',
+                         'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None, 'peak_source': peak_src},
+            'cpu_baseline': None}
 
 
 def main():
@@ -585,26 +783,45 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='mine', choices=['mine', 'reference'])
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS), help='c2 = BASELINE.json configs[1] (headline), c3 = configs[2], c5 = configs[4]')
+    ap.add_argument('--batch', type=int, default=0,
+                    help='views per optimizer step over the whole job (configs[3]: --batch 8 --gpus 1/2/4/8, strong scaling); '
+                         'default: one view per rank (weak scaling)')
+    ap.add_argument('--dp-mode', default='auto', choices=DP_MODES,
+                    help='N > 1: how gradients are summed and Adam applied.  peer-mc / peer = one kernel over NVLS multicast / '
+                         'NVLink peer memory (fgs_b200.parallel.PeerAdam); sharded = NCCL reduce-scatter + Adam on 1/W + '
+                         'all-gather; allreduce / flat / pipelined = NCCL all-reduce (six / one / six pipelined with Adam) + dense Adam')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='experiments only: resident timing + kernel profile, no e2e / drop-in / render / CPU legs')
     ap.add_argument('--unfused', action='store_true', help='headline on the drop-in path (backward, then FusedAdam.step)')
-    ap.add_argument('--fused-loss', action='store_true',
-                    help='EXPERIMENTAL (not yet measured on hardware): L1 loss and its gradient from csrc/loss.cu instead '
-                         'of the seven torch kernels of (img - gt).abs().mean() + backward')
+    ap.add_argument('--torch-loss', action='store_true', help='loss with torch ops ((img - gt).abs().mean()) instead of the fused loss kernel')
+    ap.add_argument('--yaml-loss', action='store_true',
+                    help='the loss fastergs_garden.yaml trains with (0.8 L1 + 0.2 DSSIM, Loss.py:15-16) and a live densification_info')
     ap.add_argument('--overlap-adam', action='store_true',
-                    help='EXPERIMENTAL (not yet measured on hardware): fused path with the zero-gradient Adam of invisible '
-                         'Gaussians\' sh_rest rows on a side stream under the blend backward (fgs_debug_set_overlap_adam)')
-    ap.add_argument('--flat-allreduce', action='store_true',
-                    help='N > 1 only, EXPERIMENTAL: the backward writes the six gradients into one flat buffer and ONE NCCL '
-                         'all-reduce sums it (fgs_b200.parallel.FlatGradients) instead of six collectives')
-    ap.add_argument('--peer-adam', action='store_true',
-                    help='N > 1 only, EXPERIMENTAL: gradient reduction + Adam + parameter broadcast in one kernel over '
-                         'NVLink peer memory (fgs_b200.parallel.PeerAdam) instead of NCCL all-reduce + FusedAdam.step')
+                    help='MEASURED SLOWER (profiles/r2_results.md), kept for reference: zero-gradient Adam of invisible rows on a '
+                         'side stream under the blend backward')
+    # round-1 spellings
+    ap.add_argument('--fused-loss', action='store_true', help='(default now; kept for compatibility)')
+    ap.add_argument('--flat-allreduce', action='store_true', help='= --dp-mode flat')
+    ap.add_argument('--peer-adam', action='store_true', help='= --dp-mode peer')
     args = ap.parse_args()
+    if args.flat_allreduce:
+        args.dp_mode = 'flat'
+    if args.peer_adam:
+        args.dp_mode = 'peer'
     if not torch.cuda.is_available():
         if args.impl == 'reference':
             print(json.dumps(run_cpu_port(args, 'no CUDA device')))
             return
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    if args.config == 'c5':
+        if int(os.environ.get('RANK', 0)) != 0:
+            return
+        if args.impl == 'reference':
+            print(json.dumps({'impl': 'reference', 'unavailable': 'configs[4]: the FasterGS4D branch is not in /root/reference'}))
+            return
+        print(json.dumps(run_fourd(args)))
+        return
     out = run_gpu(args, args.impl)
     if out is not None:
         print(json.dumps(out))

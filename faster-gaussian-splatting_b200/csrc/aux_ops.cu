@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kAuxBlock) add_noise_kernel(const float* __res
     means[3 * (size_t)i + 2] += f * (R31 * t1 + R32 * t2 + R33 * t3);
 }
 
-bool g_reloc_ready = false;
+PerDevice<bool> g_reloc_ready;  // the __constant__ table is per device
 
 }  // namespace
 
@@ -121,7 +121,7 @@ cudaError_t launch_update_3d_filter(const float* positions, const float* w2c, fl
 cudaError_t launch_relocation(const float* old_opacities, const float* old_scales, const long long* n_samples,
                               float* new_opacities, float* new_scales, int n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    if (!g_reloc_ready) {
+    if (!g_reloc_ready.here()) {
         static float table[kMaxSamples * kMaxSamples];
         for (int m = 0; m < kMaxSamples; ++m) {
             double binom = 1.0, sign = 1.0;
@@ -132,7 +132,7 @@ cudaError_t launch_relocation(const float* old_opacities, const float* old_scale
         }
         cudaError_t e = cudaMemcpyToSymbolAsync(c_reloc, table, sizeof(table), 0, cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) return e;
-        g_reloc_ready = true;
+        g_reloc_ready.here() = true;
     }
     FGS_LAUNCH_SERIAL(relocation_kernel, div_up(n, kAuxBlock), kAuxBlock, stream, old_opacities, old_scales, n_samples, new_opacities,
                                                                     new_scales, n);

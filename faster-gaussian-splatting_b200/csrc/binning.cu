@@ -180,7 +180,8 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
     FGS_LAUNCH(create_instances_kernel<KeyT>, div_up(n_max, kInstBlock), kInstBlock, stream,
         sorted_idx, offsets, sorted_info, inst_keys, inst_vals, n_vis_dev, grid_w, key_hist, mask, big_count, big_prims,
         big_offsets, (uint32_t)capacity);
-    static int s_sms = 0;
+    static PerDevice<int> s_sms_dev;
+    int& s_sms = s_sms_dev.here();
     if (s_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);

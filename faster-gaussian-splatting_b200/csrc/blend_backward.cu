@@ -302,9 +302,10 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
 
 template <bool kScores>
 static cudaError_t launch_blend_backward_t(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream) {
-    static int s_grid = 0;
+    static PerDevice<int> s_grid_dev;
+    int& s_grid = s_grid_dev.here();
     const size_t smem = sizeof(WarpSmem) * kWarps;
-    if (s_grid == 0) {
+    if (s_grid == 0) {  // function attributes are per device too
         cudaError_t e = cudaFuncSetAttribute(blend_backward_kernel<kScores>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(blend_backward_kernel<kScores>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);

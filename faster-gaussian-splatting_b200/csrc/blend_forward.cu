@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
 
 cudaError_t launch_blend_forward(const BlendFwdArgs& a, const Cam& cam, cudaStream_t stream) {
     if (a.n_tiles <= 0) return cudaSuccess;
-    static int s_grid_train = 0, s_grid_inf = 0;
-    int& grid = a.training ? s_grid_train : s_grid_inf;
+    static PerDevice<int> s_grid_train, s_grid_inf;
+    int& grid = a.training ? s_grid_train.here() : s_grid_inf.here();
     if (grid == 0) {
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/fgs_b200.h"
 #include "fgs_device.cuh"
@@ -203,18 +204,22 @@ Cam make_cam(const fgs_settings& s, const float* w2c, const float* cam_position,
     return c;
 }
 
-// pinned read-back slot, side stream and events, created once per process.  The 8-byte copy of (V, I) runs
-// on its own stream so that the launching stream goes from preprocess straight into the depth sort (a copy
-// queued between two kernels of one stream costs a hand-over to the copy engine and back).
+// pinned read-back slot, side stream and events, created once PER DEVICE (streams and events belong to the device
+// that was current when they were created).  The 8-byte copy of (V, I) runs on its own stream so that the launching
+// stream goes from preprocess straight into the depth sort (a copy queued between two kernels of one stream costs a
+// hand-over to the copy engine and back).  `lock` serialises the host-side launch sequences of one device: the slot,
+// the side stream and the capacity hints of a device are used by one forward / backward at a time, whichever host
+// thread or stream it comes from (calls on different devices do not contend).
 struct Readback {
     uint32_t* host = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t counted = nullptr;  // preprocess done (launching stream)
     cudaEvent_t event = nullptr;    // copy done (side stream)
+    std::mutex lock;
 };
 Readback& readback() {
-    static Readback rb;
-    return rb;
+    static Readback rb[kMaxDevices];
+    return rb[device_slot()];
 }
 cudaError_t ensure_readback() {
     Readback& rb = readback();
@@ -231,9 +236,38 @@ cudaError_t ensure_readback() {
 // Instance-buffer capacity the next forward is launched with before its own instance count has come back
 // from the device (0: none yet).  Sizing speculatively keeps the host ahead of the GPU: the one read-back of
 // (V, I) is then only *checked* after everything has been queued, instead of stalling the launch sequence
-// between the offsets scan and create_instances.  Process-wide, single-threaded host use (like the reference's
-// function-local static stream, forward.cu:47-53).
-int g_capacity_hint = 0;
+// between the offsets scan and create_instances.  Kept per device AND per shape class (tile count x training/inference):
+// a process that alternates a 1080p training view with a 4K evaluation view, or drives two GPUs, keeps one hint for each
+// instead of thrashing a single one.  A small direct-mapped table; a collision only costs the cold path once.
+struct CapacityHints {
+    static constexpr int kEntries = 8;
+    struct Entry {
+        int n_tiles = 0, n_primitives = 0, capacity = 0;
+        bool training = false;
+    } e[kEntries];
+    int forced = -1;  // fgs_debug_set_capacity_hint: overrides the table for the next forward (tests)
+    Entry& entry(int n_tiles, bool training) { return e[((unsigned)n_tiles * 2u + (training ? 1u : 0u)) % kEntries]; }
+    int get(int n_tiles, int n_primitives, bool training) {
+        if (forced >= 0) return forced;
+        const Entry& x = entry(n_tiles, training);
+        // a different scene size is a different workload: start cold rather than with a stale size
+        return (x.n_tiles == n_tiles && x.training == training && x.n_primitives == n_primitives) ? x.capacity : 0;
+    }
+    void put(int n_tiles, int n_primitives, bool training, int capacity) {
+        Entry& x = entry(n_tiles, training);
+        x.n_tiles = n_tiles;
+        x.n_primitives = n_primitives;
+        x.training = training;
+        x.capacity = capacity;
+        forced = -1;
+        last = capacity;
+    }
+    int last = 0;  // most recent suggestion on this device (fgs_debug_get_capacity_hint)
+};
+CapacityHints& capacity_hints() {
+    static CapacityHints h[kMaxDevices];
+    return h[device_slot()];
+}
 
 // Opt-in overlapped schedule of the fused backward + Adam (see backward_impl); FGS_OVERLAP_ADAM=1 in the environment or
 // fgs_debug_set_overlap_adam(1).  Off by default until it has been measured on hardware.
@@ -318,6 +352,9 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     const int end_bit = bits_for(n_tiles - 1);
     if (cam.grid_w >= kMaxGridDim || cam.grid_h >= kMaxGridDim) return fail_arg("fgs_forward: image larger than 4095 tiles per side");
     FGS_TRY(ensure_readback(), "readback alloc");
+    Readback& rb = readback();
+    std::lock_guard<std::mutex> device_lock(rb.lock);
+    CapacityHints& hints = capacity_hints();
 
     TileLayout tsz(nullptr, n_tiles, n_pixels, training);
     char* tile_blob = resize(user_tile, tsz.bytes);
@@ -336,7 +373,6 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_info, pl.keys[0],
                               pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream, rotations ? nullptr : scales),
             "preprocess");
-    Readback& rb = readback();
     FGS_TRY(cudaEventRecord(rb.counted, stream), "event record");
     FGS_TRY(cudaStreamWaitEvent(rb.stream, rb.counted, 0), "read-back stream wait");
     FGS_TRY(cudaMemcpyAsync(rb.host, pl.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, rb.stream), "count read-back");
@@ -356,7 +392,8 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // Launch the rest with the capacity the previous forward suggested, and only then look at this forward's
     // own count (the read-back has long completed by then).  No suggestion yet: wait for the count first.
     const bool keys16 = end_bit <= 16;
-    int capacity = g_capacity_hint;
+    const int hinted = hints.get(n_tiles, n, training);
+    int capacity = hinted;
     if (capacity > 0) {
         const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
                                           image, training, to_chw, clamp_output, stream);
@@ -381,7 +418,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
                                           image, training, to_chw, clamp_output, stream);
         if (rc != 0) return rc;
     }
-    g_capacity_hint = next_capacity_hint(n_instances, g_capacity_hint);
+    hints.put(n_tiles, n, training, next_capacity_hint(n_instances, hinted));
     if (state_out) {
         state_out->n_instances = n_instances;
         state_out->n_buckets = 0;
@@ -415,9 +452,11 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
     // traffic that depends on nothing the blend backward produces -- runs on the side stream while the issue-bound blend
     // backward leaves the memory system idle; the preprocess backward then skips those rows.
     const bool overlap = g_overlap_adam && state->n_instances > 0 && preprocess_backward_can_overlap(pa, cam);
+    std::unique_lock<std::mutex> device_lock;
     if (overlap) {
         FGS_TRY(ensure_readback(), "side stream");
         Readback& rb = readback();
+        device_lock = std::unique_lock<std::mutex>(rb.lock);
         FGS_TRY(cudaEventRecord(rb.counted, stream), "event record (overlap)");
         FGS_TRY(cudaStreamWaitEvent(rb.stream, rb.counted, 0), "side stream wait (overlap)");
         FGS_TRY(launch_adam_rest_invisible(pa, cam, rb.stream), "adam_rest_invisible");
@@ -644,8 +683,8 @@ int fgs_add_noise(const float* raw_scales, const float* raw_rotations, const flo
 void fgs_debug_set_overlap_adam(int32_t on) { g_overlap_adam = on != 0; }
 int32_t fgs_debug_get_overlap_adam(void) { return g_overlap_adam ? 1 : 0; }
 
-void fgs_debug_set_capacity_hint(int32_t capacity) { g_capacity_hint = capacity > 0 ? capacity : 0; }
-int32_t fgs_debug_get_capacity_hint(void) { return g_capacity_hint; }
+void fgs_debug_set_capacity_hint(int32_t capacity) { capacity_hints().forced = capacity > 0 ? capacity : 0; }
+int32_t fgs_debug_get_capacity_hint(void) { return capacity_hints().last; }
 
 void fgs_profile_enable(int32_t on) {
     prof().enabled = on != 0;

@@ -29,6 +29,21 @@ constexpr int kSortItems = FGS_SORT_ITEMS;
 constexpr int kSortTile = kSortBlock * kSortItems;  // keys per block per pass
 constexpr int kRadixMax = 256;
 
+// Host-side caches (occupancy-derived grids, one-time function attributes, side streams, capacity hints) are kept PER
+// DEVICE: a process may drive several GPUs (one rasterizer call at a time per device; calls on different devices may come
+// from different host threads).  `here()` is the slot of the calling thread's current device.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d % kMaxDevices;
+}
+template <typename T>
+struct PerDevice {
+    T slot[kMaxDevices] = {};
+    T& here() { return slot[device_slot()]; }
+};
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 

@@ -49,6 +49,12 @@ struct PeerAdamArgs {
     float beta1, beta2, eps;
     int world, rank;
     uint32_t total;         // sum of count[]
+    // NVLS variant (fgs_peer_adam_step_multicast): multicast addresses of the two flat buffers.  A load from grads_mc
+    // with multimem.ld_reduce returns the sum over all W replicas, formed inside the NVSwitch; a multimem.st to
+    // params_mc lands in all W replicas.  Per GPU and step: W-1 fewer gradient slices come in over NVLink, and the
+    // new parameters leave once instead of W-1 times.
+    const float4* grads_mc;
+    float4* params_mc;
 };
 
 __device__ __forceinline__ float4 ld_peer(const float4* p) {  // L2-only (the data is rewritten by its owner every step)
@@ -62,6 +68,47 @@ __device__ __forceinline__ void adam1(float g, float& p, float& m, float& v, flo
     v = fmaf(beta2, v - g2, g2);
     p -= step_size * m / (sqrtf(v) * b2 + eps);
 }
+
+#ifndef FGS_CUDA_EMU
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(mc)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// Same slices, same Adam, reduction and broadcast done by the switch (one load + one store per float4 instead of W + W).
+__global__ void __launch_bounds__(kPeerBlock) peer_adam_multicast_kernel(const PeerAdamArgs a) {
+    for (uint32_t idx = blockIdx.x * kPeerBlock + threadIdx.x; idx < a.total; idx += gridDim.x * kPeerBlock) {
+        uint32_t j = idx;
+        int t = 0;
+        while (t < 5 && j >= a.count[t]) {
+            j -= a.count[t];
+            ++t;
+        }
+        const size_t e = (size_t)a.begin[t] + j;
+        const float4 s = multimem_ld_reduce_add(a.grads_mc + e);
+        float4 p = a.params[a.rank][e];
+        float4 m = a.exp_avg[a.shard_off[t] + j];
+        float4 v = a.exp_avg_sq[a.shard_off[t] + j];
+        const float ss = a.step_size[t], b2 = a.b2[t];
+        adam1(s.x, p.x, m.x, v.x, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.y, p.y, m.y, v.y, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.z, p.z, m.z, v.z, ss, a.beta1, a.beta2, a.eps, b2);
+        adam1(s.w, p.w, m.w, v.w, ss, a.beta1, a.beta2, a.eps, b2);
+        a.exp_avg[a.shard_off[t] + j] = m;
+        a.exp_avg_sq[a.shard_off[t] + j] = v;
+        multimem_st(a.params_mc + e, p);
+    }
+}
+#endif
 
 __global__ void __launch_bounds__(kPeerBlock) peer_adam_kernel(const PeerAdamArgs a) {
     for (uint32_t idx = blockIdx.x * kPeerBlock + threadIdx.x; idx < a.total; idx += gridDim.x * kPeerBlock) {
@@ -152,10 +199,11 @@ int fgs_peer_adam_slice(const uint64_t counts[6], int32_t world, int32_t rank, u
     return 0;
 }
 
-int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
-                       float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
-                       const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
-                       double eps, void* stream) {
+static int peer_adam_step_impl(const float* const* peer_grads, float* const* peer_params, const float* grads_mc,
+                               float* params_mc, bool multicast, int32_t world, int32_t rank, float* exp_avg_shard,
+                               float* exp_avg_sq_shard, const uint64_t offsets[6], const uint64_t counts[6],
+                               const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
+                               void* stream) {
     auto fail = [](const char* msg) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
         return -1;
@@ -164,7 +212,15 @@ int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params
         return fail("fgs_peer_adam_step: NULL argument");
     if (world < 1 || world > FGS_MAX_PEERS || rank < 0 || rank >= world) return fail("fgs_peer_adam_step: bad world/rank");
     PeerAdamArgs a{};
+    if (multicast) {
+        if (!grads_mc || !params_mc) return fail("fgs_peer_adam_step_multicast: NULL multicast address (NVLS not available?)");
+        if ((reinterpret_cast<uintptr_t>(grads_mc) | reinterpret_cast<uintptr_t>(params_mc)) & 15u)
+            return fail("fgs_peer_adam_step_multicast: multicast addresses must be 16-byte aligned");
+        a.grads_mc = reinterpret_cast<const float4*>(grads_mc);
+        a.params_mc = reinterpret_cast<float4*>(params_mc);
+    }
     for (int q = 0; q < world; ++q) {
+        if (multicast && q != rank) continue;  // only the rank's own parameter replica is read directly
         if (!peer_grads[q] || !peer_params[q]) return fail("fgs_peer_adam_step: NULL peer pointer");
         if ((reinterpret_cast<uintptr_t>(peer_grads[q]) | reinterpret_cast<uintptr_t>(peer_params[q])) & 15u)
             return fail("fgs_peer_adam_step: peer buffers must be 16-byte aligned");
@@ -195,9 +251,14 @@ int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params
     a.eps = (float)eps;
     a.world = world;
     a.rank = rank;
+    // the grid-stride index is 32-bit: leave room for one full stride past the end so that it cannot wrap
+    if (total > 0xffffffffull - (1ull << 26)) return fail("fgs_peer_adam_step: more than 2^32 float4s per rank");
     a.total = (uint32_t)total;
     if (total == 0) return 0;
-    static int s_grid = 0;
+    static int s_grid_dev[64] = {};  // per device (fgs_host.h is not included here: this file stands alone for the emulator)
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0) cur_dev = 0;
+    int& s_grid = s_grid_dev[cur_dev % 64];
     if (s_grid == 0) {
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);
@@ -207,14 +268,53 @@ int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params
     }
     const uint64_t want = (total + kPeerBlock - 1) / kPeerBlock;
     const int grid = want < (uint64_t)s_grid ? (int)want : s_grid;
-    auto k = peer_adam_kernel;
-    FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+#ifndef FGS_CUDA_EMU
+    if (multicast) {
+        auto km = peer_adam_multicast_kernel;
+        FGS_LAUNCH_SERIAL(km, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+    } else
+#endif
+    {
+        auto k = peer_adam_kernel;
+        FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step: %s", cudaGetErrorString(e));
         return (int)e;
     }
     return 0;
+}
+
+int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                       float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
+                       const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
+                       double eps, void* stream) {
+    return peer_adam_step_impl(peer_grads, peer_params, nullptr, nullptr, false, world, rank, exp_avg_shard,
+                               exp_avg_sq_shard, offsets, counts, step, lr, beta1, beta2, eps, stream);
+}
+
+int fgs_peer_adam_step_multicast(const float* grads_multicast, float* params_multicast, float* local_params,
+                                 int32_t world, int32_t rank, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                 const uint64_t offsets[6], const uint64_t counts[6], const int32_t step[6],
+                                 const double lr[6], double beta1, double beta2, double eps, void* stream) {
+#ifdef FGS_CUDA_EMU
+    (void)grads_multicast; (void)params_multicast; (void)local_params; (void)world; (void)rank; (void)exp_avg_shard;
+    (void)exp_avg_sq_shard; (void)offsets; (void)counts; (void)step; (void)lr; (void)beta1; (void)beta2; (void)eps; (void)stream;
+    std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step_multicast: not available on the emulator");
+    return -1;
+#else
+    if (world < 1 || world > FGS_MAX_PEERS || rank < 0 || rank >= world) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step_multicast: bad world/rank");
+        return -1;
+    }
+    const float* g[FGS_MAX_PEERS] = {};
+    float* p[FGS_MAX_PEERS] = {};
+    g[rank] = reinterpret_cast<const float*>(local_params);  // placeholder (unused by the multicast kernel), non-NULL
+    p[rank] = local_params;
+    return peer_adam_step_impl(g, p, grads_multicast, params_multicast, true, world, rank, exp_avg_shard, exp_avg_sq_shard,
+                               offsets, counts, step, lr, beta1, beta2, eps, stream);
+#endif
 }
 
 }  // extern "C"

@@ -199,6 +199,14 @@ __global__ void __launch_bounds__(128, 16) adam_rest_invisible_kernel(const uint
     }
 }
 
+// Loads of the PARAMETER tensors.  In fused mode (fgs_backward_adam) means / scales / rotations / opacities / sh_rest are
+// the very tensors this launch updates in place (emit_span), so they must not go through the read-only data cache
+// (ld.global.nc is only defined for memory that stays constant for the whole launch): plain ld.global.
+template <typename T>
+__device__ __forceinline__ T ld_param(const T* p) {
+    return *p;
+}
+
 // kSkipInvisibleRest: the sh_rest rows of invisible Gaussians have already been updated by adam_rest_invisible_kernel
 // (fused mode only); everything else is identical.
 // kCov3d: covariance-input mode (see preprocess.cu): a.scales holds (N,6) covariances, a.g_scales receives their (N,6)
@@ -227,9 +235,9 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         const int nf = rows * rest_floats;
         if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (nf & 3) == 0) {
             for (int i = lane; i < (nf >> 2); i += 32)
-                reinterpret_cast<float4*>(rest)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+                reinterpret_cast<float4*>(rest)[i] = ld_param(reinterpret_cast<const float4*>(src) + i);
         } else {
-            for (int i = lane; i < nf; i += 32) rest[i] = __ldg(src + i);
+            for (int i = lane; i < nf; i += 32) rest[i] = ld_param(src + i);
         }
     }
     __syncwarp();
@@ -244,8 +252,8 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         const float4 g1 = __ldg(&gp->g1);
         const float g2x = __ldg(&gp->g2.x);
         const float3 dcol = make_float3(g1.z, g1.w, g2x);
-        const float3 mean = make_float3(__ldg(a.means + 3 * (size_t)idx), __ldg(a.means + 3 * (size_t)idx + 1),
-                                        __ldg(a.means + 3 * (size_t)idx + 2));
+        const float3 mean = make_float3(ld_param(a.means + 3 * (size_t)idx), ld_param(a.means + 3 * (size_t)idx + 1),
+                                        ld_param(a.means + 3 * (size_t)idx + 2));
 
         // ---- SH backward (sh_utils.cuh:71-155) ----
         gsh0[0] = C0 * dcol.x;
@@ -311,10 +319,10 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         const float x = (W[0] * mean.x + W[1] * mean.y + W[2] * mean.z + W[3]) * inv_z;
         const float y = (W[4] * mean.x + W[5] * mean.y + W[6] * mean.z + W[7]) * inv_z;
         const float3 var = kCov3d ? make_float3(1.f, 1.f, 1.f)
-                                  : make_float3(__expf(2.0f * __ldg(a.scales + 3 * (size_t)idx)),
-                                                __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 1)),
-                                                __expf(2.0f * __ldg(a.scales + 3 * (size_t)idx + 2)));
-        const float4 q = kCov3d ? make_float4(1.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+                                  : make_float3(__expf(2.0f * ld_param(a.scales + 3 * (size_t)idx)),
+                                                __expf(2.0f * ld_param(a.scales + 3 * (size_t)idx + 1)),
+                                                __expf(2.0f * ld_param(a.scales + 3 * (size_t)idx + 2)));
+        const float4 q = kCov3d ? make_float4(1.f, 0.f, 0.f, 0.f) : ld_param(reinterpret_cast<const float4*>(a.rotations) + idx);
         const float qxx = q.y * q.y, qyy = q.z * q.z, qzz = q.w * q.w;
         const float qxy = q.y * q.z, qxz = q.y * q.w, qyz = q.z * q.w;
         const float qrx = q.x * q.y, qry = q.x * q.z, qrz = q.x * q.w;
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
         // ---- opacity ----
         gop = g1.y;
         if (cam.proper_aa) {
-            const float o = sigmoidf_(__ldg(a.opacities + idx));
+            const float o = sigmoidf_(ld_param(a.opacities + idx));
             const float factor = sqrtf(fmaxf((a_raw * c_raw - cb * cb) * inv_det, 0.0f));
             gop = g1.y * factor * o * (1.0f - o);  // coverage factor detached from cov2d
         }
@@ -545,7 +553,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const float* __restrict__ gra
 
 cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, bool skip_invisible_rest) {
     if (a.n <= 0) return cudaSuccess;
-    static bool s_attr = false;
+    static PerDevice<bool> s_attr_dev;
+    bool& s_attr = s_attr_dev.here();
     const size_t smem = (size_t)kWarps * kWarpFloats * sizeof(float);
     if (!s_attr) {
         auto k00 = preprocess_backward_kernel<false, false>;
@@ -573,7 +582,8 @@ bool preprocess_backward_can_overlap(const PreBwdArgs& a, const Cam& cam) {
 
 cudaError_t launch_adam_rest_invisible(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream) {
     if (!preprocess_backward_can_overlap(a, cam)) return cudaSuccess;
-    static int s_sms = 0;
+    static PerDevice<int> s_sms_dev;
+    int& s_sms = s_sms_dev.here();
     if (s_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);

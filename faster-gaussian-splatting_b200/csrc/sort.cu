@@ -475,7 +475,8 @@ cudaError_t radix_sort_pairs(KeyT* keys, KeyT* keys_alt, uint32_t* vals, uint32_
     if (n_max <= 0) return cudaSuccess;
     const PassPlan plan = make_plan(end_bit);
     const int tiles = div_up(n_max, kSortTile);
-    static int s_wave = 0;  // blocks of onesweep_kernel<KeyT> one wave holds
+    static PerDevice<int> s_wave_dev;  // blocks of onesweep_kernel<KeyT> one wave holds
+    int& s_wave = s_wave_dev.here();
     if (s_wave == 0) {
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);

@@ -18,16 +18,43 @@ from . import _capi
 _lib = _capi.load()
 
 # ---- scratch management: the C ABI grows caller-owned buffers through callbacks ----------------
+# Every call that needs scratch opens its own context (device + the buffers handed out so far); the `user` word the
+# library passes back to the callback is (context id << 2 | which buffer), so calls on different devices or from different
+# host threads never see each other's buffers (ctypes releases the GIL while the library runs).
 _PRIMITIVE, _TILE, _INSTANCE = 1, 2, 3
-_current: dict[int, torch.Tensor] = {}
-_current_device = None
+_contexts: dict[int, '_Scratch'] = {}
+_next_context = [1]
+
+
+class _Scratch:
+    def __init__(self, device):
+        self.device = device
+        self.buffers: dict[int, torch.Tensor] = {}
+        self.key = _next_context[0]
+        _next_context[0] += 1
+
+    def __enter__(self):
+        _contexts[self.key] = self
+        return self
+
+    def __exit__(self, *exc):
+        _contexts.pop(self.key, None)
+        return False
+
+    def user(self, which: int) -> int:
+        return (self.key << 2) | which
+
+    def take(self, which: int):
+        return self.buffers.pop(which, None)
 
 
 def _resize(user, nbytes):
-    if int(nbytes) == 0 and int(user) in _current:  # query: the buffer handed out for this user last time
-        return _current[int(user)].data_ptr()
-    t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_current_device)
-    _current[int(user)] = t
+    ctx = _contexts[int(user) >> 2]
+    which = int(user) & 3
+    if int(nbytes) == 0 and which in ctx.buffers:  # query: the buffer handed out for this user last time
+        return ctx.buffers[which].data_ptr()
+    t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=ctx.device)
+    ctx.buffers[which] = t
     return t.data_ptr()
 
 
@@ -64,7 +91,6 @@ def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficie
             proper_antialiasing):
     """rasterization_api.h:8-28.  Returns (image, primitive_buffers, tile_buffers, instance_buffers,
     bucket_buffers, n_instances, n_buckets, selector); the buffers are opaque."""
-    global _current_device
     for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
         _check_param(t, name)
@@ -77,14 +103,14 @@ def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficie
         st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
                        far_plane, proper_antialiasing)
         state = _capi.ForwardState()
-        _current_device = dev
-        _current.clear()
-        rc = _lib.fgs_forward(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales), _ptr(rotations),
-                              _ptr(opacities), _ptr(sh_coefficients_0), _ptr(sh_coefficients_rest), _ptr(w2c_c),
-                              _ptr(pos_c), _ptr(bg_c), _ptr(image), n, C.byref(st), _stream(), C.byref(state))
-        _capi.check(rc, 'forward')
+        with _Scratch(dev) as ctx:
+            rc = _lib.fgs_forward(_resize_cb, ctx.user(_PRIMITIVE), ctx.user(_TILE), ctx.user(_INSTANCE), _ptr(means),
+                                  _ptr(scales), _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
+                                  _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image), n,
+                                  C.byref(st), _stream(), C.byref(state))
+            _capi.check(rc, 'forward')
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
-        prim, tile, inst = (_current.pop(k, empty) for k in (_PRIMITIVE, _TILE, _INSTANCE))
+        prim, tile, inst = (ctx.buffers.get(k, empty) for k in (_PRIMITIVE, _TILE, _INSTANCE))
     return image, prim, tile, inst, empty, state.n_instances, state.n_buckets, state.selector
 
 
@@ -192,7 +218,6 @@ def inference(means, scales, rotations, opacities, sh_coefficients_0, sh_coeffic
               bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
               proper_antialiasing, to_chw, clamp_output):
     """rasterization_api.h:61-83."""
-    global _current_device
     for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
         _check_param(t, name)
@@ -205,15 +230,13 @@ def inference(means, scales, rotations, opacities, sh_coefficients_0, sh_coeffic
         w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
         st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
                        far_plane, proper_antialiasing)
-        _current_device = dev
-        _current.clear()
-        rc = _lib.fgs_inference(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales), _ptr(rotations),
-                                _ptr(opacities), _ptr(sh_coefficients_0), _ptr(sh_coefficients_rest), _ptr(w2c_c),
-                                _ptr(pos_c), _ptr(bg_c), _ptr(image), n, C.byref(st), int(bool(to_chw)),
-                                int(bool(clamp_output)), _stream())
-        _capi.check(rc, 'inference')
-        # scratch must outlive the enqueued kernels: the caching allocator keeps it stream-ordered
-        _current.clear()
+        with _Scratch(dev) as ctx:
+            rc = _lib.fgs_inference(_resize_cb, ctx.user(_PRIMITIVE), ctx.user(_TILE), ctx.user(_INSTANCE), _ptr(means),
+                                    _ptr(scales), _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
+                                    _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image), n,
+                                    C.byref(st), int(bool(to_chw)), int(bool(clamp_output)), _stream())
+            _capi.check(rc, 'inference')
+        # the scratch tensors die here; the caching allocator keeps their memory stream-ordered behind the kernels
     return image
 
 
@@ -275,7 +298,6 @@ def pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_
                    cam_position, bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y,
                    near_plane, far_plane, proper_antialiasing) -> None:
     """rasterization_api.h:85-106: accumulates this view's Speedy-Splat pruning scores into `scores` (n,)."""
-    global _current_device
     for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest'),
                     (scores, 'scores')):
@@ -288,11 +310,9 @@ def pruning_scores(scores, means, scales, rotations, opacities, sh_coefficients_
         w2c_c, pos_c, bg_c = _aux(w2c, dev), _aux(cam_position, dev), _aux(bg_color, dev)
         st = _settings(active_sh_bases, total_rest, width, height, focal_x, focal_y, center_x, center_y, near_plane,
                        far_plane, proper_antialiasing)
-        _current_device = dev
-        _current.clear()
-        rc = _lib.fgs_pruning_scores(_resize_cb, _PRIMITIVE, _TILE, _INSTANCE, _ptr(means), _ptr(scales),
-                                     _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
-                                     _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image),
-                                     _ptr(scores), n, C.byref(st), _stream())
-        _capi.check(rc, 'pruning_scores')
-        _current.clear()
+        with _Scratch(dev) as ctx:
+            rc = _lib.fgs_pruning_scores(_resize_cb, ctx.user(_PRIMITIVE), ctx.user(_TILE), ctx.user(_INSTANCE),
+                                         _ptr(means), _ptr(scales), _ptr(rotations), _ptr(opacities),
+                                         _ptr(sh_coefficients_0), _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c),
+                                         _ptr(bg_c), _ptr(image), _ptr(scores), n, C.byref(st), _stream())
+            _capi.check(rc, 'pruning_scores')

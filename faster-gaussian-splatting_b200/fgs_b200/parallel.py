@@ -164,7 +164,10 @@ class PeerAdam:
     rasterizer's backward writes its gradients straight into the symmetric gradient buffer."""
 
     def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
-                 group=None) -> None:
+                 group=None, multicast: bool | str = 'auto') -> None:
+        """`multicast`: True = reduce and broadcast inside the NVSwitch through the buffers' multicast addresses
+        (multimem.ld_reduce / multimem.st, fgs_peer_adam_step_multicast), False = W peer loads / stores per element,
+        'auto' = multicast when the symmetric-memory handles expose a multicast address."""
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -196,6 +199,12 @@ class PeerAdam:
         self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=dev)
         self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in self._gh.buffer_ptrs])
         self._pptrs = (C.c_void_p * self.world)(*[int(p) for p in self._ph.buffer_ptrs])
+        g_mc, p_mc = int(getattr(self._gh, 'multicast_ptr', 0) or 0), int(getattr(self._ph, 'multicast_ptr', 0) or 0)
+        if multicast == 'auto':
+            multicast = g_mc != 0 and p_mc != 0
+        if multicast and not (g_mc and p_mc):
+            raise RuntimeError('PeerAdam(multicast=True): the symmetric-memory handles have no multicast address (no NVLS)')
+        self.multicast, self._g_mc, self._p_mc = bool(multicast), g_mc, p_mc
         _C.set_gradient_outputs(self.grads)
         self._ph.barrier()  # every replica initialised before anyone steps
 
@@ -209,11 +218,13 @@ class PeerAdam:
         self.steps += 1
         stream = self._capi.current_stream()
         self._gh.barrier()  # stream-ordered: every rank's gradients are complete
-        rc = self._lib.fgs_peer_adam_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
-                                          self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),
-                                          (C.c_uint64 * 6)(*self.counts), (C.c_int32 * 6)(*[self.steps] * 6),
-                                          (C.c_double * 6)(*self.lrs), float(self.betas[0]), float(self.betas[1]),
-                                          self.eps, stream)
+        tail = (self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),
+                (C.c_uint64 * 6)(*self.counts), (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
+                float(self.betas[0]), float(self.betas[1]), self.eps, stream)
+        if self.multicast:
+            rc = self._lib.fgs_peer_adam_step_multicast(self._g_mc, self._p_mc, self._pbuf.data_ptr(), self.world, self.rank, *tail)
+        else:
+            rc = self._lib.fgs_peer_adam_step(self._gptrs, self._pptrs, self.world, self.rank, *tail)
         if rc != 0:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
         self._ph.barrier()  # every rank's parameter stores have landed before the next forward reads them
@@ -230,3 +241,84 @@ class PeerAdam:
 
     def close(self) -> None:
         self._C.set_gradient_outputs(None)
+
+
+class ShardedAdam:
+    """The same step with NCCL collectives instead of peer memory: reduce-scatter of the flat gradient buffer, dense
+    Adam on this rank's 1/W of every tensor (moments sharded), all-gather of the flat parameter buffer.  Same wire bytes
+    as one all-reduce, Adam's HBM traffic / W; the fallback where symmetric memory is not available, and the yardstick
+    PeerAdam is measured against (bench.py --sharded-adam).
+
+        opt = ShardedAdam(initial_parameter_tensors, lrs)
+        img = diff_rasterize(*opt.params, dens, settings); loss(img).backward(); opt.step(); opt.zero_grad()
+    """
+
+    def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
+                 group=None, adam_fn=None, register: bool = True) -> None:
+        """`adam_fn(grad, param, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps)` replaces the library's Adam kernel and
+        `register=False` leaves the rasterizer's gradient outputs alone (both for the CPU tests over gloo)."""
+        import torch.distributed as dist
+        self.group = group
+        self._C = None
+        if adam_fn is None or register:
+            from . import _C
+            self._C = _C
+        self._adam = adam_fn if adam_fn is not None else self._C.adam_step
+        self._registered = False
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = tensors[0].device
+        self.shapes = [tuple(t.shape) for t in tensors]
+        self.offsets, self.counts, total = peer_layout(self.shapes)
+        self.chunk = (total + 4 * self.world - 1) // (4 * self.world) * 4  # floats per rank, multiple of 4
+        padded = self.chunk * self.world
+        self.lrs, self.betas, self.eps, self.steps = [float(x) for x in lrs], betas, float(eps), 0
+        self._pbuf = torch.zeros(padded, dtype=torch.float32, device=dev)
+        self._gbuf = torch.zeros(padded, dtype=torch.float32, device=dev)
+        view = lambda buf, i: buf[self.offsets[i]:self.offsets[i] + self.counts[i]].view(self.shapes[i])
+        with torch.no_grad():
+            for i, t in enumerate(tensors):
+                view(self._pbuf, i).copy_(t)
+        self.params = [view(self._pbuf, i).requires_grad_(True) for i in range(6)]
+        self.grads = [view(self._gbuf, i) for i in range(6)]
+        lo, hi = self.rank * self.chunk, (self.rank + 1) * self.chunk
+        self._gshard = torch.zeros(self.chunk, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(self.chunk, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.chunk, dtype=torch.float32, device=dev)
+        # pieces of this rank's chunk, one per tensor it intersects: (shard offset, length, lr)
+        self._pieces = []
+        for o, c, lr in zip(self.offsets, self.counts, self.lrs):
+            a, b = max(lo, o), min(hi, o + c)
+            if b > a:
+                self._pieces.append((a - lo, b - a, lr))
+        if register:
+            self._C.set_gradient_outputs(self.grads)
+            self._registered = True
+
+    def step(self) -> None:
+        import torch.distributed as dist
+        for p, g in zip(self.params, self.grads):
+            if p.grad is None:
+                raise RuntimeError('ShardedAdam.step: parameter without gradient (every rank must render a view)')
+            if p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+        self.steps += 1
+        dist.reduce_scatter_tensor(self._gshard, self._gbuf, op=dist.ReduceOp.SUM, group=self.group)
+        pshard = self._pbuf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+        for off, n, lr in self._pieces:
+            self._adam(self._gshard[off:off + n], pshard[off:off + n], self.exp_avg[off:off + n],
+                       self.exp_avg_sq[off:off + n], self.steps, lr, self.betas[0], self.betas[1], self.eps)
+        dist.all_gather_into_tensor(self._pbuf, pshard, group=self.group)
+
+    def zero_grad(self) -> None:
+        for p in self.params:
+            p.grad = None
+
+    def reset(self) -> None:
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.steps = 0
+
+    def close(self) -> None:
+        if self._registered:
+            self._C.set_gradient_outputs(None)
+            self._registered = False

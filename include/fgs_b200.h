@@ -260,6 +260,15 @@ int fgs_peer_adam_step(const float* const* peer_grads, float* const* peer_params
                        float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
                        const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1,
                        double beta2, double eps, void* stream);
+/* NVLS variant of fgs_peer_adam_step: `grads_multicast` / `params_multicast` are the MULTICAST addresses of the two flat
+ * buffers (torch.distributed._symmetric_memory: handle.multicast_ptr; CUDA: cuMulticastCreate / cuMulticastBindMem).  The
+ * gradient sum over all W replicas is formed inside the NVSwitch (multimem.ld_reduce.add.f32), the updated parameters are
+ * stored once and replicated by the switch (multimem.st); `local_params` is this rank's own replica of the parameter
+ * buffer (read directly).  Same slicing, same sharded moments, same barriers around the call. */
+int fgs_peer_adam_step_multicast(const float* grads_multicast, float* params_multicast, float* local_params, int32_t world,
+                                 int32_t rank, float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
+                                 const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1,
+                                 double beta2, double eps, void* stream);
 size_t fgs_peer_adam_shard_floats(const uint64_t counts[6], int32_t world);
 /* rank's slice of every tensor: first float (relative to the tensor), number of floats (padding included),
  * position of the slice's moments inside the shard arrays; any output pointer may be NULL */

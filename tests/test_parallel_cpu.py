@@ -185,3 +185,51 @@ def test_flat_gradients_single_allreduce_equals_six():
         assert torch.equal(da, db) and float(da[0, 0]) == 3.0
     for a, b in zip(out[0][0], out[1][0]):
         assert torch.equal(a, b), 'ranks diverged'
+
+
+def _worker_sharded(rank, world, port, out_dict):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from fgs_b200 import parallel
+    from oracle import torch_oracle as O
+    shapes = [(37, 3), (37, 3), (37, 4), (37, 1), (37, 1, 3), (37, 15, 3)]  # 37: tensor regions with padding
+    lrs = [1e-2, 2e-2, 3e-2, 4e-2, 5e-2, 6e-2]
+    torch.manual_seed(0)
+    init = [torch.randn(s) for s in shapes]
+
+    def grad_of(r, step, i):
+        return torch.randn(shapes[i], generator=torch.Generator().manual_seed(1000 * step + 10 * r + i))
+
+    def oracle_adam(g, p, m, v, step, lr, b1, b2, eps):
+        with torch.no_grad():
+            O.adam_step(p, g, m, v, step, lr, b1, b2, eps)
+
+    opt = parallel.ShardedAdam(init, lrs, adam_fn=oracle_adam, register=False)
+    # yardstick: all-reduce (sum) + dense Adam on every rank
+    dense = [t.clone() for t in init]
+    state = [(torch.zeros_like(t), torch.zeros_like(t)) for t in init]
+    for step in (1, 2, 3):
+        for i, p in enumerate(opt.params):
+            p.grad = grad_of(rank, step, i)
+        opt.step()
+        opt.zero_grad()
+        for i, (p, (m, v)) in enumerate(zip(dense, state)):
+            g = sum(grad_of(r, step, i) for r in range(world))
+            O.adam_step(p, g, m, v, step, lrs[i])
+    out_dict[rank] = ([p.detach().clone() for p in opt.params], dense)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_adam_equals_allreduce_then_dense_adam():
+    """reduce-scatter -> Adam on 1/W of the flat buffer -> all-gather == all-reduce -> dense Adam (gloo, 2 ranks)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_sharded, args=(2, _free_port(), out), nprocs=2, join=True)
+    for rank in range(2):
+        got, want = out[rank]
+        for a, b in zip(got, want):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b)  # replicas identical
