@@ -267,7 +267,22 @@ def run_gpu(args, impl):
         loss.backward()
         return loss
 
+    dp_events = []  # (start, end) CUDA events around the end of the step while profile_mine runs
+
     def finish_step():
+        if dp_events is not None and dp_probe['on']:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            finish_step_inner()
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            dp_events.append((e0, e1))
+        else:
+            finish_step_inner()
+
+    dp_probe = {'on': False}
+
+    def finish_step_inner():
         if dist is not None and opt_obj is None:
             if dp_mode == 'flat':
                 flat.allreduce(params)
@@ -501,8 +516,15 @@ def run_gpu(args, impl):
         out['cpu_baseline'] = None
         out['config']['reference'] = 'unmodified FasterGSCudaBackend (baseline/_ref) CUDA path on the same GPU'
     else:
+        dp_probe['on'] = True
         out.update(profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, use_fused, fused_loss, step_resident,
                                 opt_obj is not None or dist is not None, vpr))
+        dp_probe['on'] = False
+        torch.cuda.synchronize()
+        if dp_events and (dist is not None or vpr > 1):
+            # GPU time from the end of the last backward to the end of the optimizer step (waiting for the slowest rank at
+            # the barrier included): gradient exchange + Adam + parameter broadcast
+            out['step_end_ms'] = round(sum(a.elapsed_time(b) for a, b in dp_events) / len(dp_events), 4)
         if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline and not args.quick:
             out['cpu_baseline'] = cpu_baseline(with_c2_estimate=args.config == 'c2')
     if registered is not None:

@@ -171,6 +171,10 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
     }
     int i2 = grab();
     uint32_t k = 0;
+    FGS_STAT_DECL(st_pairs);
+    FGS_STAT_DECL(st_useful);
+    FGS_STAT_DECL(st_flushes);
+    FGS_STAT_DECL(st_slots);
 
     for (;;) {
         const int item = i1;
@@ -257,6 +261,8 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                 const float c_b = recs[jj].q2.x;
                 const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                 const bool c = alpha >= kMinAlpha && jj < n_rel;
+                FGS_STAT_ADD(st_pairs, lane == 0);
+                FGS_STAT_ADD(st_useful, c);
                 const float ae = c ? alpha : 0.0f;
                 const float w = __fmul_rn(T, ae);
                 const float cg = fmaf(c_b, gb, fmaf(q1.w, gg, q1.z * gr));  // c . g
@@ -280,6 +286,8 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                     if (lane < 3)
                         reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[jj])[lane];
                     if (++nslots == kSlots) {
+                        FGS_STAT_ADD(st_flushes, lane == 0);
+                        FGS_STAT_ADD(st_slots, lane == 0 ? kSlots : 0);
                         if (kScores) flush_scores(ws, nslots, lane, a.scores);
                         else flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
                         nslots = 0;
@@ -292,10 +300,16 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
         }
         k += (uint32_t)nb;
         if (nslots > 0) {
+            FGS_STAT_ADD(st_flushes, lane == 0);
+            FGS_STAT_ADD(st_slots, lane == 0 ? nslots : 0);
             if (kScores) flush_scores(ws, nslots, lane, a.scores);
             else flush_slots(ws, nslots, lane, fx0 + 0.5f, fy0 + 0.5f, cam.proper_aa != 0, a.grad2d);
         }
     }
+    FGS_STAT_FLUSH(4, st_pairs);
+    FGS_STAT_FLUSH(5, st_useful);
+    FGS_STAT_FLUSH(6, st_flushes);
+    FGS_STAT_FLUSH(7, st_slots);
 }
 
 }  // namespace

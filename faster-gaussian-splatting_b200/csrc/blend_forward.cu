@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
     uint2 r1 = i1 < n_items ? __ldg(a.tile_ranges + i1 / kBlendWarps) : make_uint2(0u, 0u);
     int i2 = grab();
     uint32_t k = 0;  // batches issued by this warp so far: slot = k % kRing, parity = (k / kRing) & 1
+    FGS_STAT_DECL(st_pairs);
+    FGS_STAT_DECL(st_useful);
+    FGS_STAT_DECL(st_batches);
+    FGS_STAT_DECL(st_empty);
+    FGS_STAT_DECL(st_live);
 
     for (;;) {
         const int item = i1;
@@ -114,6 +119,8 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                 // sub-tile culling was done once at gather time (binning.cu): bit `sub` of the record's mask
                 const bool hit = lane < count && ((__float_as_uint(recs[lane].q2.y) >> sub) & 1u) != 0u;
                 uint32_t pending = __ballot_sync(0xffffffffu, hit);
+                FGS_STAT_ADD(st_batches, lane == 0);
+                FGS_STAT_ADD(st_empty, lane == 0 && pending == 0u);
                 int last_jj = -1;  // this pixel's last contributor inside the batch
                 while (pending) {
                     const int jj = __ffs((int)pending) - 1;
@@ -123,6 +130,9 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                     const float colb = recs[jj].q2.x;
                     const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                     const bool c = alpha >= thr;
+                    FGS_STAT_ADD(st_pairs, lane == 0);
+                    FGS_STAT_ADD(st_useful, c);
+                    FGS_STAT_ADD(st_live, thr != kDone);
                     const float ae = c ? alpha : 0.0f;  // alpha_eff = 0 leaves the pixel untouched
                     const float w = __fmul_rn(T, ae);
                     cr = fmaf(w, q1.z, cr);
@@ -174,6 +184,11 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
             if (lane == 0) a.tile_max_n[item] = wmax;  // per item: exactly one writer
         }
     }
+    FGS_STAT_FLUSH(0, st_pairs);
+    FGS_STAT_FLUSH(1, st_useful);
+    FGS_STAT_FLUSH(2, st_batches);
+    FGS_STAT_FLUSH(3, st_empty);
+    FGS_STAT_FLUSH(8, st_live);
 }
 
 }  // namespace

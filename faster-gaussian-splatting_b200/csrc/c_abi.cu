@@ -263,6 +263,7 @@ struct CapacityHints {
         last = capacity;
     }
     int last = 0;  // most recent suggestion on this device (fgs_debug_get_capacity_hint)
+    int reruns = 0;  // forwards whose speculative tail had to be queued again (fgs_debug_get_forward_reruns)
 };
 CapacityHints& capacity_hints() {
     static CapacityHints h[kMaxDevices];
@@ -275,6 +276,19 @@ bool g_overlap_adam = [] {
     const char* e = std::getenv("FGS_OVERLAP_ADAM");
     return e != nullptr && e[0] == '1';
 }();
+
+// instrumentation build only: device counters of the blend kernels (fgs_device.cuh, FGS_BLEND_STATS)
+unsigned long long* blend_stats_buffer() {
+#ifdef FGS_BLEND_STATS
+    static PerDevice<unsigned long long*> buf;
+    unsigned long long*& p = buf.here();
+    if (!p && cudaMalloc(reinterpret_cast<void**>(&p), 16 * sizeof(unsigned long long)) == cudaSuccess)
+        cudaMemset(p, 0, 16 * sizeof(unsigned long long));
+    return p;
+#else
+    return nullptr;
+#endif
+}
 
 int next_capacity_hint(int n_instances, int current) {
     // grow with 25 % head-room, shrink only when more than half of the buffer is unused: sizes stay stable
@@ -321,6 +335,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
     a.n_processed = tl.n_processed;
     a.tile_max_n = tl.tile_max_n;
     a.queue = pl.counters + kCtrTileQueue;
+    a.stats = blend_stats_buffer();
     a.n_tiles = n_tiles;
     a.training = training;
     a.to_chw = to_chw;
@@ -405,6 +420,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     if (n_instances < 0) return fail_arg("fgs_forward: more than 2^31 instances");
     if (capacity == 0 || n_instances > capacity) {
         if (capacity > 0) {
+            ++hints.reruns;
             // the speculative pass ran out of room: create_instances skipped every write that did not fit and
             // the stages behind it saw an empty instance list (bounded_count), so nothing was overrun and nothing
             // uninitialised was read.  Reset what it consumed -- blend queues, sort tickets, work-list length,
@@ -475,6 +491,7 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
         ba.tile_max_n = tl.tile_max_n;
         ba.grad2d = grad2d;
         ba.queue = pl.counters + kCtrTileQueueBwd;
+        ba.stats = blend_stats_buffer();
         ba.n_tiles = n_tiles;
         FGS_KERNEL(launch_blend_backward(ba, cam, stream), "blend_backward");
     }
@@ -685,6 +702,16 @@ int32_t fgs_debug_get_overlap_adam(void) { return g_overlap_adam ? 1 : 0; }
 
 void fgs_debug_set_capacity_hint(int32_t capacity) { capacity_hints().forced = capacity > 0 ? capacity : 0; }
 int32_t fgs_debug_get_capacity_hint(void) { return capacity_hints().last; }
+int32_t fgs_debug_get_forward_reruns(void) { return capacity_hints().reruns; }
+
+int fgs_debug_blend_stats(uint64_t out[16], int32_t reset) {
+    unsigned long long* p = blend_stats_buffer();
+    if (!p) return fail_arg("fgs_debug_blend_stats: the library was not built with -DFGS_BLEND_STATS=1");
+    FGS_TRY(cudaDeviceSynchronize(), "blend stats sync");
+    if (out) FGS_TRY(cudaMemcpy(out, p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "blend stats copy");
+    if (reset) FGS_TRY(cudaMemset(p, 0, 16 * sizeof(unsigned long long)), "blend stats reset");
+    return 0;
+}
 
 void fgs_profile_enable(int32_t on) {
     prof().enabled = on != 0;

@@ -270,6 +270,27 @@ __device__ __forceinline__ float blend_alpha(float A2, float B2, float C2, float
     return exp2f(fminf(la, lop));
 }
 
+// ---- optional instrumentation of the blend kernels (build with -DFGS_BLEND_STATS=1; never in the product build) -------
+// Counters for the issue roofline (profiles/blend_stats.py): how many (Gaussian, sub-tile) pairs the inner loops execute
+// and how many of their 32 lanes do useful work.
+//  [0] fwd pairs   [1] fwd lanes with alpha >= threshold (blended)   [2] fwd batches consumed   [3] fwd batches without a hit
+//  [4] bwd pairs   [5] bwd lanes that contribute                     [6] bwd flushes            [7] bwd slots flushed
+//  [8] fwd lanes inside the image and not yet done when the pair was evaluated
+#ifdef FGS_BLEND_STATS
+#define FGS_STAT_DECL(name) unsigned int name = 0
+#define FGS_STAT_ADD(name, v) name += (unsigned int)(v)
+#define FGS_STAT_FLUSH(idx, name)                                                        \
+    do {                                                                                 \
+        const unsigned int tot_ = __reduce_add_sync(0xffffffffu, name);                 \
+        if ((threadIdx.x & 31) == 0 && tot_ && a.stats) atomicAdd(&a.stats[idx], (unsigned long long)tot_); \
+        name = 0;                                                                        \
+    } while (0)
+#else
+#define FGS_STAT_DECL(name)
+#define FGS_STAT_ADD(name, v)
+#define FGS_STAT_FLUSH(idx, name)
+#endif
+
 // mbarrier wait with explicit back-off: a warp that finds the phase incomplete sleeps instead of
 // re-issuing try_wait back to back (measured: the bare spin loop took ~15 % of all issue slots of the
 // blend kernels away from the warps that had work)

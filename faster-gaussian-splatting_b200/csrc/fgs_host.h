@@ -104,6 +104,7 @@ struct BlendFwdArgs {
     uint32_t* n_processed;    // per pixel, training only
     uint32_t* tile_max_n;     // per tile, training only
     uint32_t* queue;          // tile queue counter
+    unsigned long long* stats;  // instrumentation build only (-DFGS_BLEND_STATS), else unused
     int n_tiles;
     bool training;
     bool to_chw;
@@ -122,6 +123,7 @@ struct BlendBwdArgs {
     Grad2D* grad2d;           // indexed by primitive index, zeroed by the caller
     float* scores;            // non-null: accumulate Speedy-Splat pruning scores instead of gradients
     uint32_t* queue;
+    unsigned long long* stats;  // instrumentation build only (-DFGS_BLEND_STATS), else unused
     int n_tiles;
 };
 cudaError_t launch_blend_backward(const BlendBwdArgs& a, const Cam& cam, cudaStream_t stream);

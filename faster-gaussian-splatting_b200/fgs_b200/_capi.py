@@ -101,6 +101,8 @@ SIGNATURES = {
     'fgs_debug_get_overlap_adam': (C.c_int32, []),
     'fgs_debug_set_capacity_hint': (None, [C.c_int32]),
     'fgs_debug_get_capacity_hint': (C.c_int32, []),
+    'fgs_debug_get_forward_reruns': (C.c_int32, []),
+    'fgs_debug_blend_stats': (C.c_int, [C.POINTER(C.c_uint64), C.c_int32]),
     'fgs_profile_enable': (None, [C.c_int32]),
     'fgs_profile_read': (C.c_int, [C.c_char_p, C.c_size_t]),
     'fgs_sort_pairs_u32': (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t,

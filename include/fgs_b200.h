@@ -287,6 +287,11 @@ int fgs_profile_read(char* out, size_t out_bytes);
  * the re-run path (a tiny hint) or the cold path (0). */
 void fgs_debug_set_capacity_hint(int32_t capacity);
 int32_t fgs_debug_get_capacity_hint(void);
+/* number of forwards on the current device whose speculative tail did not fit and was queued a second time */
+int32_t fgs_debug_get_forward_reruns(void);
+/* instrumentation builds (-DFGS_BLEND_STATS=1) only: the blend kernels' pair / useful-lane counters (layout in
+ * csrc/fgs_device.cuh); returns -1 in the product build */
+int fgs_debug_blend_stats(uint64_t out[16], int32_t reset);
 
 /* EXPERIMENTAL schedule of fgs_backward_adam (default off; also FGS_OVERLAP_ADAM=1 in the environment): the
  * zero-gradient Adam update of the sh_rest rows of Gaussians that were not visible runs on a private side stream

@@ -146,7 +146,10 @@ def main():
     cam = syn.make_camera(0, 480, 270)
     st = util.settings_for(cam, device='cuda')
     gi = syn.make_grad_image(480, 270).cuda() / (3 * 480 * 270)
-    summary['mid'] = case(ref, fgs_b200, sc, st, gi, 'mid: 50 k Gaussians, 480x270, window oracle', window=(192, 96, 288, 168))
+    win = (192, 96, 288, 168)
+    giw = torch.zeros_like(gi)
+    giw[:, win[1]:win[3], win[0]:win[2]] = gi[:, win[1]:win[3], win[0]:win[2]]
+    summary['mid'] = case(ref, fgs_b200, sc, st, giw, 'mid: 50 k Gaussians, 480x270, loss restricted to a 96x72 window (fp64 oracle on that window)', window=win)
     # ---- C2 -------------------------------------------------------------------------------------------------------
     n, w, h = 1_000_000, 1920, 1080
     sc = syn.make_scene(n, 0).to('cuda')

@@ -1,11 +1,13 @@
 """GPU parity tests: the hand-written sm_100a path (through the C ABI) against the CPU oracle, the
 committed golden fixtures and -- when baseline/_ref travelled to the box -- the compiled reference.
 
-Tolerances (BASELINE.json north_star): images <= 1e-4 mean-L1; gradients rtol 1e-3.  The reference
+Tolerances (BASELINE.json north_star): images <= 1e-4 mean-L1; gradients 1e-3.  The reference
 is built with -use_fast_math and accumulates with float atomics, so single elements can flip at the
-alpha >= 1/255 / T < 1e-4 thresholds; gradient tensors are therefore compared in aggregate
-(|a-b|_1/|b|_1 <= 1e-3 against the fp64 oracle would be too strict for fast-math on either side, see
-the tolerances printed by test_reference_vs_oracle_sets_the_scale) and never by max error.
+alpha >= 1/255 / T < 1e-4 thresholds; gradient tensors are therefore compared per tensor in aggregate
+(|a-b|_1/|b|_1 <= GRAD_RTOL = 1e-3, north_star's number) and never by max error.  The floor measured on the
+B200 (profiles/r2_parity.md, tests/test_parity_r2_gpu.py::test_reference_vs_oracle_sets_the_scale) is two orders of
+magnitude below that: <= 2e-5 against the compiled reference and against the fp64 oracle at C1 and at C2, which is
+also where the reference itself sits against the oracle; GRAD_FLOOR = 2e-4 is asserted wherever that was measured.
 """
 import math
 
@@ -17,6 +19,8 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 C1 = dict(n=1000, w=128, h=128)
+GRAD_RTOL = 1e-3   # north_star
+GRAD_FLOOR = 2e-4  # 10x the worst value measured on hardware (profiles/r2_parity.md)
 
 
 def _scene(n, w, h, seed=0, device='cuda', sigma=None):
@@ -119,7 +123,7 @@ def test_forward_backward_vs_oracle_c1(cuda_device, bases):
     assert l1 <= 1e-4, f'image mean-L1 {l1}'
     for name, g, og in zip(NAMES, grads, ograds):
         e, c = util.rel_err(g.cpu(), og), util.cos_sim(g.cpu(), og)
-        assert e <= 5e-3 and c >= 0.9999, f'{name}: rel {e} cos {c}'
+        assert e <= GRAD_FLOOR and c >= 0.9999, f'{name}: rel {e} cos {c}'
         # invisible Gaussians: exactly zero rows
         inv = ~out.proj.visible
         assert float(g.cpu()[inv].abs().sum()) == 0.0, name
@@ -134,7 +138,7 @@ def test_antialiasing_vs_oracle_c1(cuda_device):
     out, ograds = _oracle(sc, st, gi)
     assert (img.cpu().double() - out.image).abs().mean().item() <= 1e-4
     for name, g, og in zip(NAMES, grads, ograds):
-        assert util.rel_err(g.cpu(), og) <= 5e-3, name
+        assert util.rel_err(g.cpu(), og) <= GRAD_FLOOR, name
 
 
 def test_densification_info_matches_oracle(cuda_device):
@@ -147,7 +151,7 @@ def test_densification_info_matches_oracle(cuda_device):
     odens = torch.ones(2, C1['n'], dtype=torch.float64)
     _oracle(sc, st, gi, densification_info=odens)
     assert torch.equal(dens[0].cpu().double(), odens[0])
-    assert util.rel_err(dens[1].cpu(), odens[1]) <= 2e-3
+    assert util.rel_err(dens[1].cpu(), odens[1]) <= GRAD_FLOOR
 
 
 def test_inference_matches_training_forward(cuda_device):
@@ -311,7 +315,7 @@ def test_vs_compiled_reference_c1(cuda_device):
         assert round(O.psnr(img.clamp(0, 1), rimg.clamp(0, 1)), 2) >= 60.0
         for name, g, rg in zip(NAMES, grads, rgrads):
             e = util.rel_err(g, rg)
-            assert e <= 5e-3, f'{name} (aa={aa}): rel {e}'
+            assert e <= GRAD_FLOOR, f'{name} (aa={aa}): rel {e}'
 
 
 def test_full_size_vs_reference_and_properties(cuda_device):
@@ -350,7 +354,7 @@ def test_full_size_vs_reference_and_properties(cuda_device):
         assert l1 <= 1e-4, f'image mean-L1 vs reference {l1}'
         for name, g, rg in zip(NAMES, grads0, rgrads):
             e = util.rel_err(g, rg)
-            assert e <= 5e-3, f'{name}: rel {e}'
+            assert e <= GRAD_FLOOR, f'{name}: rel {e} (north_star {GRAD_RTOL})'
 
 
 def test_c3_shape_fused_vs_reference(cuda_device):
@@ -384,6 +388,6 @@ def test_c3_shape_fused_vs_reference(cuda_device):
     l1 = (img - rimg).abs().mean().item()
     assert l1 <= 1e-4, f'image mean-L1 {l1}'
     for name, p0, a, b, m_a, m_b in zip(NAMES, sc, pa, pb, ma, mb):
-        assert util.rel_err(m_a, m_b) <= 5e-3, f'{name}: first moment rel {util.rel_err(m_a, m_b)}'
+        assert util.rel_err(m_a, m_b) <= GRAD_FLOOR, f'{name}: first moment rel {util.rel_err(m_a, m_b)}'  # m1 = (1 - beta1) g: linear in the gradient
         assert util.cos_sim(a - p0, b - p0) >= 0.999, f'{name}: update direction'
         assert util.rel_err(a - p0, b - p0) <= 2e-2, f'{name}: update rel {util.rel_err(a - p0, b - p0)}'

@@ -6,9 +6,11 @@ What is compared (BASELINE.json: "PSNR vs ref"): the PSNR reached after the same
   * this repo's drop-in path vs the compiled reference backend (baseline/_ref), same loop, same torch L1 loss;
   * the fused backward+Adam path vs the drop-in path;
   * the fused loss kernel (csrc/loss.cu) vs torch's L1;
-and that a run with L1 + DSSIM, densification and reordering in the loop stays healthy.  PSNRs are compared to 0.25 dB,
-not to 2 decimals: float atomics make every run of either backend slightly different, and 200 Adam steps amplify that
-(the measured values are printed; tighten once they are known -- this file was written without access to a GPU)."""
+and that a run with L1 + DSSIM, densification and reordering in the loop stays healthy.  north_star asks for "PSNR equal
+to 2 dp": measured on the B200 (round 2) all four runs -- drop-in, fused backward+Adam, fused loss kernel, compiled
+reference -- reach 37.46 dB.  Float atomics make every run of either backend slightly different and 200 Adam steps carry
+that along, so the test measures the reference's own run-to-run spread (two runs) and asserts
+|PSNR difference| <= PSNR_TOL + 3 x spread, with PSNR_TOL = 0.01 dB (= 2 dp)."""
 import math
 
 import pytest
@@ -19,6 +21,7 @@ from tests import util
 NAMES = ('means', 'scales', 'rotations', 'opacities', 'sh_coefficients_0', 'sh_coefficients_rest')
 LRS = dict(means=1.6e-4, scales=5e-3, rotations=1e-3, opacities=2.5e-2, sh_coefficients_0=2.5e-3, sh_coefficients_rest=1.25e-4)
 N, W, H, VIEWS, ITERS = 6000, 192, 144, 4, 200
+PSNR_TOL = 0.01  # dB: north_star's "equal to 2 dp"
 
 
 def _problem(device):
@@ -88,13 +91,17 @@ def test_training_psnr_parity(cuda_device):
                    settings, targets)
     print(f'PSNR initial {psnr0:.2f} dB; drop-in {p_drop:.2f}, fused backward+Adam {p_fused:.2f}, fused L1 kernel {p_loss:.2f}')
     assert p_drop >= psnr0 + 1.0, (psnr0, p_drop)  # the loop trains
-    assert abs(p_fused - p_drop) <= 0.25, (p_fused, p_drop)
-    assert abs(p_loss - p_drop) <= 0.25, (p_loss, p_drop)
     ref = util.load_reference()
+    spread = 0.0
     if ref is not None:
         p_ref = _psnr(fgs_b200, _train(ref, init, settings, targets), settings, targets)
-        print(f'PSNR reference backend {p_ref:.2f} dB')
-        assert abs(p_ref - p_drop) <= 0.25, (p_ref, p_drop)
+        p_ref2 = _psnr(fgs_b200, _train(ref, init, settings, targets), settings, targets)
+        spread = abs(p_ref - p_ref2)
+        print(f'PSNR reference backend {p_ref:.3f} / {p_ref2:.3f} dB (run-to-run spread {spread:.4f}); this repo {p_drop:.3f} / fused {p_fused:.3f} / fused loss {p_loss:.3f}')
+        assert abs(p_ref - p_drop) <= PSNR_TOL + 3 * spread, (p_ref, p_drop, spread)
+    tol = PSNR_TOL + 3 * spread
+    assert abs(p_fused - p_drop) <= tol, (p_fused, p_drop)
+    assert abs(p_loss - p_drop) <= tol, (p_loss, p_drop)
 
 
 @pytest.mark.gpu
