@@ -235,6 +235,11 @@ def run_gpu(args, impl):
     # FasterGSFused semantics (backward applies Adam in the same kernel) needs the whole batch in one backward
     use_fused = mine and dist is None and vpr == 1 and not args.unfused
     fused_loss = mine and not args.torch_loss
+    # deferred SH schedule: the sh_rest part of the fused step runs on a side stream under the next forward's geometry pass
+    defer_sh = use_fused and not args.no_defer_sh
+    if mine and args.defer_ctas:
+        from fgs_b200 import _capi as _capi0
+        _capi0.load().fgs_debug_set_deferred_ctas_per_sm(args.defer_ctas)
     if mine and args.overlap_adam:
         from fgs_b200 import _capi
         _capi.load().fgs_debug_set_overlap_adam(1)
@@ -251,7 +256,7 @@ def run_gpu(args, impl):
             # into fresh tensors that autograd adds onto it
             mine_C.set_gradient_outputs(registered.grads if opt_obj is not None else registered.views) if j == 0 else mine_C.set_gradient_outputs(None)
         if fused:  # backward applies the Adam update in the same kernel; opt.step() is then a no-op
-            img = be.diff_rasterize_fused(*params, dens_info, rs, opt)
+            img = be.diff_rasterize_fused(*params, dens_info, rs, opt, defer_sh=defer_sh)
         else:
             img = be.diff_rasterize(*params, dens_info, rs)
         if fused_loss:  # csrc/loss.cu: loss value and d loss / d image in one kernel, uint8 or float target
@@ -380,6 +385,8 @@ def run_gpu(args, impl):
     def reset_state():
         """Every timed loop starts from the same scene and a fresh optimizer: the cost of a step drifts as
         training moves the Gaussians, so loops that start from different states are not comparable."""
+        if mine:
+            mine_C.join_deferred(dev)  # a deferred sh_rest update may still be in flight
         with torch.no_grad():
             for p, p0 in zip(params, init_params):
                 p.copy_(p0)
@@ -407,6 +414,8 @@ def run_gpu(args, impl):
         e0.record()
         for it in range(steps):
             fn(warmup + it)
+        if mine:
+            mine_C.join_deferred(dev)  # the timed region ends when the last step's deferred update has finished, too
         e1.record()
         torch.cuda.synchronize()
         clocks = None
@@ -480,7 +489,8 @@ def run_gpu(args, impl):
     e2e_value = batch * 1000.0 / (ms_e2e / steps)
 
     if use_fused:
-        opt_path = 'fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)'
+        opt_path = 'fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' + (
+            '; deferred SH schedule: sh_rest Adam on a side stream under the next forward\'s geometry pass + sorts' if defer_sh else '')
     elif dp_mode in ('peer', 'peer-mc'):
         opt_path = ('backward into a symmetric-memory gradient buffer, then ONE kernel: gradient sum over the ranks + Adam on the '
                     'rank\'s 1/W slice + parameter broadcast (' + ('NVLS multimem.ld_reduce / multimem.st' if opt_obj.multicast else 'NVLink peer loads / stores') + ')')
@@ -571,7 +581,7 @@ def profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, us
     P, T = width * height, t_tiles
     N = n_gauss
     alg = algorithmic_bytes(N, V or 0, I, P, T)
-    dom = max(kern, key=kern.get)
+    dom = max((k for k in kern if 'side stream' not in k), key=kern.get)
     peak, peak_src = peak_hbm_gbs()
     dom_bytes = alg.get(dom + '_fused' if (use_fused and dom == 'preprocess_backward') else dom, alg.get(dom, 0))
     traffic = None
@@ -584,7 +594,7 @@ def profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, us
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_bytes = alg['iteration_fused'] if use_fused else alg['iteration']
     iter_achieved = iter_bytes * vpr / (ms_step * 1e-3) / 1e9
-    kernel_ms_sum = sum(kern.values()) * vpr
+    kernel_ms_sum = sum(v for k, v in kern.items() if 'side stream' not in k) * vpr  # main-stream kernels only
     out = {
         'gpu_launches': launches + (1 if fused_loss else 0) * vpr,
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 2), 'peak': peak, 'unit': 'GB/s',
@@ -819,6 +829,9 @@ def main():
     ap.add_argument('--torch-loss', action='store_true', help='loss with torch ops ((img - gt).abs().mean()) instead of the fused loss kernel')
     ap.add_argument('--yaml-loss', action='store_true',
                     help='the loss fastergs_garden.yaml trains with (0.8 L1 + 0.2 DSSIM, Loss.py:15-16) and a live densification_info')
+    ap.add_argument('--no-defer-sh', action='store_true',
+                    help='fused path without the deferred SH schedule (sh_rest Adam inside the backward kernel, SH evaluated in preprocess)')
+    ap.add_argument('--defer-ctas', type=int, default=0, help='experiments: CTAs per SM of the deferred sh_rest update kernel (default 2)')
     ap.add_argument('--overlap-adam', action='store_true',
                     help='MEASURED SLOWER (profiles/r2_results.md), kept for reference: zero-gradient Adam of invisible rows on a '
                          'side stream under the blend backward')

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
                                                             const uint32_t* __restrict__ vals,
                                                             const Rec* __restrict__ recs, Rec* __restrict__ inst_recs,
                                                             uint2* __restrict__ ranges, const uint32_t* __restrict__ n_inst_dev,
-                                                            const uint32_t capacity, const uint32_t grid_w) {
+                                                            const uint32_t capacity, const uint32_t grid_w,
+                                                            const float4* __restrict__ colors) {
     const uint32_t n_inst = bounded_count(n_inst_dev, capacity);
     const uint32_t inst = blockIdx.x * 256u + threadIdx.x;
     if (inst >= n_inst) return;
@@ -136,8 +137,14 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
     const uint32_t key = (uint32_t)keys[inst];
     const uint32_t prev = inst > 0 ? (uint32_t)keys[inst - 1] : 0xffffffffu;  // up front: not a third dependent round trip
     const float4 q0 = __ldg(&recs[prim].q0);
-    const float4 q1 = __ldg(&recs[prim].q1);
+    float4 q1 = __ldg(&recs[prim].q1);
     float4 q2 = __ldg(&recs[prim].q2);
+    if (colors != nullptr) {  // deferred-colour forward: the record's colour fields are still empty
+        const float4 c = __ldg(colors + prim);
+        q1.z = c.x;
+        q1.w = c.y;
+        q2.x = c.z;
+    }
     const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
     const uint32_t xmin = bx & 0xffffu, xmax = bx >> 16, ymin = by & 0xffffu, ymax = by >> 16;
     const uint32_t tx0 = (key % grid_w) * kTileW, ty0 = (key / grid_w) * kTileH;
@@ -204,15 +211,15 @@ template cudaError_t launch_create_instances<uint32_t>(const uint32_t*, const ui
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
                                      Rec* inst_recs, uint2* tile_ranges, const uint32_t* n_instances_dev, int capacity,
-                                     int grid_w, cudaStream_t stream) {
+                                     int grid_w, cudaStream_t stream, const float4* colors) {
     if (capacity <= 0) return cudaSuccess;
     FGS_LAUNCH(ranges_gather_kernel<KeyT>, (unsigned)((capacity + 255) / 256), 256, stream,
-        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, n_instances_dev, (uint32_t)capacity, (uint32_t)grid_w);
+        sorted_keys, sorted_vals, recs, inst_recs, tile_ranges, n_instances_dev, (uint32_t)capacity, (uint32_t)grid_w, colors);
     return cudaGetLastError();
 }
 template cudaError_t launch_ranges_and_gather<uint16_t>(const uint16_t*, const uint32_t*, const Rec*, Rec*, uint2*,
-                                                        const uint32_t*, int, int, cudaStream_t);
+                                                        const uint32_t*, int, int, cudaStream_t, const float4*);
 template cudaError_t launch_ranges_and_gather<uint32_t>(const uint32_t*, const uint32_t*, const Rec*, Rec*, uint2*,
-                                                        const uint32_t*, int, int, cudaStream_t);
+                                                        const uint32_t*, int, int, cudaStream_t, const float4*);
 
 }  // namespace fgs

@@ -112,6 +112,7 @@ struct PrimitiveLayout {
     uint32_t* n_touched;
     uint2* tile_info;    // per Gaussian: tile footprint (fgs_device.cuh)
     uint2* sorted_info;  // the footprints of the visible Gaussians in depth order
+    float4* colors;      // deferred-colour forward: colour per Gaussian (color_kernel), else unused
     uint32_t* keys[2];
     uint32_t* idx[2];
     uint32_t* offsets;
@@ -139,6 +140,7 @@ struct PrimitiveLayout {
         idx[0] = c.take<uint32_t>(nn);
         idx[1] = c.take<uint32_t>(nn);
         offsets = c.take<uint32_t>(nn);
+        colors = c.take<float4>(nn);
         bytes = c.bytes();
     }
 };
@@ -277,6 +279,40 @@ bool g_overlap_adam = [] {
     return e != nullptr && e[0] == '1';
 }();
 
+// Deferred sh_rest update (fgs_backward_adam_ex with FGS_DEFER_SH_REST): per device, a second side stream and the event
+// that marks the end of the pending update.  Whoever reads or writes the SH coefficients next makes its stream wait for
+// that event first: the deferred-colour forward just before its colour kernel (everything in front of it overlaps the
+// update), every other entry point at its very beginning (join_deferred).
+struct Deferred {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t start = nullptr;  // preprocess backward done (launching stream)
+    cudaEvent_t done = nullptr;   // adam_rest_kernel done (side stream)
+    bool pending = false;
+    int ctas_per_sm = 2;
+};
+Deferred& deferred() {
+    static Deferred d[kMaxDevices];
+    return d[device_slot()];
+}
+cudaError_t ensure_deferred() {
+    Deferred& d = deferred();
+    if (d.stream) return cudaSuccess;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lowest priority: the update yields to the forward it runs under
+    cudaError_t e = cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, lo);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&d.start, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    return cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming);
+}
+// make `stream` wait for a pending deferred update of the current device (no-op if there is none)
+cudaError_t join_deferred(cudaStream_t stream) {
+    Deferred& d = deferred();
+    if (!d.pending) return cudaSuccess;
+    d.pending = false;
+    return cudaStreamWaitEvent(stream, d.done, 0);
+}
+
 // instrumentation build only: device counters of the blend kernels (fgs_device.cuh, FGS_BLEND_STATS)
 unsigned long long* blend_stats_buffer() {
 #ifdef FGS_BLEND_STATS
@@ -302,7 +338,8 @@ int next_capacity_hint(int n_instances, int current) {
 template <typename KeyT>
 int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl, const TileLayout& tl,
                    const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit, const Cam& cam,
-                   float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
+                   float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
+                   const float4* colors) {
     InstanceLayout<KeyT> sizing(nullptr, capacity, end_bit);
     char* blob = resize(user_instance, sizing.bytes);
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
@@ -324,7 +361,7 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
                                        &in_alt, /*zero_scratch=*/false, /*pass0_hist=*/il.hist, 1, stream),
                 "tile sort");
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
-                                               tl.ranges, pl.counters + kCtrInstances, capacity, cam.grid_w, stream),
+                                               tl.ranges, pl.counters + kCtrInstances, capacity, cam.grid_w, stream, colors),
                 "ranges_and_gather");
     }
     BlendFwdArgs a{};
@@ -346,19 +383,24 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
 
 int finish_forward_any(bool keys16, fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl,
                        const TileLayout& tl, const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit,
-                       const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream) {
+                       const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
+                       const float4* colors) {
     return keys16 ? finish_forward<uint16_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                             image, training, to_chw, clamp_output, stream)
+                                             image, training, to_chw, clamp_output, stream, colors)
                   : finish_forward<uint32_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                             image, training, to_chw, clamp_output, stream);
+                                             image, training, to_chw, clamp_output, stream, colors);
 }
 
 int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
                  const float* scales, const float* rotations, const float* opacities, const float* sh0,
                  const float* sh_rest, const float* w2c, const float* cam_position, const float* bg_color, float* image,
                  int n, const fgs_settings* s, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
-                 fgs_forward_state* state_out) {
+                 fgs_forward_state* state_out, bool defer_color = false, cudaEvent_t color_wait = nullptr) {
     if (!resize || !s || !image) return fail_arg("fgs_forward: NULL argument");
+    if (defer_color && rotations == nullptr) return fail_arg("fgs_forward_ex: no deferred colour in covariance-input mode");
+    // a pending deferred update of the SH coefficients: the deferred-colour forward only needs it before its colour
+    // kernel (below); everything else reads the coefficients right away
+    if (!defer_color) FGS_TRY(join_deferred(stream), "join deferred update");
     if (s->width <= 0 || s->height <= 0) return fail_arg("fgs_forward: empty image");
     if (s->total_sh_bases_rest < 0 || s->total_sh_bases_rest > 15) return fail_arg("fgs_forward: sh_rest must have <= 15 bases");
     const Cam cam = make_cam(*s, w2c, cam_position, bg_color);
@@ -386,7 +428,8 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
 
     // rotations == NULL: covariance-input mode, `scales` holds (N,6) 3D covariances (include/fgs_b200.h)
     FGS_KERNEL(launch_preprocess(means, scales, rotations, opacities, sh0, sh_rest, pl.recs, pl.n_touched, pl.tile_info, pl.keys[0],
-                              pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream, rotations ? nullptr : scales),
+                              pl.idx[0], pl.counters, pl.depth_hist, n, cam, !training, stream, rotations ? nullptr : scales,
+                              defer_color),
             "preprocess");
     FGS_TRY(cudaEventRecord(rb.counted, stream), "event record");
     FGS_TRY(cudaStreamWaitEvent(rb.stream, rb.counted, 0), "read-back stream wait");
@@ -407,11 +450,20 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // Launch the rest with the capacity the previous forward suggested, and only then look at this forward's
     // own count (the read-back has long completed by then).  No suggestion yet: wait for the count first.
     const bool keys16 = end_bit <= 16;
+    const float4* colors = nullptr;
+    if (defer_color) {
+        // the SH coefficients are only needed from here on: wait for whoever still writes them (the deferred Adam update of
+        // the previous step on this device; `color_wait`: e.g. their broadcast from a peer GPU), then evaluate the colours
+        FGS_TRY(join_deferred(stream), "join deferred update");
+        if (color_wait) FGS_TRY(cudaStreamWaitEvent(stream, color_wait, 0), "wait for the colour event");
+        FGS_KERNEL(launch_color(means, sh0, sh_rest, pl.n_touched, pl.colors, n, cam, stream), "color");
+        colors = pl.colors;
+    }
     const int hinted = hints.get(n_tiles, n, training);
     int capacity = hinted;
     if (capacity > 0) {
         const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                          image, training, to_chw, clamp_output, stream);
+                                          image, training, to_chw, clamp_output, stream, colors);
         if (rc != 0) return rc;
     }
     FGS_TRY(cudaEventSynchronize(rb.event), "count read-back wait");
@@ -431,7 +483,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
         }
         capacity = n_instances;
         const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                          image, training, to_chw, clamp_output, stream);
+                                          image, training, to_chw, clamp_output, stream, colors);
         if (rc != 0) return rc;
     }
     hints.put(n_tiles, n, training, next_capacity_hint(n_instances, hinted));
@@ -449,9 +501,10 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
                   const float* cam_position, const float* bg_color, const char* primitive_buffers,
                   const char* tile_buffers, const char* instance_buffers, PreBwdArgs pa, void* grad2d_scratch,
                   float* densification_info, int n, const fgs_settings* s, const fgs_forward_state* state,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, bool defer_rest = false) {
     if (!s || !state) return fail_arg("fgs_backward: NULL argument");
     if (n <= 0) return 0;
+    FGS_TRY(join_deferred(stream), "join deferred update");  // the backward reads (and, fused, writes) the SH coefficients
     const Cam cam = make_cam(*s, w2c, cam_position, bg_color);
     const int n_tiles = cam.grid_w * cam.grid_h;
     const int n_pixels = s->width * s->height;
@@ -504,7 +557,23 @@ int backward_impl(const float* grad_image, const float* image, const float* mean
     pa.grad2d = grad2d;
     pa.densification_info = densification_info;
     if (overlap) FGS_TRY(cudaStreamWaitEvent(stream, readback().event, 0), "join side stream (overlap)");
+    const bool defer = defer_rest && !overlap && preprocess_backward_can_defer_rest(pa, cam);
+    pa.defer_rest = defer;
     FGS_KERNEL(launch_preprocess_backward(pa, cam, stream, overlap), "preprocess_backward");
+    if (defer) {
+        // the sh_rest part of the step (three quarters of the fused kernel's HBM traffic) goes to the low-priority side
+        // stream; the caller's stream is free to start the next forward's geometry pass and sorts
+        FGS_TRY(ensure_deferred(), "deferred stream");
+        Deferred& d = deferred();
+        FGS_TRY(cudaEventRecord(d.start, stream), "event record (deferred)");
+        FGS_TRY(cudaStreamWaitEvent(d.stream, d.start, 0), "deferred stream wait");
+        {
+            ProfScope ps_("adam_rest (deferred, side stream)", d.stream);
+            FGS_TRY(launch_adam_rest(pa, cam, d.stream, d.ctas_per_sm), "adam_rest");
+        }
+        FGS_TRY(cudaEventRecord(d.done, d.stream), "event record (deferred)");
+        d.pending = true;
+    }
     return 0;
 }
 
@@ -611,11 +680,56 @@ int fgs_backward_adam(const float* grad_image, const float* image, float* const 
                          densification_info, n_primitives, settings, state, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fgs_forward_ex(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
+                   const float* scales, const float* rotations, const float* opacities, const float* sh_coefficients_0,
+                   const float* sh_coefficients_rest, const float* w2c, const float* cam_position, const float* bg_color,
+                   float* image, int32_t n_primitives, const fgs_settings* settings, void* stream,
+                   fgs_forward_state* state_out, uint32_t flags, void* color_wait_event) {
+    return forward_impl(resize, user_primitive, user_tile, user_instance, means, scales, rotations, opacities,
+                        sh_coefficients_0, sh_coefficients_rest, w2c, cam_position, bg_color, image, n_primitives,
+                        settings, true, true, false, reinterpret_cast<cudaStream_t>(stream), state_out,
+                        (flags & FGS_DEFER_COLOR) != 0, reinterpret_cast<cudaEvent_t>(color_wait_event));
+}
+
+int fgs_backward_adam_ex(const float* grad_image, const float* image, float* const params[6], float* const exp_avg[6],
+                         float* const exp_avg_sq[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
+                         double eps, const float* w2c, const float* cam_position, const float* bg_color,
+                         const char* primitive_buffers, const char* tile_buffers, const char* instance_buffers,
+                         void* grad2d_scratch, float* densification_info, int32_t n_primitives,
+                         const fgs_settings* settings, const fgs_forward_state* state, void* stream, uint32_t flags) {
+    PreBwdArgs pa{};
+    pa.fused = true;
+    for (int t = 0; t < 6; ++t) {
+        pa.p[t] = params[t];
+        pa.m[t] = exp_avg[t];
+        pa.v[t] = exp_avg_sq[t];
+        const double bc1_rcp = 1.0 / (1.0 - std::pow(beta1, (double)step[t]));
+        const double bc2_sqrt_rcp = 1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step[t]));
+        pa.hyper.step_size[t] = (float)(lr[t] * bc1_rcp);
+        pa.hyper.bias2_sqrt_rcp[t] = (float)bc2_sqrt_rcp;
+    }
+    pa.hyper.beta1 = (float)beta1;
+    pa.hyper.beta2 = (float)beta2;
+    pa.hyper.eps = (float)eps;
+    return backward_impl(grad_image, image, params[0], params[1], params[2], params[3], params[5], w2c, cam_position,
+                         bg_color, primitive_buffers, tile_buffers, instance_buffers, pa, grad2d_scratch,
+                         densification_info, n_primitives, settings, state, reinterpret_cast<cudaStream_t>(stream),
+                         (flags & FGS_DEFER_SH_REST) != 0);
+}
+
+int fgs_join_deferred(void* stream) {
+    FGS_TRY(join_deferred(reinterpret_cast<cudaStream_t>(stream)), "fgs_join_deferred");
+    return 0;
+}
+
+void fgs_debug_set_deferred_ctas_per_sm(int32_t ctas) { deferred().ctas_per_sm = ctas > 0 ? ctas : 2; }
+
 int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* exp_avg_sq, size_t n_elements,
                   int32_t step_count, double learning_rate, double beta1, double beta2, double epsilon, void* stream) {
     const double bc1_rcp = 1.0 / (1.0 - std::pow(beta1, (double)step_count));
     const double bc2_sqrt_rcp = 1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step_count));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    FGS_TRY(join_deferred(st), "join deferred update");  // `param` may be the tensor a deferred update is still writing
     {
         ProfScope ps_("adam_step", st);
         FGS_TRY(launch_adam(param_grad, param, exp_avg, exp_avg_sq, n_elements, (float)(learning_rate * bc1_rcp),
@@ -705,12 +819,18 @@ int32_t fgs_debug_get_capacity_hint(void) { return capacity_hints().last; }
 int32_t fgs_debug_get_forward_reruns(void) { return capacity_hints().reruns; }
 
 int fgs_debug_blend_stats(uint64_t out[16], int32_t reset) {
+#ifdef FGS_BLEND_STATS
     unsigned long long* p = blend_stats_buffer();
-    if (!p) return fail_arg("fgs_debug_blend_stats: the library was not built with -DFGS_BLEND_STATS=1");
+    if (!p) return fail_arg("fgs_debug_blend_stats: no counter buffer");
     FGS_TRY(cudaDeviceSynchronize(), "blend stats sync");
     if (out) FGS_TRY(cudaMemcpy(out, p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "blend stats copy");
     if (reset) FGS_TRY(cudaMemset(p, 0, 16 * sizeof(unsigned long long)), "blend stats reset");
     return 0;
+#else
+    (void)out;
+    (void)reset;
+    return fail_arg("fgs_debug_blend_stats: the library was not built with -DFGS_BLEND_STATS=1");
+#endif
 }
 
 void fgs_profile_enable(int32_t on) {

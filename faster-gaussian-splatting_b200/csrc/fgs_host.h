@@ -53,7 +53,11 @@ cudaError_t launch_preprocess(const float* means, const float* scales, const flo
                               uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices,
                               uint32_t* counters, uint32_t* depth_hist,
                               int n, const Cam& cam, bool inference, cudaStream_t stream,
-                              const float* cov3d = nullptr /* (N,6): 3D covariances given directly, scales/rotations unused */);
+                              const float* cov3d = nullptr /* (N,6): 3D covariances given directly, scales/rotations unused */,
+                              bool defer_color = false /* geometry only; launch_color fills `colors` later */);
+// colours (clamped, sign-tagged like the record's colour fields) of the visible Gaussians, for a deferred-colour forward
+cudaError_t launch_color(const float* means, const float* sh0, const float* sh_rest, const uint32_t* n_touched,
+                         float4* colors, int n, const Cam& cam, cudaStream_t stream);
 
 // LSD radix sort of (key, value) pairs, onesweep style (one read + one write of the data per pass).
 // `n_dev` points at the element count on the device, `n_max` bounds it on the host (grid sizing).
@@ -94,7 +98,8 @@ cudaError_t launch_create_instances(const uint32_t* sorted_idx, const uint32_t* 
 template <typename KeyT>
 cudaError_t launch_ranges_and_gather(const KeyT* sorted_keys, const uint32_t* sorted_vals, const Rec* recs,
                                      Rec* inst_recs, uint2* tile_ranges, const uint32_t* n_instances_dev, int capacity,
-                                     int grid_w, cudaStream_t stream);
+                                     int grid_w, cudaStream_t stream,
+                                     const float4* colors = nullptr /* deferred-colour forward: colours per Gaussian */);
 
 struct BlendFwdArgs {
     const Rec* inst_recs;
@@ -159,12 +164,17 @@ struct PreBwdArgs {
     float* v[6];
     AdamHyper hyper;
     bool fused;
+    // fused only: leave sh_rest (parameters and moments) alone and store the view direction in the 2D gradient record;
+    // launch_adam_rest applies that part of the step later (side stream)
+    bool defer_rest;
     int n;
 };
 cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, bool skip_invisible_rest = false);
 // Overlapped schedule of the fused backward + Adam (opt-in, fgs_debug_set_overlap_adam): the zero-gradient Adam update of
 // the sh_rest rows of invisible Gaussians runs on a side stream while the blend backward runs;
 // launch_preprocess_backward(..., skip_invisible_rest = true) then leaves those rows alone.  Results are bit-identical.
+bool preprocess_backward_can_defer_rest(const PreBwdArgs& a, const Cam& cam);
+cudaError_t launch_adam_rest(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, int ctas_per_sm);
 bool preprocess_backward_can_overlap(const PreBwdArgs& a, const Cam& cam);
 cudaError_t launch_adam_rest_invisible(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream);
 

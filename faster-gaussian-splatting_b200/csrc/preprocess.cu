@@ -78,7 +78,10 @@ __device__ __forceinline__ float3 eval_sh(const float3 sh0, const float* __restr
 // kCov3d: `scales` points at (N,6) rows (xx, xy, xz, yy, yz, zz) of the 3D covariance and `rotations` is not read -- the
 // input mode of Gaussians whose covariance does not come from (scale, rotation), e.g. 4D Gaussians sliced at a time t
 // (csrc/slice4d.cu).  Everything downstream of the covariance is identical.
-template <bool kInference, bool kCov3d>
+// kDeferColor: geometry only.  sh0 / sh_rest are NOT read and the record's colour fields stay zero; color_kernel fills a
+// separate colour array later (after the sorts), so that whatever still writes the SH coefficients -- the deferred Adam
+// update of sh_rest on a side stream, or their broadcast from a peer GPU -- can overlap this kernel and the sorts.
+template <bool kInference, bool kCov3d, bool kDeferColor>
 __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const float* __restrict__ means, const float* __restrict__ scales, const float* __restrict__ rotations,
     const float* __restrict__ opacities, const float* __restrict__ sh0, const float* __restrict__ sh_rest,
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
         stage_rows<6>(s_scales, scales + (size_t)first * 6, rows * 6, tid, kPreBlock);
     else
         stage_rows<3>(s_scales, scales + (size_t)first * 3, rows * 3, tid, kPreBlock);
-    stage_rows<3>(s_sh0, sh0 + (size_t)first * 3, rows * 3, tid, kPreBlock);
+    if (!kDeferColor) stage_rows<3>(s_sh0, sh0 + (size_t)first * 3, rows * 3, tid, kPreBlock);
     __syncthreads();
     if (cam_bulk) mbar_wait(&s_bar, 0u);
     float W[12];
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     const int active_bases = min(cam.active_sh_bases, nrest + 1);
     float* my_rest = s_rest + warp * (32 * 45);
     bool rest_staged = false;
-    {
+    if (!kDeferColor) {
         const int wfirst = first + warp * 32;
         const int wrows = max(0, min(32, n - wfirst));
         const float* wsrc = sh_rest + (size_t)wfirst * 45;
@@ -306,12 +309,15 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
         rest_ptr = rest_staged ? my_rest + lane * 45 : sh_rest + (size_t)(idx < n ? idx : first) * (size_t)(nrest * 3);
     base = __shfl_sync(0xffffffffu, base, __ffs((int)vis_mask) - 1);
     if (!visible) return;
-    float3 dir = make_float3(mean.x - __ldg(cam.cam_pos), mean.y - __ldg(cam.cam_pos + 1), mean.z - __ldg(cam.cam_pos + 2));
-    const float inv_len = rsqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-    dir.x *= inv_len;
-    dir.y *= inv_len;
-    dir.z *= inv_len;
-    float3 color = eval_sh(make_float3(s_sh0[3 * r], s_sh0[3 * r + 1], s_sh0[3 * r + 2]), rest_ptr, dir, active_bases);
+    float3 color = make_float3(0.f, 0.f, 0.f);
+    if (!kDeferColor) {
+        float3 dir = make_float3(mean.x - __ldg(cam.cam_pos), mean.y - __ldg(cam.cam_pos + 1), mean.z - __ldg(cam.cam_pos + 2));
+        const float inv_len = rsqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+        dir.x *= inv_len;
+        dir.y *= inv_len;
+        dir.z *= inv_len;
+        color = eval_sh(make_float3(s_sh0[3 * r], s_sh0[3 * r + 1], s_sh0[3 * r + 2]), rest_ptr, dir, active_bases);
+    }
     // colours are stored clamped (what every blend consumes, kernels_forward.cuh:430 /
     // kernels_inference.cuh:200); the clamp mask for the backward rides in the sign bit
     Rec rec;
@@ -330,26 +336,90 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_kernel(
     atomicAdd(depth_hist + (blockIdx.x % kDepthHistReplicas) * kRadixMax + (__float_as_uint(depth) & 0xffu), 1u);
 }
 
+// The colour of every visible Gaussian (n_touched > 0), evaluated after the fact for a forward that ran
+// preprocess_kernel<.., kDeferColor = true>: same staging (cp.async of the warp's 32 SH rows), same expressions, same
+// clamped / sign-tagged encoding as the record's colour fields; colors[idx] = (r, g, b, 0).
+__global__ void __launch_bounds__(kPreBlock) color_kernel(const float* __restrict__ means, const float* __restrict__ sh0,
+                                                          const float* __restrict__ sh_rest,
+                                                          const uint32_t* __restrict__ n_touched, float4* __restrict__ colors,
+                                                          const int n, const Cam cam) {
+    FGS_DYNAMIC_SMEM(float, s_rest, 16);  // 4 warps x 32 x 45 floats
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wfirst = blockIdx.x * kPreBlock + warp * 32;
+    if (wfirst >= n) return;
+    const int idx = wfirst + lane;
+    const bool visible = idx < n && __ldg(n_touched + idx) > 0u;
+    const uint32_t vis_mask = __ballot_sync(0xffffffffu, visible);
+    if (vis_mask == 0u) return;
+    const int nrest = cam.total_sh_rest;
+    const int active_bases = min(cam.active_sh_bases, nrest + 1);
+    float* my_rest = s_rest + warp * (32 * 45);
+    bool rest_staged = false;
+    {
+        const int wrows = min(32, n - wfirst);
+        const float* wsrc = sh_rest + (size_t)wfirst * 45;
+        if (nrest == 15 && active_bases > 4 && __popc(vis_mask) >= 8 && (reinterpret_cast<uintptr_t>(wsrc) & 15u) == 0) {
+            const int n_floats = wrows * 45, n4 = n_floats >> 2;
+            for (int i = lane; i < n4; i += 32) cp_async_16(my_rest + 4 * i, wsrc + 4 * i);
+            cp_async_commit();
+            for (int i = (n4 << 2) + lane; i < n_floats; i += 32) my_rest[i] = __ldg(wsrc + i);
+            rest_staged = true;
+        }
+    }
+    float3 mean = make_float3(0.f, 0.f, 0.f), c0 = mean;
+    if (visible) {
+        mean = make_float3(__ldg(means + 3 * (size_t)idx), __ldg(means + 3 * (size_t)idx + 1), __ldg(means + 3 * (size_t)idx + 2));
+        c0 = make_float3(__ldg(sh0 + 3 * (size_t)idx), __ldg(sh0 + 3 * (size_t)idx + 1), __ldg(sh0 + 3 * (size_t)idx + 2));
+    }
+    if (rest_staged) {
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    if (!visible) return;
+    const float* rest_ptr = nullptr;
+    if (active_bases > 1) rest_ptr = rest_staged ? my_rest + lane * 45 : sh_rest + (size_t)idx * (size_t)(nrest * 3);
+    float3 dir = make_float3(mean.x - __ldg(cam.cam_pos), mean.y - __ldg(cam.cam_pos + 1), mean.z - __ldg(cam.cam_pos + 2));
+    const float inv_len = rsqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x *= inv_len;
+    dir.y *= inv_len;
+    dir.z *= inv_len;
+    const float3 color = eval_sh(c0, rest_ptr, dir, active_bases);
+    colors[idx] = make_float4(pack_color(color.x), pack_color(color.y), pack_color(color.z), 0.f);
+}
+
+cudaError_t launch_color(const float* means, const float* sh0, const float* sh_rest, const uint32_t* n_touched,
+                         float4* colors, int n, const Cam& cam, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int grid = (n + kPreBlock - 1) / kPreBlock;
+    const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
+    FGS_LAUNCH_SMEM(color_kernel, grid, kPreBlock, smem, stream, means, sh0, sh_rest, n_touched, colors, n, cam);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_preprocess(const float* means, const float* scales, const float* rotations,
                               const float* opacities, const float* sh0, const float* sh_rest, Rec* recs,
                               uint32_t* n_touched, uint2* tile_info, uint32_t* depth_keys, uint32_t* vis_indices, uint32_t* counters,
                               uint32_t* depth_hist, int n, const Cam& cam, bool inference, cudaStream_t stream,
-                              const float* cov3d) {
+                              const float* cov3d, bool defer_color) {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + kPreBlock - 1) / kPreBlock;
     const size_t smem = (size_t)(kPreBlock / 32) * 32 * 45 * sizeof(float);
-#define FGS_PRE_LAUNCH(INF, COV, SCALES)                                                                               \
+#define FGS_PRE_LAUNCH(INF, COV, DEFER, SCALES)                                                                        \
     do {                                                                                                               \
-        auto kernel = preprocess_kernel<INF, COV>;                                                                     \
-        FGS_LAUNCH_SMEM(kernel, grid, kPreBlock, smem, stream, means, SCALES, rotations, opacities, sh0, sh_rest, recs, \
-                        n_touched, tile_info, depth_keys, vis_indices, counters, depth_hist, n, cam);                  \
+        auto kernel = preprocess_kernel<INF, COV, DEFER>;                                                              \
+        FGS_LAUNCH_SMEM(kernel, grid, kPreBlock, DEFER ? 0 : smem, stream, means, SCALES, rotations, opacities, sh0,    \
+                        sh_rest, recs, n_touched, tile_info, depth_keys, vis_indices, counters, depth_hist, n, cam);   \
     } while (0)
     if (cov3d) {
-        if (inference) FGS_PRE_LAUNCH(true, true, cov3d);
-        else FGS_PRE_LAUNCH(false, true, cov3d);
+        if (defer_color) return cudaErrorInvalidValue;  // the covariance-input mode has no deferred colour
+        if (inference) FGS_PRE_LAUNCH(true, true, false, cov3d);
+        else FGS_PRE_LAUNCH(false, true, false, cov3d);
+    } else if (defer_color) {
+        if (inference) FGS_PRE_LAUNCH(true, false, true, scales);
+        else FGS_PRE_LAUNCH(false, false, true, scales);
     } else {
-        if (inference) FGS_PRE_LAUNCH(true, false, scales);
-        else FGS_PRE_LAUNCH(false, false, scales);
+        if (inference) FGS_PRE_LAUNCH(true, false, false, scales);
+        else FGS_PRE_LAUNCH(false, false, false, scales);
     }
 #undef FGS_PRE_LAUNCH
     return cudaGetLastError();

@@ -199,6 +199,80 @@ __global__ void __launch_bounds__(128, 16) adam_rest_invisible_kernel(const uint
     }
 }
 
+// SH basis values Y_1..Y_15 of a unit direction (sh_utils.cuh:32-69; same expressions as FGS_SH in the backward kernel)
+__device__ __forceinline__ void sh_basis_rest(float x, float y, float z, int active_bases, float* __restrict__ Y) {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) Y[k] = 0.f;
+    if (active_bases > 1) {
+        Y[0] = -C1 * y;
+        Y[1] = C1 * z;
+        Y[2] = -C1 * x;
+        if (active_bases > 4) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+            Y[3] = C2a * xy;
+            Y[4] = -C2a * yz;
+            Y[5] = C2b * zz - C2c;
+            Y[6] = -C2a * xz;
+            Y[7] = C2d * (xx - yy);
+            if (active_bases > 9) {
+                Y[8] = y * (C3a * yy - C3b * xx);
+                Y[9] = C3c * xy * z;
+                Y[10] = y * (C3d - C3e * zz);
+                Y[11] = z * (C3f * zz - C3g);
+                Y[12] = x * (C3d - C3e * zz);
+                Y[13] = C3h * z * (xx - yy);
+                Y[14] = x * (C3b * yy - C3a * xx);
+            }
+        }
+    }
+}
+
+// Deferred Adam update of sh_rest (fgs_backward_adam_ex, FGS_DEFER_SH_REST): launched on a side stream after
+// preprocess_backward_kernel, so that its 1080 bytes per Gaussian of pure HBM traffic -- three quarters of the fused
+// kernel's -- overlap the latency-bound front of the NEXT forward (geometry preprocess + sorts), which does not read SH
+// coefficients when run with deferred colour.  Persistent and deliberately small (one or two 128-thread CTAs per SM, <= 40
+// registers): it has to coexist with the forward's kernels, not to win the machine.  Gradient of a visible Gaussian =
+// Y_k(dir) * dcol with dir and dcol left in its 2D gradient record by the backward kernel; invisible rows get the
+// zero-gradient decay of dense Adam.  Same arithmetic as the fused kernel, same result.
+__global__ void __launch_bounds__(128, 4) adam_rest_kernel(const uint32_t* __restrict__ n_touched, const Grad2D* __restrict__ grad2d,
+                                                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                           const int n, const int row_floats, const int active_bases,
+                                                           const float step_size, const float beta1, const float beta2,
+                                                           const float eps, const float b2) {
+    FGS_DYNAMIC_SMEM(float, s_rows, 16);  // 4 warps x 32 rows x 45 floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stage = s_rows + warp * (32 * 45);
+    const int groups = (n + 31) >> 5;
+    for (int group = blockIdx.x * 4 + warp; group < groups; group += gridDim.x * 4) {
+        const int wfirst = group << 5;
+        const int rows = min(32, n - wfirst);
+        const int idx = wfirst + lane;
+        const bool visible = lane < rows && __ldg(n_touched + idx) > 0u;
+        float* mine = stage + lane * row_floats;
+        if (visible) {
+            const float4 g0 = __ldg(&grad2d[idx].g0);  // (dir.xyz, -)
+            const float4 g1 = __ldg(&grad2d[idx].g1);
+            const float g2x = __ldg(&grad2d[idx].g2.x);
+            float Y[15];
+            sh_basis_rest(g0.x, g0.y, g0.z, active_bases, Y);
+#pragma unroll
+            for (int k = 0; k < 15; ++k) {
+                if (3 * k < row_floats) {
+                    mine[3 * k] = Y[k] * g1.z;
+                    mine[3 * k + 1] = Y[k] * g1.w;
+                    mine[3 * k + 2] = Y[k] * g2x;
+                }
+            }
+        } else if (lane < rows) {
+            for (int k = 0; k < row_floats; ++k) mine[k] = 0.f;
+        }
+        __syncwarp();
+        emit_span(stage, nullptr, p, m, v, (size_t)wfirst * row_floats, rows * row_floats, true, step_size, beta1, beta2, eps,
+                  b2, lane);
+        __syncwarp();
+    }
+}
+
 // Loads of the PARAMETER tensors.  In fused mode (fgs_backward_adam) means / scales / rotations / opacities / sh_rest are
 // the very tensors this launch updates in place (emit_span), so they must not go through the read-only data cache
 // (ld.global.nc is only defined for memory that stays constant for the whole launch): plain ld.global.
@@ -248,7 +322,7 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
 
     if (visible) {
         const Grad2D* gp = a.grad2d + idx;
-        const float4 g0 = __ldg(&gp->g0);
+        const float4 g0 = ld_param(&gp->g0);  // plain load: the deferred mode overwrites this quarter of the record below
         const float4 g1 = __ldg(&gp->g1);
         const float g2x = __ldg(&gp->g2.x);
         const float3 dcol = make_float3(g1.z, g1.w, g2x);
@@ -265,6 +339,10 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
             const float len2 = rx * rx + ry * ry + rz * rz;
             const float inv_len = rsqrtf(len2);
             const float x = rx * inv_len, y = ry * inv_len, z = rz * inv_len;
+            // deferred sh_rest update: adam_rest_kernel rebuilds this Gaussian's sh_rest gradient (Y_k(dir) * dcol) later,
+            // from the view direction of THIS forward (the means are updated below, so it cannot be recomputed) --
+            // the direction replaces the consumed (dmean2d, dconic.xy) quarter of the 2D gradient record
+            if (a.defer_rest) const_cast<Grad2D*>(gp)->g0 = make_float4(x, y, z, 0.f);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;  // dL/d(direction)
             // coefficient k: reads c_k . dcol for the direction gradient, then overwrites it with Y_k * dcol
 #define FGS_SH(k, Y, DX, DY, DZ)                                                             \
@@ -507,7 +585,7 @@ __global__ void __launch_bounds__(kBlock) preprocess_backward_kernel(const PreBw
               h.eps, h.bias2_sqrt_rcp[3], lane);
     emit_span(st + kOffSh0, a.g_sh0, a.p[4], a.m[4], a.v[4], w0 * 3, rows * 3, a.fused, h.step_size[4], h.beta1, h.beta2,
               h.eps, h.bias2_sqrt_rcp[4], lane);
-    if (rest_floats > 0) {
+    if (rest_floats > 0 && !a.defer_rest && (a.fused || a.g_sh_rest != nullptr)) {
         if (kSkipInvisibleRest) {
             if (vis_mask != 0u)
                 emit_span_rows<4>(rest, a.p[5], a.m[5], a.v[5], w0 * rest_floats, rows * rest_floats, rest_floats, vis_mask,
@@ -572,6 +650,34 @@ cudaError_t launch_preprocess_backward(const PreBwdArgs& a, const Cam& cam, cuda
     auto kernel = a.cov3d ? preprocess_backward_kernel<false, true>
                           : (skip_invisible_rest && a.fused) ? preprocess_backward_kernel<true, false> : preprocess_backward_kernel<false, false>;
     FGS_LAUNCH_SMEM(kernel, div_up(a.n, kBlock), kBlock, smem, stream, a, cam);
+    return cudaGetLastError();
+}
+
+bool preprocess_backward_can_defer_rest(const PreBwdArgs& a, const Cam& cam) {
+    const int rest_floats = cam.total_sh_rest * 3;
+    return a.fused && !a.cov3d && a.n > 0 && rest_floats >= 3 && rest_floats <= 45 && cam.active_sh_bases > 1;
+}
+
+cudaError_t launch_adam_rest(const PreBwdArgs& a, const Cam& cam, cudaStream_t stream, int ctas_per_sm) {
+    if (!preprocess_backward_can_defer_rest(a, cam)) return cudaErrorInvalidValue;
+    static PerDevice<int> s_sms_dev;
+    int& s_sms = s_sms_dev.here();
+    if (s_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (s_sms < 1) s_sms = 1;
+    }
+    const int groups = (a.n + 31) / 32;
+    const int want = (groups + 3) / 4;
+    const int cap = s_sms * (ctas_per_sm > 0 ? ctas_per_sm : 2);
+    const int grid = want < cap ? want : cap;
+    const AdamHyper& h = a.hyper;
+    const size_t smem = 4 * 32 * 45 * sizeof(float);
+    const int rest_floats = cam.total_sh_rest * 3;
+    const int active_bases = cam.active_sh_bases < cam.total_sh_rest + 1 ? cam.active_sh_bases : cam.total_sh_rest + 1;
+    FGS_LAUNCH_SMEM(adam_rest_kernel, grid, 128, smem, stream, a.n_touched, a.grad2d, a.p[5], a.m[5], a.v[5], a.n, rest_floats,
+                    active_bases, h.step_size[5], h.beta1, h.beta2, h.eps, h.bias2_sqrt_rcp[5]);
     return cudaGetLastError();
 }
 

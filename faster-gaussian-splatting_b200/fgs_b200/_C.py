@@ -91,6 +91,17 @@ def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficie
             proper_antialiasing):
     """rasterization_api.h:8-28.  Returns (image, primitive_buffers, tile_buffers, instance_buffers,
     bucket_buffers, n_instances, n_buckets, selector); the buffers are opaque."""
+    return forward_ex(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c, cam_position,
+                      bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+                      proper_antialiasing)
+
+
+def forward_ex(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest, w2c, cam_position,
+               bg_color, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
+               proper_antialiasing, defer_color=False, color_event=None):
+    """`forward` with the extension of include/fgs_b200.h "deferred SH schedule": `defer_color` = geometry pass without
+    SH, colours evaluated after the sorts -- a pending deferred sh_rest update and `color_event` (a torch.cuda.Event,
+    optional) are only waited for there.  Same image, same return tuple."""
     for t, name in ((means, 'means'), (scales, 'scales'), (rotations, 'rotations'), (opacities, 'opacities'),
                     (sh_coefficients_0, 'sh_coefficients_0'), (sh_coefficients_rest, 'sh_coefficients_rest')):
         _check_param(t, name)
@@ -104,10 +115,14 @@ def forward(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficie
                        far_plane, proper_antialiasing)
         state = _capi.ForwardState()
         with _Scratch(dev) as ctx:
-            rc = _lib.fgs_forward(_resize_cb, ctx.user(_PRIMITIVE), ctx.user(_TILE), ctx.user(_INSTANCE), _ptr(means),
-                                  _ptr(scales), _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
-                                  _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image), n,
-                                  C.byref(st), _stream(), C.byref(state))
+            args = (_resize_cb, ctx.user(_PRIMITIVE), ctx.user(_TILE), ctx.user(_INSTANCE), _ptr(means),
+                    _ptr(scales), _ptr(rotations), _ptr(opacities), _ptr(sh_coefficients_0),
+                    _ptr(sh_coefficients_rest), _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(image), n,
+                    C.byref(st), _stream(), C.byref(state))
+            if defer_color:
+                rc = _lib.fgs_forward_ex(*args, 1, None if color_event is None else color_event.cuda_event)
+            else:
+                rc = _lib.fgs_forward(*args)
             _capi.check(rc, 'forward')
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         prim, tile, inst = (ctx.buffers.get(k, empty) for k in (_PRIMITIVE, _TILE, _INSTANCE))
@@ -187,13 +202,25 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
     return grads[0], grads[1], grads[2], grads[3], g_sh0, g_rest
 
 
+_deferred_keepalive: dict = {}  # device -> tensors the pending deferred update of that device still reads
+
+
+def join_deferred(device=None) -> None:
+    """Make the current stream wait for a pending deferred sh_rest update (stream-ordered, no host wait).  Call it before
+    touching sh_coefficients_rest or its Adam moments with anything but this package's operators."""
+    with _capi.device_guard(device if device is not None else torch.cuda.current_device()):
+        _capi.check(_lib.fgs_join_deferred(_stream()), 'join_deferred')
+
+
 def backward_adam(densification_info, grad_image, image, params, exp_avgs, exp_avg_sqs, steps, lrs, beta1, beta2, eps,
                   primitive_buffers, tile_buffers, instance_buffers, w2c, cam_position, bg_color, active_sh_bases,
                   width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane, proper_antialiasing,
-                  n_instances) -> None:
+                  n_instances, defer_rest=False) -> None:
     """FasterGSFused semantics: backward + FusedAdam.step in one pass (include/fgs_b200.h).
     `params`, `exp_avgs`, `exp_avg_sqs`: six tensors each in the order means, scales, rotations,
-    opacities, sh_coefficients_0, sh_coefficients_rest; updated in place."""
+    opacities, sh_coefficients_0, sh_coefficients_rest; updated in place.
+    `defer_rest`: the sh_rest part of the update runs on the library's side stream (include/fgs_b200.h "deferred SH
+    schedule"); the next `forward(..., defer_color=True)` overlaps it with its geometry pass and sorts."""
     dev, st, state, w2c_c, pos_c, bg_c, gi, dens_ptr = _backward_common(
         image, primitive_buffers, w2c, cam_position, bg_color, grad_image, densification_info, params[5],
         active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane, far_plane,
@@ -205,12 +232,19 @@ def backward_adam(densification_info, grad_image, image, params, exp_avgs, exp_a
         n = params[0].shape[0]
         scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)
         arr = lambda ts: (C.c_void_p * 6)(*[_ptr(t) for t in ts])
-        rc = _lib.fgs_backward_adam(_ptr(gi), _ptr(image), arr(params), arr(exp_avgs), arr(exp_avg_sqs),
-                                    (C.c_int32 * 6)(*[int(s) for s in steps]),
-                                    (C.c_double * 6)(*[float(l) for l in lrs]), float(beta1), float(beta2), float(eps),
-                                    _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(primitive_buffers), _ptr(tile_buffers),
-                                    _ptr(instance_buffers), _ptr(scratch), dens_ptr, n, C.byref(st), C.byref(state),
-                                    _stream())
+        args = (_ptr(gi), _ptr(image), arr(params), arr(exp_avgs), arr(exp_avg_sqs),
+                (C.c_int32 * 6)(*[int(s) for s in steps]),
+                (C.c_double * 6)(*[float(l) for l in lrs]), float(beta1), float(beta2), float(eps),
+                _ptr(w2c_c), _ptr(pos_c), _ptr(bg_c), _ptr(primitive_buffers), _ptr(tile_buffers),
+                _ptr(instance_buffers), _ptr(scratch), dens_ptr, n, C.byref(st), C.byref(state), _stream())
+        if defer_rest:
+            rc = _lib.fgs_backward_adam_ex(*args, 1)
+            # the side-stream kernel reads the 2D gradient scratch and the primitive buffers after this call has returned:
+            # they stay referenced until the NEXT deferred backward on this device, by which time the forward in between
+            # has made the caller's stream wait for the update (so the allocator may hand the memory out again)
+            _deferred_keepalive[dev] = (scratch, primitive_buffers, params[5], exp_avgs[5], exp_avg_sqs[5])
+        else:
+            rc = _lib.fgs_backward_adam(*args)
         _capi.check(rc, 'backward_adam')
 
 

@@ -21,4 +21,6 @@ def __getattr__(name):
         return getattr(tb, name)
     if name in ('_C', '_capi', 'torch_bindings', 'synthetic', 'parallel', 'loss', 'densification', 'fourd'):
         return importlib.import_module('.' + name, __name__)
+    if name == 'join_deferred':  # deferred SH schedule (diff_rasterize_fused(..., defer_sh=True)): see _C.join_deferred
+        return importlib.import_module('._C', __name__).join_deferred
     raise AttributeError(f'module {__name__!r} has no attribute {name!r}')

@@ -67,6 +67,13 @@ SIGNATURES = {
     'fgs_backward_adam': (C.c_int, [_P, _P, _PtrArr6, _PtrArr6, _PtrArr6, _I32Arr6, _F64Arr6, C.c_double,
                                      C.c_double, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
                                      C.POINTER(Settings), C.POINTER(ForwardState), _P]),
+    'fgs_forward_ex': (C.c_int, [ResizeFn, _P, _P, _P] + [_P] * 9 + [_P, C.c_int32, C.POINTER(Settings), _P,
+                                                                       C.POINTER(ForwardState), C.c_uint32, _P]),
+    'fgs_backward_adam_ex': (C.c_int, [_P, _P, _PtrArr6, _PtrArr6, _PtrArr6, _I32Arr6, _F64Arr6, C.c_double,
+                                        C.c_double, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
+                                        C.POINTER(Settings), C.POINTER(ForwardState), _P, C.c_uint32]),
+    'fgs_join_deferred': (C.c_int, [_P]),
+    'fgs_debug_set_deferred_ctas_per_sm': (None, [C.c_int32]),
     'fgs_inference': (C.c_int, [ResizeFn, _P, _P, _P] + [_P] * 9 + [_P, C.c_int32, C.POINTER(Settings), C.c_int32,
                                                                       C.c_int32, _P]),
     'fgs_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_int32, C.c_double, C.c_double, C.c_double,

@@ -36,7 +36,9 @@ RowTensor = _capi.RowTensor
 
 
 def _stream() -> int:
-    return _capi.current_stream()
+    s = _capi.current_stream()
+    _capi.load().fgs_join_deferred(s)  # these operators move sh_rest and its moments: a pending deferred update comes first
+    return s
 
 
 def _check(t: torch.Tensor, name: str) -> torch.Tensor:

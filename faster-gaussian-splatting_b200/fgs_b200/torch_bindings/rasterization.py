@@ -62,11 +62,12 @@ class _RasterizeFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx: Any, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
-                densification_info, rasterizer_settings: RasterizerSettings, optimizer) -> torch.Tensor:
+                densification_info, rasterizer_settings: RasterizerSettings, optimizer, defer_sh: bool = False) -> torch.Tensor:
         (image, primitive_buffers, tile_buffers, instance_buffers, _bucket_buffers,
-         n_instances, _n_buckets, _selector) = _C.forward(
+         n_instances, _n_buckets, _selector) = _C.forward_ex(
             means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
-            *rasterizer_settings.as_tuple())
+            *rasterizer_settings.as_tuple(), defer_color=bool(defer_sh))
+        ctx.defer_sh = bool(defer_sh)
         ctx.rasterizer_settings = rasterizer_settings
         ctx.n_instances = n_instances
         ctx.params = (means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest)
@@ -94,8 +95,8 @@ class _RasterizeFused(torch.autograd.Function):
                          [s['exp_avg'] for s in states], [s['exp_avg_sq'] for s in states],
                          [s['step'] for s in states], [g['lr'] for g in groups], betas[0], betas[1], eps,
                          primitive_buffers, tile_buffers, instance_buffers,
-                         *ctx.rasterizer_settings.as_tuple(), ctx.n_instances)
-        return (None,) * 9
+                         *ctx.rasterizer_settings.as_tuple(), ctx.n_instances, defer_rest=ctx.defer_sh)
+        return (None,) * 10
 
 
 def diff_rasterize(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
@@ -105,9 +106,15 @@ def diff_rasterize(means, scales, rotations, opacities, sh_coefficients_0, sh_co
 
 
 def diff_rasterize_fused(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
-                         densification_info, rasterizer_settings: RasterizerSettings, optimizer) -> torch.Tensor:
+                         densification_info, rasterizer_settings: RasterizerSettings, optimizer,
+                         defer_sh: bool = False) -> torch.Tensor:
+    """`defer_sh=True`: the deferred SH schedule (include/fgs_b200.h) -- identical parameters and moments after the
+    step, but the Adam update of sh_coefficients_rest runs on a side stream under the NEXT forward's geometry pass and
+    sorts.  Between iterations sh_coefficients_rest and its moments may still be in flight: call
+    `fgs_b200.join_deferred()` before reading or writing them with anything but this package's operators (checkpoints,
+    densification with plain torch ops, ...)."""
     return _RasterizeFused.apply(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
-                                 densification_info, rasterizer_settings, optimizer)
+                                 densification_info, rasterizer_settings, optimizer, defer_sh)
 
 
 def rasterize(means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,

@@ -116,6 +116,37 @@ int fgs_inference(fgs_resize_fn resize, void* user_primitive, void* user_tile, v
                   const float* cam_position, const float* bg_color, float* image, int32_t n_primitives,
                   const fgs_settings* settings, int32_t to_chw, int32_t clamp_output, void* stream);
 
+/* ---- deferred SH schedule (no reference counterpart; same results as fgs_forward / fgs_backward_adam) -----------------
+ * The SH coefficients (sh0, sh_rest: 192 of the 236 parameter bytes of a Gaussian, with their Adam moments three quarters of
+ * the optimizer's HBM traffic) are only needed late in the forward -- to colour the visible Gaussians -- while the front of
+ * the forward (projection, both sorts, instance generation) is latency-bound and leaves HBM idle.  Two flags move the SH
+ * work under that front:
+ *   fgs_backward_adam_ex(..., FGS_DEFER_SH_REST): the fused backward + Adam updates means / scales / rotations / opacities /
+ *     sh0 on `stream` as usual; the Adam update of sh_rest (gradient rebuilt from the view direction and dL/dcolour the
+ *     backward leaves behind) runs on a low-priority side stream of the library and is "pending" afterwards.
+ *     `grad2d_scratch` and `primitive_buffers` must stay allocated until the pending update has been joined.
+ *   fgs_forward_ex(..., FGS_DEFER_COLOR, color_wait_event): geometry pass without SH, colours evaluated by a separate kernel
+ *     after the tile sort; the pending update (and `color_wait_event`, an optional cudaEvent_t -- e.g. the arrival of the
+ *     coefficients from a peer GPU) is waited for only there.
+ * Every other entry point that reads or writes the coefficients joins a pending update first; code outside the library that
+ * touches sh_rest or its moments calls fgs_join_deferred(stream) before (stream-ordered, no host wait). */
+#define FGS_DEFER_COLOR 1u
+#define FGS_DEFER_SH_REST 1u
+int fgs_forward_ex(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
+                   const float* scales, const float* rotations, const float* opacities, const float* sh_coefficients_0,
+                   const float* sh_coefficients_rest, const float* w2c, const float* cam_position, const float* bg_color,
+                   float* image, int32_t n_primitives, const fgs_settings* settings, void* stream,
+                   fgs_forward_state* state_out, uint32_t flags, void* color_wait_event);
+int fgs_backward_adam_ex(const float* grad_image, const float* image, float* const params[6], float* const exp_avg[6],
+                         float* const exp_avg_sq[6], const int32_t step[6], const double lr[6], double beta1, double beta2,
+                         double eps, const float* w2c, const float* cam_position, const float* bg_color,
+                         const char* primitive_buffers, const char* tile_buffers, const char* instance_buffers,
+                         void* grad2d_scratch, float* densification_info, int32_t n_primitives,
+                         const fgs_settings* settings, const fgs_forward_state* state, void* stream, uint32_t flags);
+int fgs_join_deferred(void* stream);
+/* CTAs per SM of the deferred update kernel (default 2): how much of the machine it may take from the forward it runs under */
+void fgs_debug_set_deferred_ctas_per_sm(int32_t ctas);
+
 /* adam.h:7-16 -- one dense Adam step on one tensor of n_elements floats. */
 int fgs_adam_step(const float* param_grad, float* param, float* exp_avg, float* exp_avg_sq,
                   size_t n_elements, int32_t step_count, double learning_rate, double beta1, double beta2,

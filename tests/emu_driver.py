@@ -57,7 +57,7 @@ def settings_struct(st, total_rest):
                           float(st[9]), float(st[10]), float(st[11]), int(bool(st[12])))
 
 
-def forward(lib, params, st, training=True, to_chw=True, clamp=False):
+def forward(lib, params, st, training=True, to_chw=True, clamp=False, defer_color=False):
     """params: six tensors (means, scales, rotations, opacities, sh0, sh_rest); st: RasterizerSettings tuple.
     Returns (image, state, scratch, inputs) -- keep `scratch` and `inputs` alive for the backward."""
     p = [None if t is None else _copy_aligned(_f32(t)) for t in params]  # rotations None: covariance-input mode
@@ -70,7 +70,10 @@ def forward(lib, params, st, training=True, to_chw=True, clamp=False):
     sc = Scratch()
     state = _capi.ForwardState()
     ptr = lambda a: None if a is None else a.ctypes.data
-    if training:
+    if training and defer_color:
+        rc = lib.fgs_forward_ex(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), n, C.byref(s), None,
+                                C.byref(state), 1, None)
+    elif training:
         rc = lib.fgs_forward(sc.cb, 1, 2, 3, *[ptr(a) for a in p], ptr(w2c), ptr(pos), ptr(bg), ptr(image), n, C.byref(s), None,
                              C.byref(state))
     else:
@@ -96,18 +99,20 @@ def backward(lib, image, grad_image, state, sc, inp, densification_info=None):
 
 
 def backward_adam(lib, image, grad_image, state, sc, inp, moments_m, moments_v, steps, lrs, betas=(0.9, 0.999), eps=1e-15,
-                  densification_info=None):
-    """fgs_backward_adam: updates inp['p'] (parameters) and the moment arrays in place."""
+                  densification_info=None, defer_rest=False):
+    """fgs_backward_adam (or fgs_backward_adam_ex with FGS_DEFER_SH_REST): updates inp['p'] (parameters) and the moment
+    arrays in place.  On the emulator the side stream is synchronous: the deferred kernel has run when the call returns."""
     p, n = inp['p'], inp['n']
     gi = _copy_aligned(_f32(grad_image))
     scratch2d = _aligned(lib.fgs_grad2d_scratch_bytes(n))
     ptr = lambda a: a.ctypes.data
     arr = lambda ts: (C.c_void_p * 6)(*[ptr(t) for t in ts])
     dens = ptr(densification_info) if densification_info is not None else None
-    rc = lib.fgs_backward_adam(ptr(gi), ptr(image), arr(p), arr(moments_m), arr(moments_v), (C.c_int32 * 6)(*steps),
-                               (C.c_double * 6)(*lrs), betas[0], betas[1], eps, ptr(inp['w2c']), ptr(inp['pos']), ptr(inp['bg']),
-                               ptr(sc.buf[1]), ptr(sc.buf[2]), ptr(sc.buf[3]), ptr(scratch2d), dens, n, C.byref(inp['s']),
-                               C.byref(state), None)
+    args = (ptr(gi), ptr(image), arr(p), arr(moments_m), arr(moments_v), (C.c_int32 * 6)(*steps),
+            (C.c_double * 6)(*lrs), betas[0], betas[1], eps, ptr(inp['w2c']), ptr(inp['pos']), ptr(inp['bg']),
+            ptr(sc.buf[1]), ptr(sc.buf[2]), ptr(sc.buf[3]), ptr(scratch2d), dens, n, C.byref(inp['s']),
+            C.byref(state), None)
+    rc = lib.fgs_backward_adam_ex(*args, 1) if defer_rest else lib.fgs_backward_adam(*args)
     assert rc == 0, lib.fgs_last_error()
 
 

@@ -126,6 +126,45 @@ def test_emulated_fused_backward_adam_equals_backward_then_step_and_reference(em
         assert util.rel_err(tt(np.array(mb[t])), tt(mc[t])) <= 1e-4 and util.rel_err(tt(np.array(vb[t])), tt(vc[t])) <= 1e-3, k
 
 
+def test_emulated_deferred_sh_schedule_equals_fused_step(emu):
+    """The deferred SH schedule (fgs_forward_ex FGS_DEFER_COLOR + fgs_backward_adam_ex FGS_DEFER_SH_REST: geometry pass
+    without SH, colour kernel after the sorts, sh_rest Adam in its own kernel) gives the image and, after three steps over
+    three views, the parameters and moments of the plain fused path -- for full and partial SH degrees."""
+    from fgs_b200 import synthetic as syn
+    E, lib = emu
+    for bases, n in ((16, 300), (4, 150), (9, 97)):
+        sc = syn.make_scene(n, 11)
+        results = []
+        for deferred in (False, True):
+            params = [t.clone() for t in sc]
+            m = v = None
+            imgs = []
+            for step in (1, 2, 3):
+                cam = syn.make_camera(step, 80, 60)
+                st = util.settings_for(cam, active_sh_bases=bases, bg=(0.1, 0.3, 0.2))
+                gi = syn.make_grad_image(80, 60, seed=step)
+                img, state, scr, inp = E.forward(lib, params, st, defer_color=deferred)
+                if m is None:
+                    m = [E._copy_aligned(np.zeros_like(a)) for a in inp['p']]
+                    v = [E._copy_aligned(np.zeros_like(a)) for a in inp['p']]
+                E.backward_adam(lib, img, gi, state, scr, inp, m, v, [step] * 6, LRS, defer_rest=deferred)
+                assert lib.fgs_join_deferred(None) == 0
+                imgs.append(np.array(img))
+                params = [torch.from_numpy(np.array(a)) for a in inp['p']]
+            results.append((imgs, params, [np.array(a) for a in m], [np.array(a) for a in v]))
+        (ia, pa, ma, va), (ib, pb, mb, vb) = results
+        for a, b in zip(ia, ib):
+            assert np.abs(a - b).max() <= 1e-6, bases
+        for t, k in enumerate(NAMES):
+            tt = torch.from_numpy
+            assert util.rel_err(pb[t] - sc.params()[t], pa[t] - sc.params()[t]) <= 2e-3, (bases, k)
+            assert util.rel_err(tt(mb[t]), tt(ma[t])) <= 1e-4 and util.rel_err(tt(vb[t]), tt(va[t])) <= 1e-3, (bases, k)
+        # sh_rest itself is independent of the float-atomic order only through dL/dcolour: same bound; its inactive bases
+        # never move (zero gradient, zero moments)
+        if bases < 16:
+            assert float(np.abs(mb[5][:, bases - 1:, :]).max()) == 0.0
+
+
 def test_emulated_speculative_capacity_paths(emu):
     """Cold call (no hint), a hint that is too small (checked re-run) and the normal path give the same image."""
     from fgs_b200 import synthetic as syn

@@ -197,3 +197,55 @@ def test_alternating_resolutions_and_devices_keep_their_own_state(cuda_device):
         with torch.cuda.device(d):
             # every (device, shape, training/inference) class starts cold exactly once; afterwards its own hint fits
             assert lib.fgs_debug_get_forward_reruns() == reruns0[d], 'a forward re-ran its speculative tail'
+
+
+def test_deferred_sh_schedule_equals_fused_step(cuda_device):
+    """diff_rasterize_fused(..., defer_sh=True): geometry pass without SH + colour kernel after the sorts + sh_rest Adam on
+    the library's side stream.  Six training steps over different views give the images, parameters and moments of the
+    plain fused path; inference renders, pruning scores and torch ops in between see a consistent sh_rest (joins)."""
+    import fgs_b200
+    from fgs_b200 import synthetic as syn
+    n, w, h = 200_000, 960, 540
+    sc = syn.make_scene(n, 3, width=960).to('cuda')
+    lrs = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4]
+    cams = [syn.make_camera(k, w, h) for k in range(6)]
+    gis = [(syn.make_grad_image(w, h, seed=k) / (3 * w * h)).cuda() for k in range(6)]
+
+    def run(defer):
+        params = [p.clone().requires_grad_(True) for p in sc]
+        opt = fgs_b200.FusedAdam([{'params': [p], 'lr': lr} for p, lr in zip(params, lrs)], lr=0.0, eps=1e-15)
+        imgs, extra = [], []
+        for k in range(6):
+            rs = fgs_b200.RasterizerSettings(*util.settings_for(cams[k], device='cuda'))
+            img = fgs_b200.diff_rasterize_fused(*params, torch.empty(0), rs, opt, defer_sh=defer)
+            img.backward(gis[k])
+            opt.step()
+            opt.zero_grad()
+            imgs.append(img.detach())
+            if k == 2:  # an evaluation render and pruning scores in the middle of training: both read sh_rest
+                with torch.no_grad():
+                    det = [p.detach() for p in params]
+                    extra.append(fgs_b200.rasterize(*det, rs, to_chw=True))
+                    scores = torch.zeros(n, device='cuda')
+                    fgs_b200.update_pruning_scores(scores, *det, rs)
+                    extra.append(scores)
+            if k == 4:  # a plain torch read of sh_rest: the documented protocol is to join first
+                fgs_b200.join_deferred()
+                extra.append(params[5].detach().abs().sum().reshape(1))
+        fgs_b200.join_deferred()
+        torch.cuda.synchronize()
+        return imgs, [p.detach() for p in params], [opt.state[p]['exp_avg'] for p in params], [opt.state[p]['exp_avg_sq'] for p in params], extra
+
+    ia, pa, ma, va, xa = run(False)
+    ib, pb, mb, vb, xb = run(True)
+    for k, (a, b) in enumerate(zip(ia, ib)):
+        assert (a - b).abs().mean().item() <= 1e-6, k
+    for name, p0, a, b in zip(NAMES, sc, pa, pb):
+        assert util.rel_err(b - p0, a - p0) <= 2e-3, (name, util.rel_err(b - p0, a - p0))  # Adam's first steps are sign-like in g
+    for name, a, b in zip(NAMES, ma, mb):
+        assert util.rel_err(b, a) <= 1e-4, (name, util.rel_err(b, a))
+    for name, a, b in zip(NAMES, va, vb):
+        assert util.rel_err(b, a) <= 1e-3, (name, util.rel_err(b, a))
+    assert (xa[0] - xb[0]).abs().mean().item() <= 1e-6
+    assert util.rel_err(xb[1], xa[1]) <= 1e-3
+    assert util.rel_err(xb[2], xa[2]) <= 1e-5
