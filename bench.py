@@ -48,7 +48,7 @@ CONFIGS = {
     'c5': dict(n=500_000, w=1920, h=1080, metric='train_iters_per_sec_500k_4d_gaussians_1080p',
                workload='configs[4]: FasterGS4D shape, 500k 4D Gaussians x 150 time steps, 1920x1080, 16 SH bases'),
 }
-DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc')
+DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc', 'peer-rows', 'peer-rows-sync')
 
 
 def peak_hbm_gbs():
@@ -201,11 +201,17 @@ def run_gpu(args, impl):
     # ---- how the step ends: who sums the gradients and who applies Adam ------------------------------------------
     dp_mode = args.dp_mode if (dist is not None and mine) else 'none'
     if dp_mode == 'auto':
-        dp_mode = 'peer-mc'
+        # one view per rank and step: compact gradient exchange + sh_rest broadcast under the next forward; several
+        # views per rank (gradient accumulation): the plain one-kernel reduce + Adam + broadcast
+        dp_mode = 'peer-rows' if vpr == 1 else 'peer'
     opt_obj = None  # PeerAdam / ShardedAdam own flat parameter + gradient buffers
-    if dp_mode in ('peer', 'peer-mc'):
+    if dp_mode in ('peer', 'peer-mc', 'peer-rows', 'peer-rows-sync'):
+        if dp_mode.startswith('peer-rows') and vpr != 1:
+            raise SystemExit('bench.py: --dp-mode peer-rows needs one view per rank and step')
         try:
-            opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=(dp_mode == 'peer-mc'))
+            opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=(dp_mode == 'peer-mc'),
+                                        compact=dp_mode.startswith('peer-rows'), active_sh_bases=SH_BASES,
+                                        overlap_sh_broadcast=(dp_mode == 'peer-rows'))
         except Exception as e:  # no symmetric memory / no NVLS on this box: NCCL collectives instead, and say so
             if args.dp_mode != 'auto':
                 raise
@@ -491,6 +497,11 @@ def run_gpu(args, impl):
     if use_fused:
         opt_path = 'fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' + (
             '; deferred SH schedule: sh_rest Adam on a side stream under the next forward\'s geometry pass + sorts' if defer_sh else '')
+    elif dp_mode.startswith('peer-rows'):
+        opt_path = ('backward into a symmetric-memory gradient buffer (no sh_rest gradient), then ONE kernel over NVLink peer memory: '
+                    'compact gradient sum (14 of 59 floats per Gaussian; sh_rest gradients rebuilt by the owner) + Adam on the rank\'s '
+                    'Gaussians + broadcast' + ('; sh_rest parameters broadcast by copy engines under the next forward\'s geometry pass'
+                                               if dp_mode == 'peer-rows' else ''))
     elif dp_mode in ('peer', 'peer-mc'):
         opt_path = ('backward into a symmetric-memory gradient buffer, then ONE kernel: gradient sum over the ranks + Adam on the '
                     'rank\'s 1/W slice + parameter broadcast (' + ('NVLS multimem.ld_reduce / multimem.st' if opt_obj.multicast else 'NVLink peer loads / stores') + ')')

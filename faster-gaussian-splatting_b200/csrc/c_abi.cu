@@ -333,13 +333,23 @@ int next_capacity_hint(int n_instances, int current) {
     return want > 0x7fffffffLL ? 0x7fffffff : (int)want;
 }
 
+// deferred-colour forward (fgs_forward_ex): what the colour kernel needs, and the event it additionally waits for
+struct DeferredColor {
+    bool on;
+    const float* means;
+    const float* sh0;
+    const float* sh_rest;
+    cudaEvent_t wait;
+    int n;
+};
+
 // everything after the offsets scan: instances, tile sort, ranges + record gather, blend.  `capacity` is the
 // number of instances the instance buffers are sized for (>= the true count, or the caller re-runs this).
 template <typename KeyT>
 int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl, const TileLayout& tl,
                    const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit, const Cam& cam,
                    float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
-                   const float4* colors) {
+                   const DeferredColor& dc) {
     InstanceLayout<KeyT> sizing(nullptr, capacity, end_bit);
     char* blob = resize(user_instance, sizing.bytes);
     if (!blob) return fail_arg("instance buffer resize callback returned NULL");
@@ -360,6 +370,16 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
                                        capacity, end_bit, il.hist, il.lookback, pl.counters + kCtrTicket0 + 5,
                                        &in_alt, /*zero_scratch=*/false, /*pass0_hist=*/il.hist, 1, stream),
                 "tile sort");
+        const float4* colors = nullptr;
+        if (dc.on) {
+            // the SH coefficients are only needed from here on: wait for whoever still writes them (the deferred Adam
+            // update of the previous step on this device; `dc.wait`: e.g. their broadcast from a peer GPU), then colour
+            // the visible Gaussians
+            FGS_TRY(join_deferred(stream), "join deferred update");
+            if (dc.wait) FGS_TRY(cudaStreamWaitEvent(stream, dc.wait, 0), "wait for the colour event");
+            FGS_KERNEL(launch_color(dc.means, dc.sh0, dc.sh_rest, pl.n_touched, pl.colors, dc.n, cam, stream), "color");
+            colors = pl.colors;
+        }
         FGS_KERNEL(launch_ranges_and_gather<KeyT>(il.keys[in_alt ? 1 : 0], il.vals[in_alt ? 1 : 0], pl.recs, il.inst_recs,
                                                tl.ranges, pl.counters + kCtrInstances, capacity, cam.grid_w, stream, colors),
                 "ranges_and_gather");
@@ -384,11 +404,11 @@ int finish_forward(fgs_resize_fn resize, void* user_instance, const PrimitiveLay
 int finish_forward_any(bool keys16, fgs_resize_fn resize, void* user_instance, const PrimitiveLayout& pl,
                        const TileLayout& tl, const uint32_t* sorted_idx, int n, int capacity, int n_tiles, int end_bit,
                        const Cam& cam, float* image, bool training, bool to_chw, bool clamp_output, cudaStream_t stream,
-                       const float4* colors) {
+                       const DeferredColor& dc) {
     return keys16 ? finish_forward<uint16_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                             image, training, to_chw, clamp_output, stream, colors)
+                                             image, training, to_chw, clamp_output, stream, dc)
                   : finish_forward<uint32_t>(resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                             image, training, to_chw, clamp_output, stream, colors);
+                                             image, training, to_chw, clamp_output, stream, dc);
 }
 
 int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, void* user_instance, const float* means,
@@ -450,20 +470,19 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
     // Launch the rest with the capacity the previous forward suggested, and only then look at this forward's
     // own count (the read-back has long completed by then).  No suggestion yet: wait for the count first.
     const bool keys16 = end_bit <= 16;
-    const float4* colors = nullptr;
-    if (defer_color) {
-        // the SH coefficients are only needed from here on: wait for whoever still writes them (the deferred Adam update of
-        // the previous step on this device; `color_wait`: e.g. their broadcast from a peer GPU), then evaluate the colours
-        FGS_TRY(join_deferred(stream), "join deferred update");
-        if (color_wait) FGS_TRY(cudaStreamWaitEvent(stream, color_wait, 0), "wait for the colour event");
-        FGS_KERNEL(launch_color(means, sh0, sh_rest, pl.n_touched, pl.colors, n, cam, stream), "color");
-        colors = pl.colors;
-    }
+    // deferred colour: evaluated inside finish_forward, between the tile sort and the record gather -- as late as possible
+    DeferredColor dc{};
+    dc.on = defer_color;
+    dc.means = means;
+    dc.sh0 = sh0;
+    dc.sh_rest = sh_rest;
+    dc.wait = color_wait;
+    dc.n = n;
     const int hinted = hints.get(n_tiles, n, training);
     int capacity = hinted;
     if (capacity > 0) {
         const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                          image, training, to_chw, clamp_output, stream, colors);
+                                          image, training, to_chw, clamp_output, stream, dc);
         if (rc != 0) return rc;
     }
     FGS_TRY(cudaEventSynchronize(rb.event), "count read-back wait");
@@ -483,7 +502,7 @@ int forward_impl(fgs_resize_fn resize, void* user_primitive, void* user_tile, vo
         }
         capacity = n_instances;
         const int rc = finish_forward_any(keys16, resize, user_instance, pl, tl, sorted_idx, n, capacity, n_tiles, end_bit, cam,
-                                          image, training, to_chw, clamp_output, stream, colors);
+                                          image, training, to_chw, clamp_output, stream, dc);
         if (rc != 0) return rc;
     }
     hints.put(n_tiles, n, training, next_capacity_hint(n_instances, hinted));

@@ -150,6 +150,208 @@ __global__ void __launch_bounds__(kPeerBlock) peer_adam_kernel(const PeerAdamArg
     }
 }
 
+// ---- row-sliced variant with a COMPACT gradient exchange (fgs_peer_adam_rows_step) ------------------------------------
+// One view per rank and step.  The sh_rest gradient of a view is rank-1 per Gaussian: dL/dsh_rest[k] = Y_k(dir) * dL/dcolour
+// (sh_utils.cuh:85-153), and dL/dsh0 = C0 * dL/dcolour is in the exchange anyway.  So the 45 sh_rest floats of every peer
+// are never read: the owner of a Gaussian rebuilds each peer's contribution from that peer's sh0 gradient (3 floats), the
+// peer's camera position (a 4-float slot at the end of its gradient buffer) and the Gaussian's mean -- 14 instead of 59
+// floats per Gaussian and peer cross NVLink.  Ranks own ROWS (Gaussians), not float4 ranges, so that a warp sees whole
+// Gaussians; the new sh_rest parameters are optionally kept local (`broadcast_rest` = 0) for the caller to broadcast on a
+// side stream while the next forward's geometry pass runs (fgs_b200.parallel.PeerAdam(compact=True)).
+constexpr int kRowsBlock = 128;
+constexpr int kRowsWarps = kRowsBlock / 32;
+constexpr int kRowsWarpFloats = 32 * 45 + FGS_MAX_PEERS * 96 + 96;  // staged sh_rest gradient, per-peer sh0 gradients, their sum
+
+struct PeerRowsArgs {
+    const float* grads[FGS_MAX_PEERS];
+    float* params[FGS_MAX_PEERS];
+    float* exp_avg;
+    float* exp_avg_sq;
+    uint32_t off[6];        // float offset of tensor t inside the flat buffers
+    uint32_t kf[6];         // floats per row of tensor t (3, 3, 4, 1, 3, 3 * n_rest)
+    uint32_t shard_off[6];  // float offset of tensor t inside the moment shards
+    uint32_t cam_off;       // float offset of the camera-position slot inside every gradient buffer
+    uint32_t row_begin, row_count;
+    int active_bases;
+    int broadcast_rest;
+    float step_size[6];
+    float b2[6];
+    float beta1, beta2, eps;
+    int world, rank;
+};
+
+constexpr float kShC0 = 0.28209479177387814f;
+constexpr float kShC1 = 0.48860251190291987f;
+constexpr float kShC2a = 1.0925484305920792f, kShC2b = 0.94617469575755997f, kShC2c = 0.31539156525251999f,
+                kShC2d = 0.54627421529603959f;
+constexpr float kShC3a = 0.59004358992664352f, kShC3b = 1.7701307697799304f, kShC3c = 2.8906114426405538f,
+                kShC3d = 0.45704579946446572f, kShC3e = 2.2852289973223288f, kShC3f = 1.865881662950577f,
+                kShC3g = 1.1195289977703462f, kShC3h = 1.4453057213202769f;
+
+// Y_1 .. Y_15 of a unit direction: the expressions of the backward kernel (preprocess_backward.cu, sh_utils.cuh:32-69)
+__device__ __forceinline__ void peer_sh_basis(float x, float y, float z, int active_bases, float* __restrict__ Y) {
+#pragma unroll
+    for (int k = 0; k < 15; ++k) Y[k] = 0.f;
+    if (active_bases > 1) {
+        Y[0] = -kShC1 * y;
+        Y[1] = kShC1 * z;
+        Y[2] = -kShC1 * x;
+        if (active_bases > 4) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+            Y[3] = kShC2a * xy;
+            Y[4] = -kShC2a * yz;
+            Y[5] = kShC2b * zz - kShC2c;
+            Y[6] = -kShC2a * xz;
+            Y[7] = kShC2d * (xx - yy);
+            if (active_bases > 9) {
+                Y[8] = y * (kShC3a * yy - kShC3b * xx);
+                Y[9] = kShC3c * xy * z;
+                Y[10] = y * (kShC3d - kShC3e * zz);
+                Y[11] = z * (kShC3f * zz - kShC3g);
+                Y[12] = x * (kShC3d - kShC3e * zz);
+                Y[13] = kShC3h * z * (xx - yy);
+                Y[14] = x * (kShC3b * yy - kShC3a * xx);
+            }
+        }
+    }
+}
+
+// One tensor's rows of the warp: gradient = sum over the peers' buffers (stage == nullptr) or the staged values; Adam with
+// the rank's moment shard; new parameters to every peer (or only to this rank's replica).
+__device__ __forceinline__ void rows_span(const PeerRowsArgs& a, int t, size_t elem0, size_t shard0, int n_floats,
+                                          const float* __restrict__ stage, bool to_all, int lane) {
+    float* m = a.exp_avg + shard0;
+    float* v = a.exp_avg_sq + shard0;
+    const float ss = a.step_size[t], b2 = a.b2[t];
+    const bool vec = (n_floats & 3) == 0 && (elem0 & 3u) == 0 && (shard0 & 3u) == 0;
+    if (vec) {
+        for (int i = lane; i < (n_floats >> 2); i += 32) {
+            float4 g;
+            if (stage) {
+                g = reinterpret_cast<const float4*>(stage)[i];
+            } else {
+                float4 gq[FGS_MAX_PEERS];
+#pragma unroll
+                for (int q = 0; q < FGS_MAX_PEERS; ++q)
+                    if (q < a.world) gq[q] = ld_peer(reinterpret_cast<const float4*>(a.grads[q] + elem0) + i);
+                g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < FGS_MAX_PEERS; ++q) {
+                    if (q < a.world) {
+                        g.x += gq[q].x;
+                        g.y += gq[q].y;
+                        g.z += gq[q].z;
+                        g.w += gq[q].w;
+                    }
+                }
+            }
+            float4 p4 = reinterpret_cast<const float4*>(a.params[a.rank] + elem0)[i];
+            float4 m4 = reinterpret_cast<const float4*>(m)[i];
+            float4 v4 = reinterpret_cast<const float4*>(v)[i];
+            adam1(g.x, p4.x, m4.x, v4.x, ss, a.beta1, a.beta2, a.eps, b2);
+            adam1(g.y, p4.y, m4.y, v4.y, ss, a.beta1, a.beta2, a.eps, b2);
+            adam1(g.z, p4.z, m4.z, v4.z, ss, a.beta1, a.beta2, a.eps, b2);
+            adam1(g.w, p4.w, m4.w, v4.w, ss, a.beta1, a.beta2, a.eps, b2);
+            reinterpret_cast<float4*>(m)[i] = m4;
+            reinterpret_cast<float4*>(v)[i] = v4;
+            if (to_all) {
+#pragma unroll
+                for (int q = 0; q < FGS_MAX_PEERS; ++q)
+                    if (q < a.world) reinterpret_cast<float4*>(a.params[q] + elem0)[i] = p4;
+            } else {
+                reinterpret_cast<float4*>(a.params[a.rank] + elem0)[i] = p4;
+            }
+        }
+    } else {
+        for (int i = lane; i < n_floats; i += 32) {
+            float g = 0.f;
+            if (stage) {
+                g = stage[i];
+            } else {
+                for (int q = 0; q < a.world; ++q) g += __ldcg(a.grads[q] + elem0 + i);
+            }
+            float pe = a.params[a.rank][elem0 + i], me = m[i], ve = v[i];
+            adam1(g, pe, me, ve, ss, a.beta1, a.beta2, a.eps, b2);
+            m[i] = me;
+            v[i] = ve;
+            if (to_all) {
+                for (int q = 0; q < a.world; ++q) a.params[q][elem0 + i] = pe;
+            } else {
+                a.params[a.rank][elem0 + i] = pe;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kRowsBlock) peer_adam_rows_kernel(const PeerRowsArgs a) {
+    FGS_DYNAMIC_SMEM(float, s_rows, 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* stage_rest = s_rows + warp * kRowsWarpFloats;
+    float* s_dcol = stage_rest + 32 * 45;          // [peer][96]
+    float* stage_sh0 = s_dcol + FGS_MAX_PEERS * 96;  // [96]
+    const int rest_floats = (int)a.kf[5];
+    const uint32_t groups = (a.row_count + 31u) >> 5;
+    for (uint32_t group = blockIdx.x * kRowsWarps + warp; group < groups; group += gridDim.x * kRowsWarps) {
+        const uint32_t r0 = a.row_begin + (group << 5);
+        const int rows = (int)min(32u, a.row_begin + a.row_count - r0);
+        const uint32_t local0 = group << 5;  // first row of the group inside this rank's slice
+        // the Gaussian's mean BEFORE this step's update: the view directions of the forward pass were computed from it
+        float3 mean = make_float3(0.f, 0.f, 0.f);
+        if (lane < rows) {
+            const float* mp = a.params[a.rank] + a.off[0] + (size_t)(r0 + lane) * 3;
+            mean = make_float3(mp[0], mp[1], mp[2]);
+        }
+        // every peer's sh0 gradient of these rows (= C0 * dL/dcolour of that peer's view), and their sum in peer order
+        for (int i = lane; i < rows * 3; i += 32) {
+            float sum = 0.f;
+            for (int q = 0; q < a.world; ++q) {
+                const float g = __ldcg(a.grads[q] + a.off[4] + (size_t)r0 * 3 + i);
+                s_dcol[q * 96 + i] = g;
+                sum += g;
+            }
+            stage_sh0[i] = sum;
+        }
+        __syncwarp();
+        // rebuild the summed sh_rest gradient of this lane's Gaussian: sum over peers of Y_k(dir_q) * dL/dcolour_q
+        if (rest_floats > 0 && lane < rows) {
+            float acc[45];
+#pragma unroll
+            for (int k = 0; k < 45; ++k) acc[k] = 0.f;
+            for (int q = 0; q < a.world; ++q) {
+                const float dr = s_dcol[q * 96 + 3 * lane] * (1.0f / kShC0);
+                const float dg = s_dcol[q * 96 + 3 * lane + 1] * (1.0f / kShC0);
+                const float db = s_dcol[q * 96 + 3 * lane + 2] * (1.0f / kShC0);
+                if (dr == 0.f && dg == 0.f && db == 0.f) continue;  // not visible in that view
+                const float* cam = a.grads[q] + a.cam_off;
+                const float rx = mean.x - __ldcg(cam), ry = mean.y - __ldcg(cam + 1), rz = mean.z - __ldcg(cam + 2);
+                const float inv_len = rsqrtf(rx * rx + ry * ry + rz * rz);
+                float Y[15];
+                peer_sh_basis(rx * inv_len, ry * inv_len, rz * inv_len, a.active_bases, Y);
+#pragma unroll
+                for (int k = 0; k < 15; ++k) {
+                    acc[3 * k] += Y[k] * dr;
+                    acc[3 * k + 1] += Y[k] * dg;
+                    acc[3 * k + 2] += Y[k] * db;
+                }
+            }
+            float* mine = stage_rest + lane * rest_floats;
+#pragma unroll
+            for (int k = 0; k < 45; ++k)
+                if (k < rest_floats) mine[k] = acc[k];
+        }
+        __syncwarp();
+        // means, scales, rotations, opacities: plain sums over the peers; sh0: the staged sum; sh_rest: the rebuilt gradient
+        for (int t = 0; t < 4; ++t)
+            rows_span(a, t, (size_t)a.off[t] + (size_t)r0 * a.kf[t], (size_t)a.shard_off[t] + (size_t)local0 * a.kf[t],
+                      rows * (int)a.kf[t], nullptr, true, lane);
+        rows_span(a, 4, (size_t)a.off[4] + (size_t)r0 * 3, (size_t)a.shard_off[4] + (size_t)local0 * 3, rows * 3, stage_sh0, true, lane);
+        if (rest_floats > 0)
+            rows_span(a, 5, (size_t)a.off[5] + (size_t)r0 * rest_floats, (size_t)a.shard_off[5] + (size_t)local0 * rest_floats,
+                      rows * rest_floats, stage_rest, a.broadcast_rest != 0, lane);
+        __syncwarp();
+    }
+}
+
 // slice of tensor t (count floats, padded to float4s) owned by `rank`: [begin4, begin4 + count4), chunk4 per rank
 void slice_of(uint64_t count, int world, int rank, uint64_t* chunk4, uint64_t* begin4, uint64_t* count4) {
     const uint64_t n4 = (count + 3) / 4;
@@ -281,6 +483,90 @@ static int peer_adam_step_impl(const float* const* peer_grads, float* const* pee
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_step: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+uint64_t fgs_peer_adam_rows_per_rank(uint64_t n_rows, int32_t world) {
+    if (world < 1) return 0;
+    const uint64_t per = (n_rows + (uint64_t)world - 1) / (uint64_t)world;
+    return (per + 31) / 32 * 32;  // multiples of 32 rows: every tensor's slice starts float4-aligned
+}
+
+int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                            float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
+                            int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
+                            const int32_t step[6], const double lr[6], double beta1, double beta2, double eps, void* stream) {
+    auto fail = [](const char* msg) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
+        return -1;
+    };
+    if (!peer_grads || !peer_params || !exp_avg_shard || !exp_avg_sq_shard || !offsets || !step || !lr)
+        return fail("fgs_peer_adam_rows_step: NULL argument");
+    if (world < 1 || world > FGS_MAX_PEERS || rank < 0 || rank >= world) return fail("fgs_peer_adam_rows_step: bad world/rank");
+    if (n_rest < 0 || n_rest > 15) return fail("fgs_peer_adam_rows_step: sh_rest must have <= 15 bases");
+    PeerRowsArgs a{};
+    for (int q = 0; q < world; ++q) {
+        if (!peer_grads[q] || !peer_params[q]) return fail("fgs_peer_adam_rows_step: NULL peer pointer");
+        if ((reinterpret_cast<uintptr_t>(peer_grads[q]) | reinterpret_cast<uintptr_t>(peer_params[q])) & 15u)
+            return fail("fgs_peer_adam_rows_step: peer buffers must be 16-byte aligned");
+        a.grads[q] = peer_grads[q];
+        a.params[q] = peer_params[q];
+    }
+    if ((reinterpret_cast<uintptr_t>(exp_avg_shard) | reinterpret_cast<uintptr_t>(exp_avg_sq_shard)) & 15u)
+        return fail("fgs_peer_adam_rows_step: moment shards must be 16-byte aligned");
+    a.exp_avg = exp_avg_shard;
+    a.exp_avg_sq = exp_avg_sq_shard;
+    const uint32_t kf[6] = {3u, 3u, 4u, 1u, 3u, 3u * (uint32_t)n_rest};
+    const uint64_t per = fgs_peer_adam_rows_per_rank(n_rows, world);
+    const uint64_t begin = (uint64_t)rank * per < n_rows ? (uint64_t)rank * per : n_rows;
+    const uint64_t end = begin + per < n_rows ? begin + per : n_rows;
+    uint64_t shard = 0;
+    for (int t = 0; t < 6; ++t) {
+        if (offsets[t] & 3u) return fail("fgs_peer_adam_rows_step: tensor offsets must be multiples of 4 floats");
+        if (offsets[t] + n_rows * kf[t] > 0xffffffffull) return fail("fgs_peer_adam_rows_step: buffers too large");
+        a.off[t] = (uint32_t)offsets[t];
+        a.kf[t] = kf[t];
+        a.shard_off[t] = (uint32_t)shard;
+        shard += per * kf[t];
+        a.step_size[t] = (float)(lr[t] / (1.0 - std::pow(beta1, (double)step[t])));
+        a.b2[t] = (float)(1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step[t])));
+    }
+    if (cam_offset > 0xffffffffull) return fail("fgs_peer_adam_rows_step: buffers too large");
+    a.cam_off = (uint32_t)cam_offset;
+    a.row_begin = (uint32_t)begin;
+    a.row_count = (uint32_t)(end - begin);
+    a.active_bases = active_sh_bases < n_rest + 1 ? active_sh_bases : n_rest + 1;
+    a.broadcast_rest = broadcast_rest;
+    a.beta1 = (float)beta1;
+    a.beta2 = (float)beta2;
+    a.eps = (float)eps;
+    a.world = world;
+    a.rank = rank;
+    if (a.row_count == 0) return 0;
+    const size_t smem = (size_t)kRowsWarps * kRowsWarpFloats * sizeof(float);
+    static int s_rows_grid[64] = {};
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0) cur_dev = 0;
+    int& grid_cap = s_rows_grid[cur_dev % 64];
+    if (grid_cap == 0) {
+        auto kf_ = peer_adam_rows_kernel;
+        if (cudaFuncSetAttribute(kf_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("fgs_peer_adam_rows_step: cannot reserve shared memory");
+        int sms = 0, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_adam_rows_kernel, kRowsBlock, smem);
+        grid_cap = (sms > 0 ? sms : 1) * (occ > 0 ? occ : 1);
+    }
+    const uint32_t groups = (a.row_count + 31u) / 32u;
+    const uint32_t want = (groups + kRowsWarps - 1) / kRowsWarps;
+    const int grid = want < (uint32_t)grid_cap ? (int)want : grid_cap;
+    auto k = peer_adam_rows_kernel;
+    FGS_LAUNCH_SMEM(k, dim3((unsigned)grid), dim3(kRowsBlock), smem, reinterpret_cast<cudaStream_t>(stream), a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_rows_step: %s", cudaGetErrorString(e));
         return (int)e;
     }
     return 0;

@@ -149,21 +149,27 @@ def _backward_common(image, primitive_buffers, w2c, cam_position, bg_color, grad
 
 
 _grad_outputs = None
+_camera_out = None
 
 
-def set_gradient_outputs(tensors) -> None:
+def set_gradient_outputs(tensors, camera_out=None) -> None:
     """Where `backward` writes the six gradients: None (default) = freshly allocated tensors, as the reference does
     (rasterization_api.cu:127-134); or six preallocated contiguous CUDA float tensors of the parameters' shapes,
     e.g. views of a symmetric-memory buffer that peer GPUs read (fgs_b200.parallel.PeerAdam).  The returned
-    gradients ARE these tensors (autograd then stores them as .grad without a copy)."""
-    global _grad_outputs
+    gradients ARE these tensors (autograd then stores them as .grad without a copy).  The sixth entry (sh_rest) may be
+    None: that gradient is then not computed at all and `None` is returned for it (compact view-parallel exchange).
+    `camera_out`: a 3-float CUDA tensor that receives the view's camera position at every backward."""
+    global _grad_outputs, _camera_out
     if tensors is not None:
         tensors = list(tensors)
         if len(tensors) != 6:
             raise ValueError('set_gradient_outputs: six tensors expected (means, scales, rotations, opacities, sh0, sh_rest)')
-        for t in tensors:
+        for i, t in enumerate(tensors):
+            if t is None and i == 5:
+                continue
             _check_param(t, 'gradient output')
     _grad_outputs = tensors
+    _camera_out = camera_out if tensors is not None else None
 
 
 def backward(densification_info, grad_image, image, means, scales, rotations, opacities, sh_coefficients_rest,
@@ -184,12 +190,16 @@ def backward(densification_info, grad_image, image, means, scales, rotations, op
         else:
             # fresh tensor objects over the same memory: autograd adopts a gradient as .grad without a copy only if
             # nobody else holds a reference to the object it was handed
-            outs = [t.view(t.shape) for t in _grad_outputs]
+            outs = [None if t is None else t.view(t.shape) for t in _grad_outputs]
             grads, g_sh0, g_rest = outs[:4], outs[4], outs[5]
+            if _camera_out is not None:
+                _camera_out.copy_(pos_c.reshape(-1)[:3])
             if rotations is None:
                 raise RuntimeError('set_gradient_outputs is not available in covariance-input mode')
             shapes = [tuple(p.shape) for p in (means, scales, rotations, opacities)] + [(n, 1, 3), tuple(sh_coefficients_rest.shape)]
             for t, shape in zip(_grad_outputs, shapes):
+                if t is None:
+                    continue
                 if tuple(t.shape) != shape or t.device != dev:
                     raise RuntimeError(f'gradient output has shape {tuple(t.shape)} on {t.device}, expected {shape} on {dev}')
         scratch = torch.empty(_lib.fgs_grad2d_scratch_bytes(n), dtype=torch.uint8, device=dev)

@@ -164,10 +164,19 @@ class PeerAdam:
     rasterizer's backward writes its gradients straight into the symmetric gradient buffer."""
 
     def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
-                 group=None, multicast: bool | str = 'auto') -> None:
+                 group=None, multicast: bool | str = 'auto', compact: bool = False, active_sh_bases: int = 16,
+                 overlap_sh_broadcast: bool = True) -> None:
         """`multicast`: True = reduce and broadcast inside the NVSwitch through the buffers' multicast addresses
         (multimem.ld_reduce / multimem.st, fgs_peer_adam_step_multicast), False = W peer loads / stores per element,
-        'auto' = multicast when the symmetric-memory handles expose a multicast address."""
+        'auto' = multicast when the symmetric-memory handles expose a multicast address.
+
+        `compact` (one view per rank and step): ranks own Gaussians (rows) and the peers' sh_rest gradients are never
+        exchanged -- the owner rebuilds them from the peers' sh0 gradients and camera positions
+        (fgs_peer_adam_rows_step): 14 instead of 59 floats per Gaussian and peer.  The backward then does not even write
+        the sh_rest gradient (`p.grad` of sh_rest stays None).  With `overlap_sh_broadcast` the new sh_rest parameters
+        (three quarters of the parameter bytes) travel to the peers on a side stream, by copy engines, while the next
+        forward's geometry pass and sorts run; that forward must be `forward_settings()`-aware: pass
+        `color_event=opt.sh_ready` and `defer_color=True` (fgs_b200.parallel.diff_rasterize_dp does)."""
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -182,8 +191,9 @@ class PeerAdam:
         self.shapes = [tuple(t.shape) for t in tensors]
         self.offsets, self.counts, total = peer_layout(self.shapes)
         self.lrs, self.betas, self.eps, self.steps = [float(x) for x in lrs], betas, float(eps), 0
+        self._cam_off = total  # 4 floats behind the six gradient regions: this rank's camera position (compact exchange)
         self._pbuf = symm.empty(total, dtype=torch.float32, device=dev)
-        self._gbuf = symm.empty(total, dtype=torch.float32, device=dev)
+        self._gbuf = symm.empty(total + 4, dtype=torch.float32, device=dev)
         self._pbuf.zero_()
         self._gbuf.zero_()
         self._ph = symm.rendezvous(self._pbuf, self.group.group_name)
@@ -194,7 +204,18 @@ class PeerAdam:
                 view(self._pbuf, i).copy_(t)
         self.params = [view(self._pbuf, i).requires_grad_(True) for i in range(6)]
         self.grads = [view(self._gbuf, i) for i in range(6)]
-        shard = int(self._lib.fgs_peer_adam_shard_floats((C.c_uint64 * 6)(*self.counts), self.world))
+        self.compact, self.active_sh_bases = bool(compact), int(active_sh_bases)
+        self.overlap_sh_broadcast = bool(overlap_sh_broadcast) and self.compact and self.world > 1
+        self.n_rows = int(self.shapes[0][0])
+        self.n_rest = int(self.shapes[5][1]) if len(self.shapes[5]) > 1 else 0
+        if self.compact:
+            row_floats = [3, 3, 4, 1, 3, 3 * self.n_rest]
+            if [c for c in self.counts] != [self.n_rows * k for k in row_floats]:
+                raise ValueError('PeerAdam(compact=True): tensors must be (N,3) (N,3) (N,4) (N,1) (N,1,3) (N,R,3)')
+            self.rows_per_rank = int(self._lib.fgs_peer_adam_rows_per_rank(self.n_rows, self.world))
+            shard = self.rows_per_rank * sum(row_floats)
+        else:
+            shard = int(self._lib.fgs_peer_adam_shard_floats((C.c_uint64 * 6)(*self.counts), self.world))
         self.exp_avg = torch.zeros(shard, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(shard, dtype=torch.float32, device=dev)
         self._gptrs = (C.c_void_p * self.world)(*[int(p) for p in self._gh.buffer_ptrs])
@@ -205,12 +226,31 @@ class PeerAdam:
         if multicast and not (g_mc and p_mc):
             raise RuntimeError('PeerAdam(multicast=True): the symmetric-memory handles have no multicast address (no NVLS)')
         self.multicast, self._g_mc, self._p_mc = bool(multicast), g_mc, p_mc
-        _C.set_gradient_outputs(self.grads)
+        if self.compact:
+            self.multicast = False
+            # the backward skips the sh_rest gradient altogether and leaves the view's camera position in the slot
+            _C.set_gradient_outputs(self.grads[:5] + [None], camera_out=self._gbuf[self._cam_off:self._cam_off + 3])
+            self._side = torch.cuda.Stream(device=dev)
+            self._k1_done = torch.cuda.Event()
+            self.sh_ready = torch.cuda.Event()  # all peers' sh_rest slices have landed in this replica
+            self.sh_ready.record()
+            lo = min(self.rank * self.rows_per_rank, self.n_rows)
+            hi = min(lo + self.rows_per_rank, self.n_rows)
+            k = 3 * self.n_rest
+            self._rest_lo, self._rest_hi = self.offsets[5] + lo * k, self.offsets[5] + hi * k
+            self._peer_pbufs = [self._ph.get_buffer(q, (total,), torch.float32) for q in range(self.world)]
+            if self.overlap_sh_broadcast:  # every diff_rasterize forward from now on defers its colour kernel behind sh_ready
+                from .torch_bindings import rasterization as _rast
+                _rast.set_forward_kwargs(self.forward_kwargs)
+        else:
+            _C.set_gradient_outputs(self.grads)
         self._ph.barrier()  # every replica initialised before anyone steps
 
     def step(self) -> None:
         C = self._ctypes
-        for p, g in zip(self.params, self.grads):
+        for i, (p, g) in enumerate(zip(self.params, self.grads)):
+            if self.compact and i == 5:
+                continue  # rebuilt by the owner from the sh0 gradients
             if p.grad is None:
                 raise RuntimeError('PeerAdam.step: parameter without gradient (every rank must render a view)')
             if p.grad.data_ptr() != g.data_ptr():  # gradient produced elsewhere (e.g. a regulariser): bring it in
@@ -218,6 +258,9 @@ class PeerAdam:
         self.steps += 1
         stream = self._capi.current_stream()
         self._gh.barrier()  # stream-ordered: every rank's gradients are complete
+        if self.compact:
+            self._step_compact(stream)
+            return
         tail = (self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),
                 (C.c_uint64 * 6)(*self.counts), (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
                 float(self.betas[0]), float(self.betas[1]), self.eps, stream)
@@ -229,17 +272,58 @@ class PeerAdam:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
         self._ph.barrier()  # every rank's parameter stores have landed before the next forward reads them
 
+    def _step_compact(self, stream: int) -> None:
+        C = self._ctypes
+        overlap = self.overlap_sh_broadcast
+        rc = self._lib.fgs_peer_adam_rows_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
+                                               self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets), self.n_rows,
+                                               self.n_rest, self.active_sh_bases, self._cam_off, 0 if overlap else 1,
+                                               (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
+                                               float(self.betas[0]), float(self.betas[1]), self.eps, stream)
+        if rc != 0:
+            raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+        if overlap:
+            # this rank's slice of the new sh_rest parameters goes to the peers on the side stream (copy engines over NVLink)
+            # while the caller's stream continues with the next forward's geometry pass; `sh_ready` = all slices are here
+            self._k1_done.record()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._k1_done)
+                if self._rest_hi > self._rest_lo:
+                    src = self._pbuf[self._rest_lo:self._rest_hi]
+                    for q in range(self.world):
+                        if q != self.rank:
+                            self._peer_pbufs[q][self._rest_lo:self._rest_hi].copy_(src, non_blocking=True)
+                self._ph.barrier(channel=1)
+                self.sh_ready.record()
+        self._ph.barrier()  # the geometry parameters (and sh0) of every rank's slice have landed everywhere
+        if not overlap:
+            self.sh_ready.record()
+
+    def forward_kwargs(self) -> dict:
+        """Keyword arguments for `_C.forward_ex` / `diff_rasterize_dp` of the NEXT forward: with the overlapped sh_rest
+        broadcast its colour kernel has to wait for `sh_ready`."""
+        if self.compact and self.overlap_sh_broadcast:
+            return {'defer_color': True, 'color_event': self.sh_ready}
+        return {}
+
     def zero_grad(self) -> None:
         for p in self.params:
             p.grad = None
 
     def reset(self) -> None:
         """Fresh optimizer state (moments and step count); the parameters are left alone."""
+        if self.compact:
+            torch.cuda.current_stream().wait_event(self.sh_ready)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.steps = 0
 
     def close(self) -> None:
+        if self.compact:
+            torch.cuda.current_stream().wait_event(self.sh_ready)
+            if self.overlap_sh_broadcast:
+                from .torch_bindings import rasterization as _rast
+                _rast.set_forward_kwargs(None)
         self._C.set_gradient_outputs(None)
 
 

@@ -31,14 +31,26 @@ class RasterizerSettings(NamedTuple):
         return tuple(self)
 
 
+_forward_kwargs = None
+
+
+def set_forward_kwargs(provider) -> None:
+    """`provider()` -> keyword arguments of `_C.forward_ex` for every following `diff_rasterize` forward (None: plain
+    forward).  Used by the view-parallel optimizer whose sh_rest parameters arrive from the peer GPUs while the forward's
+    geometry pass already runs (fgs_b200.parallel.PeerAdam(compact=True)): {'defer_color': True, 'color_event': ...}."""
+    global _forward_kwargs
+    _forward_kwargs = provider
+
+
 class _Rasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx: Any, means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
                 densification_info, rasterizer_settings: RasterizerSettings) -> torch.Tensor:
+        kwargs = _forward_kwargs() if _forward_kwargs is not None else {}
         (image, primitive_buffers, tile_buffers, instance_buffers, bucket_buffers,
-         n_instances, n_buckets, selector) = _C.forward(
+         n_instances, n_buckets, selector) = _C.forward_ex(
             means, scales, rotations, opacities, sh_coefficients_0, sh_coefficients_rest,
-            *rasterizer_settings.as_tuple())
+            *rasterizer_settings.as_tuple(), **kwargs)
         ctx.rasterizer_settings = rasterizer_settings
         ctx.buffer_state = (n_instances, n_buckets, selector)
         ctx.save_for_backward(image, means, scales, rotations, opacities, sh_coefficients_rest,

@@ -300,6 +300,22 @@ int fgs_peer_adam_step_multicast(const float* grads_multicast, float* params_mul
                                  int32_t rank, float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6],
                                  const uint64_t counts[6], const int32_t step[6], const double lr[6], double beta1,
                                  double beta2, double eps, void* stream);
+/* Row-sliced variant with a compact gradient exchange (one view per rank and step): rank r owns the Gaussians
+ * [r * R, (r + 1) * R), R = fgs_peer_adam_rows_per_rank(n_rows, world) (a multiple of 32); the peers' sh_rest gradients are
+ * never read -- the owner rebuilds them from each peer's sh0 gradient (= C0 * dL/dcolour), the peer's camera position (3
+ * floats at float offset `cam_offset` of its gradient buffer, written by the caller before the barrier) and the Gaussian's
+ * mean, so 14 instead of 59 floats per Gaussian and peer cross NVLink.  `offsets[t]`: float offset of tensor t (means,
+ * scales, rotations, opacities, sh0, sh_rest; rows of 3, 3, 4, 1, 3, 3 * n_rest floats) in the flat buffers; moment shards:
+ * R * 59-ish floats, tensor after tensor.  `broadcast_rest` = 0 keeps the new sh_rest parameters in this rank's replica
+ * only: the caller copies the slice to the peers itself (e.g. on a side stream, overlapped with the next forward's
+ * geometry pass, whose colour kernel waits for it: fgs_forward_ex).  Same result as fgs_peer_adam_step up to the rounding
+ * of dL/dcolour = (C0 * dL/dcolour) / C0. */
+uint64_t fgs_peer_adam_rows_per_rank(uint64_t n_rows, int32_t world);
+int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                            float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
+                            int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
+                            const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
+                            void* stream);
 size_t fgs_peer_adam_shard_floats(const uint64_t counts[6], int32_t world);
 /* rank's slice of every tensor: first float (relative to the tensor), number of floats (padding included),
  * position of the slice's moments inside the shard arrays; any output pointer may be NULL */

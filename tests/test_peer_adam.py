@@ -122,6 +122,123 @@ def test_peer_adam_kernel_emulated_ranks(world):
         assert np.all(m_full[o + c:o + (c + 3) // 4 * 4] == 0)  # the padding of every tensor region stays zero
 
 
+def _sh_basis_np(d, active):
+    """Y_1..Y_15 of unit directions d (n,3), float32 like the kernels (sh_utils.cuh:32-69); zero beyond the active degree."""
+    import numpy as np
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    f = np.float32
+    Y = np.zeros((d.shape[0], 15), dtype=np.float32)
+    if active > 1:
+        Y[:, 0], Y[:, 1], Y[:, 2] = -f(0.48860251190291987) * y, f(0.48860251190291987) * z, -f(0.48860251190291987) * x
+    if active > 4:
+        xx, yy, zz, xy, xz, yz = x * x, y * y, z * z, x * y, x * z, y * z
+        Y[:, 3] = f(1.0925484305920792) * xy
+        Y[:, 4] = -f(1.0925484305920792) * yz
+        Y[:, 5] = f(0.94617469575755997) * zz - f(0.31539156525251999)
+        Y[:, 6] = -f(1.0925484305920792) * xz
+        Y[:, 7] = f(0.54627421529603959) * (xx - yy)
+    if active > 9:
+        Y[:, 8] = y * (f(0.59004358992664352) * yy - f(1.7701307697799304) * xx)
+        Y[:, 9] = f(2.8906114426405538) * xy * z
+        Y[:, 10] = y * (f(0.45704579946446572) - f(2.2852289973223288) * zz)
+        Y[:, 11] = z * (f(1.865881662950577) * zz - f(1.1195289977703462))
+        Y[:, 12] = x * (f(0.45704579946446572) - f(2.2852289973223288) * zz)
+        Y[:, 13] = f(1.4453057213202769) * z * (xx - yy)
+        Y[:, 14] = x * (f(1.7701307697799304) * yy - f(0.59004358992664352) * xx)
+    return Y
+
+
+@pytest.mark.parametrize('world,n,active,broadcast', [(1, 70, 16, 1), (2, 101, 16, 1), (3, 333, 9, 1), (8, 1000, 16, 0), (2, 64, 4, 0)])
+def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast):
+    """fgs_peer_adam_rows_step (compact exchange) under the emulator: W ranks, every rank's gradient buffer holds what its
+    backward would have written for its view -- the five small gradients, NO sh_rest gradient (poisoned with NaN: it must
+    never be read) and the view's camera position in the slot behind the tensors.  After two steps every replica equals
+    dense Adam on the SUMMED full gradients, where view q's sh_rest gradient is Y_k(dir_q) * dcol_q."""
+    import numpy as np
+    from fgs_b200 import parallel
+    from tests import cuda_emu
+    lib = cuda_emu.build('peer_adam')
+    lib.fgs_peer_adam_rows_per_rank.restype = C.c_uint64
+    lib.fgs_peer_adam_rows_per_rank.argtypes = [C.c_uint64, C.c_int32]
+    shapes = [(n, 3), (n, 3), (n, 4), (n, 1), (n, 1, 3), (n, 15, 3)]
+    kf = [3, 3, 4, 1, 3, 45]
+    offsets, counts, total = parallel.peer_layout(shapes)
+    cam_off = total
+    arr64 = lambda v: (C.c_uint64 * 6)(*v)
+    rng = np.random.default_rng(100 * world + n)
+    lrs, b1, b2, eps = [1.6e-4, 5e-3, 1e-3, 2.5e-2, 2.5e-3, 1.25e-4], 0.9, 0.999, 1e-15
+    C0 = np.float32(0.28209479177387814)
+    p0 = np.zeros(total, dtype=np.float32)
+    for o, c in zip(offsets, counts):
+        p0[o:o + c] = rng.standard_normal(c).astype(np.float32)
+    params = [p0.copy() for _ in range(world)]
+    per = int(lib.fgs_peer_adam_rows_per_rank(n, world))
+    assert per % 32 == 0 and per * world >= n
+    m_sh = [np.zeros(per * 59, dtype=np.float32) for _ in range(world)]
+    v_sh = [np.zeros(per * 59, dtype=np.float32) for _ in range(world)]
+    p_ref, m_ref, v_ref = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for step in (1, 2):
+        means = p_ref[offsets[0]:offsets[0] + 3 * n].reshape(n, 3).copy()  # the means the "forward" of this step saw
+        grads, full = [], np.zeros(total, dtype=np.float32)
+        for q in range(world):
+            g = np.zeros(total + 4, dtype=np.float32)
+            for t in range(4):
+                g[offsets[t]:offsets[t] + counts[t]] = (rng.standard_normal(counts[t]) * 1e-3).astype(np.float32)
+            dcol = (rng.standard_normal((n, 3)) * 1e-3).astype(np.float32)
+            dcol[rng.random(n) < 0.3] = 0.0  # not visible in this view
+            cam = (rng.standard_normal(3) * 5).astype(np.float32)
+            g[offsets[4]:offsets[4] + 3 * n] = (C0 * dcol).reshape(-1)
+            g[offsets[5]:offsets[5] + 45 * n] = np.nan  # never exchanged
+            g[cam_off:cam_off + 3] = cam
+            grads.append(g)
+            # the full gradient of this view, as the unfused backward would have produced it
+            fg = g[:total].copy()
+            r = means - cam[None, :]
+            d = (r / np.sqrt((r * r).sum(1, keepdims=True))).astype(np.float32)
+            dc = (C0 * dcol) * (np.float32(1.0) / C0)
+            Y = _sh_basis_np(d, active)
+            fg[offsets[5]:offsets[5] + 45 * n] = (Y[:, :, None] * dc[:, None, :]).astype(np.float32).reshape(-1)
+            full = full + fg
+        gp = (C.c_void_p * world)(*[g.ctypes.data for g in grads])
+        pp = (C.c_void_p * world)(*[p.ctypes.data for p in params])
+        for rank in range(world):
+            rc = lib.fgs_peer_adam_rows_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data), C.c_void_p(v_sh[rank].ctypes.data),
+                                             arr64(offsets), C.c_uint64(n), 15, active, C.c_uint64(cam_off), broadcast,
+                                             (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs), C.c_double(b1), C.c_double(b2),
+                                             C.c_double(eps), None)
+            assert rc == 0, lib.fgs_peer_last_error()
+        if not broadcast:  # the caller's job (copy engines on a side stream in the product): hand every slice of sh_rest round
+            for rank in range(world):
+                lo, hi = min(rank * per, n), min(rank * per + per, n)
+                a, b = offsets[5] + lo * 45, offsets[5] + hi * 45
+                for q in range(world):
+                    params[q][a:b] = params[rank][a:b]
+        for t, (o, c) in enumerate(zip(offsets, counts)):
+            sl = slice(o, o + c)
+            g = full[sl]
+            m_ref[sl] = np.float32(b1) * (m_ref[sl] - g) + g
+            v_ref[sl] = np.float32(b2) * (v_ref[sl] - g * g) + g * g
+            ss = np.float32(lrs[t] / (1.0 - b1 ** step))
+            bb = np.float32(1.0 / np.sqrt(1.0 - b2 ** step))
+            p_ref[sl] = p_ref[sl] - ss * m_ref[sl] / (np.sqrt(v_ref[sl]) * bb + np.float32(eps))
+        for q in range(1, world):
+            assert np.array_equal(params[q], params[0]), f'replica {q} differs after step {step}'
+        for t, (o, c, lr) in enumerate(zip(offsets, counts, lrs)):
+            got, want = params[0][o:o + c] - p0[o:o + c], p_ref[o:o + c] - p0[o:o + c]
+            assert np.isfinite(got).all()
+            # rsqrt / fma vs numpy's sqrt and separate roundings: compared in aggregate, like every gradient in this repo
+            assert np.abs(got - want).sum() <= 2e-4 * np.abs(want).sum(), (t, step)
+    # moments of the rows a rank owns sit tensor after tensor in its shard
+    for rank in range(world):
+        lo, hi = min(rank * per, n), min(rank * per + per, n)
+        off = 0
+        for t in range(6):
+            want = m_ref[offsets[t] + lo * kf[t]:offsets[t] + hi * kf[t]]
+            got = m_sh[rank][off:off + (hi - lo) * kf[t]]
+            assert np.abs(got - want).sum() <= 2e-4 * np.abs(want).sum() + 1e-12
+            off += per * kf[t]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
@@ -164,8 +281,9 @@ def _worker(rank, world, port, out):
             fgs_b200.diff_rasterize(*ob.params, torch.empty(0), settings(k)).backward(gis[k])
             ob.step()
             ob.zero_grad()
-        torch.cuda.synchronize()
         ob.close()
+        torch.cuda.synchronize()
+        dist.barrier()
         errs = [util.rel_err(b.detach() - p0.to(dev), a.detach() - p0.to(dev)) for a, b, p0 in zip(pa, ob.params, sc)]
         flat = torch.cat([p.detach().reshape(-1) for p in ob.params])
         both = [torch.empty_like(flat) for _ in range(world)]
@@ -183,6 +301,10 @@ def _worker(rank, world, port, out):
         results['peer-mc'] = None
     # NCCL reduce-scatter + sharded Adam + all-gather
     run_variant('sharded', lambda: parallel.ShardedAdam([p.to(dev) for p in sc], lrs))
+    # compact exchange (the owner rebuilds the peers' sh_rest gradients), everything broadcast by the kernel ...
+    run_variant('peer-rows-sync', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=False))
+    # ... and with the sh_rest broadcast on the side stream under the next forward (deferred colour kernel waits for it)
+    run_variant('peer-rows', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True))
     out[rank] = results
     dist.barrier()
     dist.destroy_process_group()
