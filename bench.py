@@ -242,7 +242,7 @@ def run_gpu(args, impl):
     use_fused = mine and dist is None and vpr == 1 and not args.unfused
     fused_loss = mine and not args.torch_loss
     # deferred SH schedule: the sh_rest part of the fused step runs on a side stream under the next forward's geometry pass
-    defer_sh = use_fused and not args.no_defer_sh
+    defer_sh = use_fused and args.defer_sh  # measured +0.5 % at C2 (profiles/r2_results.md): opt-in
     if mine and args.defer_ctas:
         from fgs_b200 import _capi as _capi0
         _capi0.load().fgs_debug_set_deferred_ctas_per_sm(args.defer_ctas)
@@ -840,8 +840,10 @@ def main():
     ap.add_argument('--torch-loss', action='store_true', help='loss with torch ops ((img - gt).abs().mean()) instead of the fused loss kernel')
     ap.add_argument('--yaml-loss', action='store_true',
                     help='the loss fastergs_garden.yaml trains with (0.8 L1 + 0.2 DSSIM, Loss.py:15-16) and a live densification_info')
-    ap.add_argument('--no-defer-sh', action='store_true',
-                    help='fused path without the deferred SH schedule (sh_rest Adam inside the backward kernel, SH evaluated in preprocess)')
+    ap.add_argument('--defer-sh', action='store_true',
+                    help='fused path with the deferred SH schedule (sh_rest Adam on a side stream under the next forward\'s geometry '
+                         'pass; measured +0.5 % at C2, so not the default)')
+    ap.add_argument('--no-defer-sh', action='store_true', help='(default; kept for compatibility)')
     ap.add_argument('--defer-ctas', type=int, default=0, help='experiments: CTAs per SM of the deferred sh_rest update kernel (default 2)')
     ap.add_argument('--overlap-adam', action='store_true',
                     help='MEASURED SLOWER (profiles/r2_results.md), kept for reference: zero-gradient Adam of invisible rows on a '
