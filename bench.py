@@ -48,7 +48,7 @@ CONFIGS = {
     'c5': dict(n=500_000, w=1920, h=1080, metric='train_iters_per_sec_500k_4d_gaussians_1080p',
                workload='configs[4]: FasterGS4D shape, 500k 4D Gaussians x 150 time steps, 1920x1080, 16 SH bases'),
 }
-DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc', 'peer-rows', 'peer-rows-sync')
+DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc', 'peer-rows', 'peer-rows-sync', 'peer-rows-p2p', 'peer-rows-sync-p2p')
 
 
 def peak_hbm_gbs():
@@ -209,9 +209,10 @@ def run_gpu(args, impl):
         if dp_mode.startswith('peer-rows') and vpr != 1:
             raise SystemExit('bench.py: --dp-mode peer-rows needs one view per rank and step')
         try:
-            opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=(dp_mode == 'peer-mc'),
-                                        compact=dp_mode.startswith('peer-rows'), active_sh_bases=SH_BASES,
-                                        overlap_sh_broadcast=(dp_mode == 'peer-rows'))
+            compact = dp_mode.startswith('peer-rows')
+            mc = (dp_mode == 'peer-mc') if not compact else ('auto' if not dp_mode.endswith('-p2p') else False)
+            opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=mc, compact=compact,
+                                        active_sh_bases=SH_BASES, overlap_sh_broadcast=('sync' not in dp_mode))
         except Exception as e:  # no symmetric memory / no NVLS on this box: NCCL collectives instead, and say so
             if args.dp_mode != 'auto':
                 raise
@@ -500,8 +501,9 @@ def run_gpu(args, impl):
     elif dp_mode.startswith('peer-rows'):
         opt_path = ('backward into a symmetric-memory gradient buffer (no sh_rest gradient), then ONE kernel over NVLink peer memory: '
                     'compact gradient sum (14 of 59 floats per Gaussian; sh_rest gradients rebuilt by the owner) + Adam on the rank\'s '
-                    'Gaussians + broadcast' + ('; sh_rest parameters broadcast by copy engines under the next forward\'s geometry pass'
-                                               if dp_mode == 'peer-rows' else ''))
+                    'Gaussians + broadcast' + (' (NVLS multimem.ld_reduce / multimem.st)' if opt_obj.multicast else ' (peer loads / stores)')
+                    + ('; sh_rest parameters broadcast on a side stream under the next forward\'s geometry pass'
+                       if opt_obj.overlap_sh_broadcast else ''))
     elif dp_mode in ('peer', 'peer-mc'):
         opt_path = ('backward into a symmetric-memory gradient buffer, then ONE kernel: gradient sum over the ranks + Adam on the '
                     'rank\'s 1/W slice + parameter broadcast (' + ('NVLS multimem.ld_reduce / multimem.st' if opt_obj.multicast else 'NVLink peer loads / stores') + ')')
@@ -538,6 +540,8 @@ def run_gpu(args, impl):
         out['config']['reference'] = 'unmodified FasterGSCudaBackend (baseline/_ref) CUDA path on the same GPU'
     else:
         dp_probe['on'] = True
+        if hasattr(opt_obj, 'timing'):
+            opt_obj.timing, opt_obj._timings = True, []
         out.update(profile_mine(be, cfg, params, opt, st_dev, gt_dev, gt8_dev, dev, ms_step, use_fused, fused_loss, step_resident,
                                 opt_obj is not None or dist is not None, vpr))
         dp_probe['on'] = False
@@ -546,6 +550,15 @@ def run_gpu(args, impl):
             # GPU time from the end of the last backward to the end of the optimizer step (waiting for the slowest rank at
             # the barrier included): gradient exchange + Adam + parameter broadcast
             out['step_end_ms'] = round(sum(a.elapsed_time(b) for a, b in dp_events) / len(dp_events), 4)
+        if dist is not None:
+            # per rank: the rasterizer's own kernels, the end of the step and its phases (who waits for whom)
+            mine_row = {'rank': rank, 'kernels_ms_sum': out.get('kernels_ms_sum'), 'step_end_ms': out.get('step_end_ms')}
+            if hasattr(opt_obj, 'timing'):
+                mine_row['phases_ms'] = opt_obj.timing_summary()
+                opt_obj.timing = False
+            rows_all = [None] * world
+            dist.all_gather_object(rows_all, mine_row)
+            out['per_rank'] = rows_all
         if rank == 0 and n_ranks == 1 and not args.no_cpu_baseline and not args.quick:
             out['cpu_baseline'] = cpu_baseline(with_c2_estimate=args.config == 'c2')
     if registered is not None:

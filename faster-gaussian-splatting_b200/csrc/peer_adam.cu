@@ -110,6 +110,16 @@ __global__ void __launch_bounds__(kPeerBlock) peer_adam_multicast_kernel(const P
 }
 #endif
 
+#ifndef FGS_CUDA_EMU
+// a contiguous range of this rank's buffer to the same range of every replica: one multimem.st per 16 bytes, replicated by
+// the NVSwitch (the sh_rest slice after the row-sliced step, on a side stream under the next forward)
+__global__ void __launch_bounds__(kPeerBlock) peer_broadcast_multicast_kernel(const float4* __restrict__ src, float4* mc_dst,
+                                                                              const uint64_t n4) {
+    for (uint64_t i = (uint64_t)blockIdx.x * kPeerBlock + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * kPeerBlock)
+        multimem_st(mc_dst + i, src[i]);
+}
+#endif
+
 __global__ void __launch_bounds__(kPeerBlock) peer_adam_kernel(const PeerAdamArgs a) {
     for (uint32_t idx = blockIdx.x * kPeerBlock + threadIdx.x; idx < a.total; idx += gridDim.x * kPeerBlock) {
         uint32_t j = idx;
@@ -178,6 +188,11 @@ struct PeerRowsArgs {
     float b2[6];
     float beta1, beta2, eps;
     int world, rank;
+    // NVLS (optional, both or none): multicast addresses of the flat gradient / parameter buffers.  The four plain sums
+    // (means, scales, rotations, opacities) then come back from the switch already reduced (multimem.ld_reduce) and every
+    // broadcast is ONE store that the switch replicates (multimem.st) instead of W peer loads / stores.
+    const float* grads_mc;
+    float* params_mc;
 };
 
 constexpr float kShC0 = 0.28209479177387814f;
@@ -229,6 +244,10 @@ __device__ __forceinline__ void rows_span(const PeerRowsArgs& a, int t, size_t e
             float4 g;
             if (stage) {
                 g = reinterpret_cast<const float4*>(stage)[i];
+#ifndef FGS_CUDA_EMU
+            } else if (a.grads_mc != nullptr) {
+                g = multimem_ld_reduce_add(reinterpret_cast<const float4*>(a.grads_mc + elem0) + i);
+#endif
             } else {
                 float4 gq[FGS_MAX_PEERS];
 #pragma unroll
@@ -255,9 +274,16 @@ __device__ __forceinline__ void rows_span(const PeerRowsArgs& a, int t, size_t e
             reinterpret_cast<float4*>(m)[i] = m4;
             reinterpret_cast<float4*>(v)[i] = v4;
             if (to_all) {
+#ifndef FGS_CUDA_EMU
+                if (a.params_mc != nullptr) {
+                    multimem_st(reinterpret_cast<float4*>(a.params_mc + elem0) + i, p4);
+                } else
+#endif
+                {
 #pragma unroll
-                for (int q = 0; q < FGS_MAX_PEERS; ++q)
-                    if (q < a.world) reinterpret_cast<float4*>(a.params[q] + elem0)[i] = p4;
+                    for (int q = 0; q < FGS_MAX_PEERS; ++q)
+                        if (q < a.world) reinterpret_cast<float4*>(a.params[q] + elem0)[i] = p4;
+                }
             } else {
                 reinterpret_cast<float4*>(a.params[a.rank] + elem0)[i] = p4;
             }
@@ -488,6 +514,40 @@ static int peer_adam_step_impl(const float* const* peer_grads, float* const* pee
     return 0;
 }
 
+int fgs_peer_broadcast_multicast(const float* local_buffer, float* multicast_buffer, uint64_t first_float, uint64_t n_floats,
+                                 int32_t max_ctas, void* stream) {
+#ifdef FGS_CUDA_EMU
+    (void)local_buffer; (void)multicast_buffer; (void)first_float; (void)n_floats; (void)max_ctas; (void)stream;
+    std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_broadcast_multicast: not available on the emulator");
+    return -1;
+#else
+    if (!local_buffer || !multicast_buffer) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_broadcast_multicast: NULL buffer (NVLS not available?)");
+        return -1;
+    }
+    if ((first_float & 3u) || (n_floats & 3u) ||
+        ((reinterpret_cast<uintptr_t>(local_buffer) | reinterpret_cast<uintptr_t>(multicast_buffer)) & 15u)) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_broadcast_multicast: range and buffers must be 16-byte aligned");
+        return -1;
+    }
+    if (n_floats == 0) return 0;
+    const uint64_t n4 = n_floats / 4;
+    const uint64_t want = (n4 + kPeerBlock - 1) / kPeerBlock;
+    const int cap = max_ctas > 0 ? max_ctas : 64;  // small on purpose: it runs next to the forward's kernels
+    const int grid = want < (uint64_t)cap ? (int)want : cap;
+    auto k = peer_broadcast_multicast_kernel;
+    FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream),
+                      reinterpret_cast<const float4*>(local_buffer + first_float),
+                      reinterpret_cast<float4*>(multicast_buffer + first_float), n4);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_broadcast_multicast: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+#endif
+}
+
 uint64_t fgs_peer_adam_rows_per_rank(uint64_t n_rows, int32_t world) {
     if (world < 1) return 0;
     const uint64_t per = (n_rows + (uint64_t)world - 1) / (uint64_t)world;
@@ -497,7 +557,8 @@ uint64_t fgs_peer_adam_rows_per_rank(uint64_t n_rows, int32_t world) {
 int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
                             float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
                             int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
-                            const int32_t step[6], const double lr[6], double beta1, double beta2, double eps, void* stream) {
+                            const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
+                            const float* grads_multicast, float* params_multicast, void* stream) {
     auto fail = [](const char* msg) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
         return -1;
@@ -539,6 +600,12 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
     a.row_count = (uint32_t)(end - begin);
     a.active_bases = active_sh_bases < n_rest + 1 ? active_sh_bases : n_rest + 1;
     a.broadcast_rest = broadcast_rest;
+    if ((grads_multicast == nullptr) != (params_multicast == nullptr))
+        return fail("fgs_peer_adam_rows_step: pass both multicast addresses or none");
+    if ((reinterpret_cast<uintptr_t>(grads_multicast) | reinterpret_cast<uintptr_t>(params_multicast)) & 15u)
+        return fail("fgs_peer_adam_rows_step: multicast addresses must be 16-byte aligned");
+    a.grads_mc = grads_multicast;
+    a.params_mc = params_multicast;
     a.beta1 = (float)beta1;
     a.beta2 = (float)beta2;
     a.eps = (float)eps;

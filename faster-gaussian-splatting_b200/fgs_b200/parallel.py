@@ -227,7 +227,9 @@ class PeerAdam:
             raise RuntimeError('PeerAdam(multicast=True): the symmetric-memory handles have no multicast address (no NVLS)')
         self.multicast, self._g_mc, self._p_mc = bool(multicast), g_mc, p_mc
         if self.compact:
-            self.multicast = False
+            # NVLS for the compact step: plain sums via multimem.ld_reduce, broadcasts via multimem.st (K1), and the
+            # overlapped sh_rest broadcast as one small multimem.st kernel instead of W - 1 copy-engine transfers
+            self.multicast = bool(self.multicast and g_mc and p_mc)
             # the backward skips the sh_rest gradient altogether and leaves the view's camera position in the slot
             _C.set_gradient_outputs(self.grads[:5] + [None], camera_out=self._gbuf[self._cam_off:self._cam_off + 3])
             self._side = torch.cuda.Stream(device=dev)
@@ -257,9 +259,11 @@ class PeerAdam:
                 g.copy_(p.grad)
         self.steps += 1
         stream = self._capi.current_stream()
+        ev = self._mark('enter')
         self._gh.barrier()  # stream-ordered: every rank's gradients are complete
+        self._mark('gradients complete on every rank', ev)
         if self.compact:
-            self._step_compact(stream)
+            self._step_compact(stream, ev)
             return
         tail = (self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets),
                 (C.c_uint64 * 6)(*self.counts), (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
@@ -270,32 +274,75 @@ class PeerAdam:
             rc = self._lib.fgs_peer_adam_step(self._gptrs, self._pptrs, self.world, self.rank, *tail)
         if rc != 0:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+        self._mark('kernel', ev)
         self._ph.barrier()  # every rank's parameter stores have landed before the next forward reads them
+        self._mark('parameters landed everywhere', ev)
 
-    def _step_compact(self, stream: int) -> None:
+    broadcast_ctas = 64  # grid of the overlapped sh_rest broadcast kernel (NVLS): small, it runs next to the forward
+
+    # ---- optional timing of the phases of a step (bench.py): CUDA events on the streams the work is queued on
+    timing = False
+    _timings: list = []
+
+    def _mark(self, name, ev=None):
+        if not self.timing:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if ev is None:
+            ev = []
+            self._timings.append(ev)
+        ev.append((name, e))
+        return ev
+
+    def timing_summary(self) -> dict:
+        """Mean milliseconds per phase over the recorded steps: waiting for the slowest rank (first barrier), the
+        kernel, the closing barrier; for the overlapped sh_rest broadcast also the side stream's copies + barrier."""
+        torch.cuda.synchronize()
+        out: dict = {}
+        for ev in self._timings:
+            for (_, a), (name, b) in zip(ev, ev[1:]):
+                out.setdefault(name, []).append(a.elapsed_time(b))
+        self._timings = []
+        return {k: round(sum(v) / len(v), 4) for k, v in out.items()}
+
+    def _step_compact(self, stream: int, ev=None) -> None:
         C = self._ctypes
         overlap = self.overlap_sh_broadcast
         rc = self._lib.fgs_peer_adam_rows_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
                                                self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets), self.n_rows,
                                                self.n_rest, self.active_sh_bases, self._cam_off, 0 if overlap else 1,
                                                (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
-                                               float(self.betas[0]), float(self.betas[1]), self.eps, stream)
+                                               float(self.betas[0]), float(self.betas[1]), self.eps,
+                                               self._g_mc if self.multicast else None, self._p_mc if self.multicast else None,
+                                               stream)
         if rc != 0:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+        self._mark('kernel', ev)
         if overlap:
             # this rank's slice of the new sh_rest parameters goes to the peers on the side stream (copy engines over NVLink)
             # while the caller's stream continues with the next forward's geometry pass; `sh_ready` = all slices are here
             self._k1_done.record()
             with torch.cuda.stream(self._side):
                 self._side.wait_event(self._k1_done)
-                if self._rest_hi > self._rest_lo:
+                sev = self._mark('side: start')
+                if self._rest_hi > self._rest_lo and self.multicast:
+                    rc = self._lib.fgs_peer_broadcast_multicast(self._pbuf.data_ptr(), self._p_mc, self._rest_lo,
+                                                                self._rest_hi - self._rest_lo, self.broadcast_ctas,
+                                                                self._capi.current_stream())
+                    if rc != 0:
+                        raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+                elif self._rest_hi > self._rest_lo:
                     src = self._pbuf[self._rest_lo:self._rest_hi]
                     for q in range(self.world):
                         if q != self.rank:
                             self._peer_pbufs[q][self._rest_lo:self._rest_hi].copy_(src, non_blocking=True)
+                self._mark('side: sh_rest copies to the peers', sev)
                 self._ph.barrier(channel=1)
+                self._mark('side: barrier', sev)
                 self.sh_ready.record()
         self._ph.barrier()  # the geometry parameters (and sh0) of every rank's slice have landed everywhere
+        self._mark('parameters landed everywhere', ev)
         if not overlap:
             self.sh_ready.record()
 

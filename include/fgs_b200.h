@@ -315,7 +315,12 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
                             float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
                             int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
                             const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
-                            void* stream);
+                            const float* grads_multicast /* NVLS: both multicast addresses, or both NULL */,
+                            float* params_multicast, void* stream);
+/* floats [first_float, first_float + n_floats) of this rank's buffer to the same range of every replica through the
+ * buffer's multicast address (one multimem.st per 16 bytes); `max_ctas` bounds the grid (default 64) */
+int fgs_peer_broadcast_multicast(const float* local_buffer, float* multicast_buffer, uint64_t first_float, uint64_t n_floats,
+                                 int32_t max_ctas, void* stream);
 size_t fgs_peer_adam_shard_floats(const uint64_t counts[6], int32_t world);
 /* rank's slice of every tensor: first float (relative to the tensor), number of floats (padding included),
  * position of the slice's moments inside the shard arrays; any output pointer may be NULL */

@@ -205,7 +205,7 @@ def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast):
             rc = lib.fgs_peer_adam_rows_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data), C.c_void_p(v_sh[rank].ctypes.data),
                                              arr64(offsets), C.c_uint64(n), 15, active, C.c_uint64(cam_off), broadcast,
                                              (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs), C.c_double(b1), C.c_double(b2),
-                                             C.c_double(eps), None)
+                                             C.c_double(eps), None, None, None)
             assert rc == 0, lib.fgs_peer_last_error()
         if not broadcast:  # the caller's job (copy engines on a side stream in the product): hand every slice of sh_rest round
             for rank in range(world):
@@ -305,6 +305,9 @@ def _worker(rank, world, port, out):
     run_variant('peer-rows-sync', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=False))
     # ... and with the sh_rest broadcast on the side stream under the next forward (deferred colour kernel waits for it)
     run_variant('peer-rows', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True))
+    # the same over plain peer loads / stores and copy engines (no NVLS)
+    run_variant('peer-rows-p2p', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True,
+                                                           multicast=False))
     out[rank] = results
     dist.barrier()
     dist.destroy_process_group()
