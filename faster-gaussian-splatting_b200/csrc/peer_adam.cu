@@ -115,8 +115,17 @@ __global__ void __launch_bounds__(kPeerBlock) peer_adam_multicast_kernel(const P
 // the NVSwitch (the sh_rest slice after the row-sliced step, on a side stream under the next forward)
 __global__ void __launch_bounds__(kPeerBlock) peer_broadcast_multicast_kernel(const float4* __restrict__ src, float4* mc_dst,
                                                                               const uint64_t n4) {
-    for (uint64_t i = (uint64_t)blockIdx.x * kPeerBlock + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * kPeerBlock)
-        multimem_st(mc_dst + i, src[i]);
+    constexpr int kU = 4;  // loads in flight per thread: the grid is small on purpose, the bytes in flight must not be
+    const uint64_t stride = (uint64_t)gridDim.x * kPeerBlock;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * kPeerBlock + threadIdx.x; i0 < n4; i0 += stride * kU) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (i0 + stride * u < n4) v[u] = src[i0 + stride * u];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (i0 + stride * u < n4) multimem_st(mc_dst + i0 + stride * u, v[u]);
+    }
 }
 #endif
 
@@ -309,18 +318,99 @@ __device__ __forceinline__ void rows_span(const PeerRowsArgs& a, int t, size_t e
     }
 }
 
-__global__ void __launch_bounds__(kRowsBlock) peer_adam_rows_kernel(const PeerRowsArgs a) {
+// ---- the fast path of a full group (rows a multiple of 4: every tensor's span is whole float4s) -------------------------
+// The kernel is a chain of memory round trips (remote loads cost microseconds), so every phase first issues ALL its loads
+// and only then consumes them: the five small tensors are one merged list of float4 items (up to four per lane in flight),
+// sh_rest goes four float4s per lane at a time, the peers' sh0 gradients arrive as one float4 per lane and peer.
+struct RowsItem {
+    size_t e;   // float offset inside the flat buffers
+    size_t s;   // float offset inside the moment shards
+    int t;      // tensor: 0 means, 1 scales, 2 rotations, 3 opacities, 4 sh0 (gradient staged), 5 sh_rest (gradient staged)
+    int i;      // float4 index inside the tensor's span of this group
+    bool valid;
+};
+
+__device__ __forceinline__ RowsItem rows_small_item(const PeerRowsArgs& a, int j, int rows, uint32_t r0, uint32_t local0) {
+    const int c0 = (rows * 3) >> 2, c2 = rows, c3 = rows >> 2;  // float4s of means (= scales = sh0), rotations, opacities
+    RowsItem it;
+    it.valid = j < 3 * c0 + c2 + c3;
+    if (j < c0) { it.t = 0; it.i = j; }
+    else if (j < 2 * c0) { it.t = 1; it.i = j - c0; }
+    else if (j < 2 * c0 + c2) { it.t = 2; it.i = j - 2 * c0; }
+    else if (j < 2 * c0 + c2 + c3) { it.t = 3; it.i = j - 2 * c0 - c2; }
+    else { it.t = 4; it.i = j - 2 * c0 - c2 - c3; }
+    if (!it.valid) { it.t = 0; it.i = 0; }
+    it.e = (size_t)a.off[it.t] + (size_t)r0 * a.kf[it.t] + 4u * (size_t)it.i;
+    it.s = (size_t)a.shard_off[it.t] + (size_t)local0 * a.kf[it.t] + 4u * (size_t)it.i;
+    return it;
+}
+
+template <bool kMC>
+__device__ __forceinline__ float4 rows_peer_sum(const PeerRowsArgs& a, size_t e) {
+#ifndef FGS_CUDA_EMU
+    if (kMC) return multimem_ld_reduce_add(reinterpret_cast<const float4*>(a.grads_mc + e));
+#endif
+    float4 gq[FGS_MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < FGS_MAX_PEERS; ++q)
+        if (q < a.world) gq[q] = ld_peer(reinterpret_cast<const float4*>(a.grads[q] + e));
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < FGS_MAX_PEERS; ++q) {
+        if (q < a.world) {
+            g.x += gq[q].x;
+            g.y += gq[q].y;
+            g.z += gq[q].z;
+            g.w += gq[q].w;
+        }
+    }
+    return g;
+}
+
+template <bool kMC>
+__device__ __forceinline__ void rows_store_param(const PeerRowsArgs& a, size_t e, float4 p4, bool to_all) {
+    if (!to_all) {
+        *reinterpret_cast<float4*>(a.params[a.rank] + e) = p4;
+        return;
+    }
+#ifndef FGS_CUDA_EMU
+    if (kMC) {
+        multimem_st(reinterpret_cast<float4*>(a.params_mc + e), p4);
+        return;
+    }
+#endif
+#pragma unroll
+    for (int q = 0; q < FGS_MAX_PEERS; ++q)
+        if (q < a.world) *reinterpret_cast<float4*>(a.params[q] + e) = p4;
+}
+
+__device__ __forceinline__ void rows_adam4(const PeerRowsArgs& a, int t, float4 g, float4& p4, float4& m4, float4& v4) {
+    const float ss = a.step_size[t], b2 = a.b2[t];
+    adam1(g.x, p4.x, m4.x, v4.x, ss, a.beta1, a.beta2, a.eps, b2);
+    adam1(g.y, p4.y, m4.y, v4.y, ss, a.beta1, a.beta2, a.eps, b2);
+    adam1(g.z, p4.z, m4.z, v4.z, ss, a.beta1, a.beta2, a.eps, b2);
+    adam1(g.w, p4.w, m4.w, v4.w, ss, a.beta1, a.beta2, a.eps, b2);
+}
+
+// kMC: NVLS build (multimem.ld_reduce sums, multimem.st broadcasts); otherwise W peer loads / stores per float4.
+template <bool kMC>
+__global__ void __launch_bounds__(kRowsBlock, 3) peer_adam_rows_kernel(const PeerRowsArgs a) {
     FGS_DYNAMIC_SMEM(float, s_rows, 16);
+    __shared__ float s_cam[FGS_MAX_PEERS * 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* stage_rest = s_rows + warp * kRowsWarpFloats;
     float* s_dcol = stage_rest + 32 * 45;          // [peer][96]
     float* stage_sh0 = s_dcol + FGS_MAX_PEERS * 96;  // [96]
     const int rest_floats = (int)a.kf[5];
     const uint32_t groups = (a.row_count + 31u) >> 5;
+    // every peer's camera position (remote, but only once per CTA)
+    if ((int)threadIdx.x < a.world * 3) s_cam[threadIdx.x] = __ldcg(a.grads[threadIdx.x / 3] + a.cam_off + threadIdx.x % 3);
+    __syncthreads();
     for (uint32_t group = blockIdx.x * kRowsWarps + warp; group < groups; group += gridDim.x * kRowsWarps) {
         const uint32_t r0 = a.row_begin + (group << 5);
         const int rows = (int)min(32u, a.row_begin + a.row_count - r0);
         const uint32_t local0 = group << 5;  // first row of the group inside this rank's slice
+        const bool fast = (rows & 3) == 0;
         // the Gaussian's mean BEFORE this step's update: the view directions of the forward pass were computed from it
         float3 mean = make_float3(0.f, 0.f, 0.f);
         if (lane < rows) {
@@ -328,52 +418,148 @@ __global__ void __launch_bounds__(kRowsBlock) peer_adam_rows_kernel(const PeerRo
             mean = make_float3(mp[0], mp[1], mp[2]);
         }
         // every peer's sh0 gradient of these rows (= C0 * dL/dcolour of that peer's view), and their sum in peer order
-        for (int i = lane; i < rows * 3; i += 32) {
-            float sum = 0.f;
-            for (int q = 0; q < a.world; ++q) {
-                const float g = __ldcg(a.grads[q] + a.off[4] + (size_t)r0 * 3 + i);
-                s_dcol[q * 96 + i] = g;
-                sum += g;
+        if (fast) {
+            const int n4 = (rows * 3) >> 2;
+            if (lane < n4) {
+                float4 gq[FGS_MAX_PEERS];
+#pragma unroll
+                for (int q = 0; q < FGS_MAX_PEERS; ++q)
+                    if (q < a.world) gq[q] = ld_peer(reinterpret_cast<const float4*>(a.grads[q] + a.off[4] + (size_t)r0 * 3) + lane);
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < FGS_MAX_PEERS; ++q) {
+                    if (q < a.world) {
+                        reinterpret_cast<float4*>(s_dcol + q * 96)[lane] = gq[q];
+                        sum.x += gq[q].x;
+                        sum.y += gq[q].y;
+                        sum.z += gq[q].z;
+                        sum.w += gq[q].w;
+                    }
+                }
+                reinterpret_cast<float4*>(stage_sh0)[lane] = sum;
             }
-            stage_sh0[i] = sum;
+        } else {
+            for (int i = lane; i < rows * 3; i += 32) {
+                float sum = 0.f;
+                for (int q = 0; q < a.world; ++q) {
+                    const float g = __ldcg(a.grads[q] + a.off[4] + (size_t)r0 * 3 + i);
+                    s_dcol[q * 96 + i] = g;
+                    sum += g;
+                }
+                stage_sh0[i] = sum;
+            }
         }
         __syncwarp();
         // rebuild the summed sh_rest gradient of this lane's Gaussian: sum over peers of Y_k(dir_q) * dL/dcolour_q
         if (rest_floats > 0 && lane < rows) {
-            float acc[45];
-#pragma unroll
-            for (int k = 0; k < 45; ++k) acc[k] = 0.f;
-            for (int q = 0; q < a.world; ++q) {
-                const float dr = s_dcol[q * 96 + 3 * lane] * (1.0f / kShC0);
-                const float dg = s_dcol[q * 96 + 3 * lane + 1] * (1.0f / kShC0);
-                const float db = s_dcol[q * 96 + 3 * lane + 2] * (1.0f / kShC0);
-                if (dr == 0.f && dg == 0.f && db == 0.f) continue;  // not visible in that view
-                const float* cam = a.grads[q] + a.cam_off;
-                const float rx = mean.x - __ldcg(cam), ry = mean.y - __ldcg(cam + 1), rz = mean.z - __ldcg(cam + 2);
-                const float inv_len = rsqrtf(rx * rx + ry * ry + rz * rz);
-                float Y[15];
-                peer_sh_basis(rx * inv_len, ry * inv_len, rz * inv_len, a.active_bases, Y);
-#pragma unroll
-                for (int k = 0; k < 15; ++k) {
-                    acc[3 * k] += Y[k] * dr;
-                    acc[3 * k + 1] += Y[k] * dg;
-                    acc[3 * k + 2] += Y[k] * db;
-                }
-            }
+            // one colour channel at a time (15 accumulators + 15 basis values live instead of 45 + 15: the basis is cheap to
+            // recompute, registers are what limits the CTAs per SM here)
             float* mine = stage_rest + lane * rest_floats;
+#pragma unroll 1
+            for (int ch = 0; ch < 3; ++ch) {
+                float acc[15];
 #pragma unroll
-            for (int k = 0; k < 45; ++k)
-                if (k < rest_floats) mine[k] = acc[k];
+                for (int k = 0; k < 15; ++k) acc[k] = 0.f;
+                for (int q = 0; q < a.world; ++q) {
+                    const float d = s_dcol[q * 96 + 3 * lane + ch] * (1.0f / kShC0);
+                    if (d == 0.f) continue;  // not visible in that view (or no gradient in this channel)
+                    const float rx = mean.x - s_cam[3 * q], ry = mean.y - s_cam[3 * q + 1], rz = mean.z - s_cam[3 * q + 2];
+                    const float inv_len = rsqrtf(rx * rx + ry * ry + rz * rz);
+                    float Y[15];
+                    peer_sh_basis(rx * inv_len, ry * inv_len, rz * inv_len, a.active_bases, Y);
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) acc[k] += Y[k] * d;
+                }
+#pragma unroll
+                for (int k = 0; k < 15; ++k)
+                    if (3 * k < rest_floats) mine[3 * k + ch] = acc[k];
+            }
         }
         __syncwarp();
-        // means, scales, rotations, opacities: plain sums over the peers; sh0: the staged sum; sh_rest: the rebuilt gradient
-        for (int t = 0; t < 4; ++t)
-            rows_span(a, t, (size_t)a.off[t] + (size_t)r0 * a.kf[t], (size_t)a.shard_off[t] + (size_t)local0 * a.kf[t],
-                      rows * (int)a.kf[t], nullptr, true, lane);
-        rows_span(a, 4, (size_t)a.off[4] + (size_t)r0 * 3, (size_t)a.shard_off[4] + (size_t)local0 * 3, rows * 3, stage_sh0, true, lane);
-        if (rest_floats > 0)
-            rows_span(a, 5, (size_t)a.off[5] + (size_t)r0 * rest_floats, (size_t)a.shard_off[5] + (size_t)local0 * rest_floats,
-                      rows * rest_floats, stage_rest, a.broadcast_rest != 0, lane);
+        if (!fast) {
+            // ragged tail of the tensor (at most one group per rank): tensor after tensor, scalar where it has to be
+            for (int t = 0; t < 4; ++t)
+                rows_span(a, t, (size_t)a.off[t] + (size_t)r0 * a.kf[t], (size_t)a.shard_off[t] + (size_t)local0 * a.kf[t],
+                          rows * (int)a.kf[t], nullptr, true, lane);
+            rows_span(a, 4, (size_t)a.off[4] + (size_t)r0 * 3, (size_t)a.shard_off[4] + (size_t)local0 * 3, rows * 3, stage_sh0, true, lane);
+            if (rest_floats > 0)
+                rows_span(a, 5, (size_t)a.off[5] + (size_t)r0 * rest_floats, (size_t)a.shard_off[5] + (size_t)local0 * rest_floats,
+                          rows * rest_floats, stage_rest, a.broadcast_rest != 0, lane);
+            __syncwarp();
+            continue;
+        }
+        // means, scales, rotations, opacities (sums over the peers) and sh0 (the staged sum): one merged list of float4
+        // items, up to four per lane, every load in flight before the first Adam update
+        {
+            constexpr int kU = 4;
+            RowsItem it[kU];
+            float4 g4[kU], p4[kU], m4[kU], v4[kU];
+            if (!kMC) {  // W peer loads per item: one item at a time keeps the registers (and still overlaps its W + 3 loads)
+#pragma unroll 1
+                for (int u = 0; u < kU; ++u) {
+                    const RowsItem x = rows_small_item(a, lane + 32 * u, rows, r0, local0);
+                    if (!x.valid) continue;
+                    float4 g = x.t == 4 ? reinterpret_cast<const float4*>(stage_sh0)[x.i] : rows_peer_sum<false>(a, x.e);
+                    float4 pp = *reinterpret_cast<const float4*>(a.params[a.rank] + x.e);
+                    float4 mm = *reinterpret_cast<const float4*>(a.exp_avg + x.s);
+                    float4 vv = *reinterpret_cast<const float4*>(a.exp_avg_sq + x.s);
+                    rows_adam4(a, x.t, g, pp, mm, vv);
+                    *reinterpret_cast<float4*>(a.exp_avg + x.s) = mm;
+                    *reinterpret_cast<float4*>(a.exp_avg_sq + x.s) = vv;
+                    rows_store_param<false>(a, x.e, pp, true);
+                }
+            } else {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                it[u] = rows_small_item(a, lane + 32 * u, rows, r0, local0);
+                if (it[u].valid) {
+                    g4[u] = it[u].t == 4 ? reinterpret_cast<const float4*>(stage_sh0)[it[u].i] : rows_peer_sum<true>(a, it[u].e);
+                    p4[u] = *reinterpret_cast<const float4*>(a.params[a.rank] + it[u].e);
+                    m4[u] = *reinterpret_cast<const float4*>(a.exp_avg + it[u].s);
+                    v4[u] = *reinterpret_cast<const float4*>(a.exp_avg_sq + it[u].s);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (it[u].valid) {
+                    rows_adam4(a, it[u].t, g4[u], p4[u], m4[u], v4[u]);
+                    *reinterpret_cast<float4*>(a.exp_avg + it[u].s) = m4[u];
+                    *reinterpret_cast<float4*>(a.exp_avg_sq + it[u].s) = v4[u];
+                    rows_store_param<true>(a, it[u].e, p4[u], true);
+                }
+            }
+            }
+        }
+        // sh_rest: the rebuilt gradient from shared memory, parameters and moments of this rank's rows, four float4s per lane
+        // in flight; the new parameters go to every replica here or stay local for the caller's side-stream broadcast
+        if (rest_floats > 0) {
+            constexpr int kU = 4;
+            const int n4 = (rows * rest_floats) >> 2;
+            const size_t e0 = (size_t)a.off[5] + (size_t)r0 * rest_floats, s0 = (size_t)a.shard_off[5] + (size_t)local0 * rest_floats;
+            const bool to_all = a.broadcast_rest != 0;
+            for (int i0 = lane; i0 < n4; i0 += 32 * kU) {
+                float4 p4[kU], m4[kU], v4[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int i = i0 + 32 * u;
+                    if (i < n4) {
+                        p4[u] = reinterpret_cast<const float4*>(a.params[a.rank] + e0)[i];
+                        m4[u] = reinterpret_cast<const float4*>(a.exp_avg + s0)[i];
+                        v4[u] = reinterpret_cast<const float4*>(a.exp_avg_sq + s0)[i];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int i = i0 + 32 * u;
+                    if (i < n4) {
+                        rows_adam4(a, 5, reinterpret_cast<const float4*>(stage_rest)[i], p4[u], m4[u], v4[u]);
+                        reinterpret_cast<float4*>(a.exp_avg + s0)[i] = m4[u];
+                        reinterpret_cast<float4*>(a.exp_avg_sq + s0)[i] = v4[u];
+                        rows_store_param<kMC>(a, e0 + 4u * (size_t)i, p4[u], to_all);
+                    }
+                }
+            }
+        }
         __syncwarp();
     }
 }
@@ -617,20 +803,27 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
     int cur_dev = 0;
     if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0) cur_dev = 0;
     int& grid_cap = s_rows_grid[cur_dev % 64];
+    const bool mc = a.grads_mc != nullptr;
     if (grid_cap == 0) {
-        auto kf_ = peer_adam_rows_kernel;
-        if (cudaFuncSetAttribute(kf_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        auto k0 = peer_adam_rows_kernel<false>;
+        auto k1 = peer_adam_rows_kernel<true>;
+        if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail("fgs_peer_adam_rows_step: cannot reserve shared memory");
-        int sms = 0, occ = 0;
+        int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_adam_rows_kernel, kRowsBlock, smem);
-        grid_cap = (sms > 0 ? sms : 1) * (occ > 0 ? occ : 1);
+        grid_cap = (sms > 0 ? sms : 1) * 3;  // a persistent wave: three 128-thread CTAs per SM (168 registers)
     }
     const uint32_t groups = (a.row_count + 31u) / 32u;
     const uint32_t want = (groups + kRowsWarps - 1) / kRowsWarps;
     const int grid = want < (uint32_t)grid_cap ? (int)want : grid_cap;
-    auto k = peer_adam_rows_kernel;
-    FGS_LAUNCH_SMEM(k, dim3((unsigned)grid), dim3(kRowsBlock), smem, reinterpret_cast<cudaStream_t>(stream), a);
+    if (mc) {
+        auto k = peer_adam_rows_kernel<true>;
+        FGS_LAUNCH_SMEM(k, dim3((unsigned)grid), dim3(kRowsBlock), smem, reinterpret_cast<cudaStream_t>(stream), a);
+    } else {
+        auto k = peer_adam_rows_kernel<false>;
+        FGS_LAUNCH_SMEM(k, dim3((unsigned)grid), dim3(kRowsBlock), smem, reinterpret_cast<cudaStream_t>(stream), a);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_rows_step: %s", cudaGetErrorString(e));
