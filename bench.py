@@ -48,7 +48,7 @@ CONFIGS = {
     'c5': dict(n=500_000, w=1920, h=1080, metric='train_iters_per_sec_500k_4d_gaussians_1080p',
                workload='configs[4]: FasterGS4D shape, 500k 4D Gaussians x 150 time steps, 1920x1080, 16 SH bases'),
 }
-DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc', 'peer-rows', 'peer-rows-sync', 'peer-rows-p2p', 'peer-rows-sync-p2p')
+DP_MODES = ('auto', 'allreduce', 'flat', 'pipelined', 'sharded', 'peer', 'peer-mc', 'peer-rows', 'peer-rows-sync', 'peer-rows-mono', 'peer-rows-mono-p2p')
 
 
 def peak_hbm_gbs():
@@ -205,14 +205,17 @@ def run_gpu(args, impl):
         # views per rank (gradient accumulation): the plain one-kernel reduce + Adam + broadcast
         dp_mode = 'peer-rows' if vpr == 1 else 'peer'
     opt_obj = None  # PeerAdam / ShardedAdam own flat parameter + gradient buffers
-    if dp_mode in ('peer', 'peer-mc', 'peer-rows', 'peer-rows-sync'):
+    if dp_mode.startswith('peer'):
         if dp_mode.startswith('peer-rows') and vpr != 1:
             raise SystemExit('bench.py: --dp-mode peer-rows needs one view per rank and step')
         try:
             compact = dp_mode.startswith('peer-rows')
             mc = (dp_mode == 'peer-mc') if not compact else ('auto' if not dp_mode.endswith('-p2p') else False)
             opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=mc, compact=compact,
-                                        active_sh_bases=SH_BASES, overlap_sh_broadcast=('sync' not in dp_mode))
+                                        active_sh_bases=SH_BASES, overlap_sh_broadcast=('sync' not in dp_mode),
+                                        split=('mono' not in dp_mode))
+            if args.side_ctas:
+                opt_obj.side_ctas_per_sm = args.side_ctas
         except Exception as e:  # no symmetric memory / no NVLS on this box: NCCL collectives instead, and say so
             if args.dp_mode != 'auto':
                 raise
@@ -499,11 +502,12 @@ def run_gpu(args, impl):
         opt_path = 'fused backward+Adam (diff_rasterize_fused, FasterGSFused semantics)' + (
             '; deferred SH schedule: sh_rest Adam on a side stream under the next forward\'s geometry pass + sorts' if defer_sh else '')
     elif dp_mode.startswith('peer-rows'):
-        opt_path = ('backward into a symmetric-memory gradient buffer (no sh_rest gradient), then ONE kernel over NVLink peer memory: '
-                    'compact gradient sum (14 of 59 floats per Gaussian; sh_rest gradients rebuilt by the owner) + Adam on the rank\'s '
-                    'Gaussians + broadcast' + (' (NVLS multimem.ld_reduce / multimem.st)' if opt_obj.multicast else ' (peer loads / stores)')
-                    + ('; sh_rest parameters broadcast on a side stream under the next forward\'s geometry pass'
-                       if opt_obj.overlap_sh_broadcast else ''))
+        opt_path = ('backward into a symmetric-memory gradient buffer (no sh_rest gradient), then over NVLink peer memory: compact '
+                    'gradient sum (14 of 59 floats per Gaussian and peer; sh_rest gradients rebuilt by the owner) + Adam on the '
+                    'rank\'s Gaussians + broadcast' + (' (NVLS multimem.ld_reduce / multimem.st)' if opt_obj.multicast else ' (peer loads / stores)')
+                    + ('; two kernels: the five small tensors on the main stream, ' if opt_obj.split else '; one kernel, ')
+                    + ('sh_rest on a side stream under the next forward\'s geometry pass + sorts' if opt_obj.overlap_sh_broadcast
+                       else 'sh_rest on the same stream'))
     elif dp_mode in ('peer', 'peer-mc'):
         opt_path = ('backward into a symmetric-memory gradient buffer, then ONE kernel: gradient sum over the ranks + Adam on the '
                     'rank\'s 1/W slice + parameter broadcast (' + ('NVLS multimem.ld_reduce / multimem.st' if opt_obj.multicast else 'NVLink peer loads / stores') + ')')
@@ -857,6 +861,7 @@ def main():
                     help='fused path with the deferred SH schedule (sh_rest Adam on a side stream under the next forward\'s geometry '
                          'pass; measured +0.5 % at C2, so not the default)')
     ap.add_argument('--no-defer-sh', action='store_true', help='(default; kept for compatibility)')
+    ap.add_argument('--side-ctas', type=int, default=0, help='experiments: CTAs per SM of the side-stream sh_rest kernel at N > 1 (default 2)')
     ap.add_argument('--defer-ctas', type=int, default=0, help='experiments: CTAs per SM of the deferred sh_rest update kernel (default 2)')
     ap.add_argument('--overlap-adam', action='store_true',
                     help='MEASURED SLOWER (profiles/r2_results.md), kept for reference: zero-gradient Adam of invisible rows on a '

@@ -55,6 +55,9 @@ struct PeerAdamArgs {
     // new parameters leave once instead of W-1 times.
     const float4* grads_mc;
     float4* params_mc;
+    // split compact step: the pre-update values of tensor 0 (means) of this rank's slice, float4 j of the slice -> means_old[j];
+    // the sh_rest kernel that runs later on a side stream rebuilds the view directions from them
+    float4* means_old;
 };
 
 __device__ __forceinline__ float4 ld_peer(const float4* p) {  // L2-only (the data is rewritten by its owner every step)
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(kPeerBlock) peer_adam_kernel(const PeerAdamArg
         float4 p = a.params[a.rank][e];
         float4 m = a.exp_avg[a.shard_off[t] + j];
         float4 v = a.exp_avg_sq[a.shard_off[t] + j];
+        if (t == 0 && a.means_old != nullptr) a.means_old[j] = p;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < FGS_MAX_PEERS; ++q) {  // fixed order: every replica receives the same bits
@@ -202,6 +206,10 @@ struct PeerRowsArgs {
     // broadcast is ONE store that the switch replicates (multimem.st) instead of W peer loads / stores.
     const float* grads_mc;
     float* params_mc;
+    // split compact step: only sh_rest is handled here (the five small tensors went through the float4-sliced kernel), and
+    // the means come from the snapshot that kernel took before updating them (floats 3 * local_row ..)
+    int rest_only;
+    const float* means_old;
 };
 
 constexpr float kShC0 = 0.28209479177387814f;
@@ -414,7 +422,8 @@ __global__ void __launch_bounds__(kRowsBlock, 3) peer_adam_rows_kernel(const Pee
         // the Gaussian's mean BEFORE this step's update: the view directions of the forward pass were computed from it
         float3 mean = make_float3(0.f, 0.f, 0.f);
         if (lane < rows) {
-            const float* mp = a.params[a.rank] + a.off[0] + (size_t)(r0 + lane) * 3;
+            const float* mp = a.rest_only ? a.means_old + (size_t)(local0 + lane) * 3
+                                          : a.params[a.rank] + a.off[0] + (size_t)(r0 + lane) * 3;
             mean = make_float3(mp[0], mp[1], mp[2]);
         }
         // every peer's sh0 gradient of these rows (= C0 * dL/dcolour of that peer's view), and their sum in peer order
@@ -478,10 +487,12 @@ __global__ void __launch_bounds__(kRowsBlock, 3) peer_adam_rows_kernel(const Pee
         __syncwarp();
         if (!fast) {
             // ragged tail of the tensor (at most one group per rank): tensor after tensor, scalar where it has to be
-            for (int t = 0; t < 4; ++t)
-                rows_span(a, t, (size_t)a.off[t] + (size_t)r0 * a.kf[t], (size_t)a.shard_off[t] + (size_t)local0 * a.kf[t],
-                          rows * (int)a.kf[t], nullptr, true, lane);
-            rows_span(a, 4, (size_t)a.off[4] + (size_t)r0 * 3, (size_t)a.shard_off[4] + (size_t)local0 * 3, rows * 3, stage_sh0, true, lane);
+            if (!a.rest_only) {
+                for (int t = 0; t < 4; ++t)
+                    rows_span(a, t, (size_t)a.off[t] + (size_t)r0 * a.kf[t], (size_t)a.shard_off[t] + (size_t)local0 * a.kf[t],
+                              rows * (int)a.kf[t], nullptr, true, lane);
+                rows_span(a, 4, (size_t)a.off[4] + (size_t)r0 * 3, (size_t)a.shard_off[4] + (size_t)local0 * 3, rows * 3, stage_sh0, true, lane);
+            }
             if (rest_floats > 0)
                 rows_span(a, 5, (size_t)a.off[5] + (size_t)r0 * rest_floats, (size_t)a.shard_off[5] + (size_t)local0 * rest_floats,
                           rows * rest_floats, stage_rest, a.broadcast_rest != 0, lane);
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(kRowsBlock, 3) peer_adam_rows_kernel(const Pee
         }
         // means, scales, rotations, opacities (sums over the peers) and sh0 (the staged sum): one merged list of float4
         // items, up to four per lane, every load in flight before the first Adam update
-        {
+        if (!a.rest_only) {
             constexpr int kU = 4;
             RowsItem it[kU];
             float4 g4[kU], p4[kU], m4[kU], v4[kU];
@@ -700,6 +711,77 @@ static int peer_adam_step_impl(const float* const* peer_grads, float* const* pee
     return 0;
 }
 
+// The five small tensors of the split compact step through the float4-sliced kernel, with ROW-aligned slices (rank r owns
+// the Gaussians [r * R, (r + 1) * R), like fgs_peer_adam_rows_step) and the moment layout of the row-sliced step.
+int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                             float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
+                             int32_t n_rest, const int32_t step[6], const double lr[6], double beta1, double beta2,
+                             double eps, float* means_old, void* stream) {
+    auto fail = [](const char* msg) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
+        return -1;
+    };
+    if (!peer_grads || !peer_params || !exp_avg_shard || !exp_avg_sq_shard || !offsets || !step || !lr)
+        return fail("fgs_peer_adam_small_step: NULL argument");
+    if (world < 1 || world > FGS_MAX_PEERS || rank < 0 || rank >= world) return fail("fgs_peer_adam_small_step: bad world/rank");
+    if (n_rest < 0 || n_rest > 15) return fail("fgs_peer_adam_small_step: sh_rest must have <= 15 bases");
+    PeerAdamArgs a{};
+    for (int q = 0; q < world; ++q) {
+        if (!peer_grads[q] || !peer_params[q]) return fail("fgs_peer_adam_small_step: NULL peer pointer");
+        if ((reinterpret_cast<uintptr_t>(peer_grads[q]) | reinterpret_cast<uintptr_t>(peer_params[q])) & 15u)
+            return fail("fgs_peer_adam_small_step: peer buffers must be 16-byte aligned");
+        a.grads[q] = reinterpret_cast<const float4*>(peer_grads[q]);
+        a.params[q] = reinterpret_cast<float4*>(peer_params[q]);
+    }
+    if ((reinterpret_cast<uintptr_t>(exp_avg_shard) | reinterpret_cast<uintptr_t>(exp_avg_sq_shard) |
+         reinterpret_cast<uintptr_t>(means_old)) & 15u)
+        return fail("fgs_peer_adam_small_step: moment shards and the means snapshot must be 16-byte aligned");
+    a.exp_avg = reinterpret_cast<float4*>(exp_avg_shard);
+    a.exp_avg_sq = reinterpret_cast<float4*>(exp_avg_sq_shard);
+    a.means_old = reinterpret_cast<float4*>(means_old);
+    const uint32_t kf[6] = {3u, 3u, 4u, 1u, 3u, 3u * (uint32_t)n_rest};
+    const uint64_t per = (((n_rows + (uint64_t)world - 1) / (uint64_t)world) + 31) / 32 * 32;
+    const uint64_t begin = (uint64_t)rank * per < n_rows ? (uint64_t)rank * per : n_rows;
+    const uint64_t end = begin + per < n_rows ? begin + per : n_rows;
+    uint64_t shard = 0, total = 0;
+    for (int t = 0; t < 6; ++t) {
+        if (offsets[t] & 3u) return fail("fgs_peer_adam_small_step: tensor offsets must be multiples of 4 floats");
+        // rows [begin, end) of tensor t: whole float4s (begin * kf is a multiple of 4; a ragged end takes the padding along)
+        const uint64_t f0 = begin * kf[t], f1 = end * kf[t];
+        const uint64_t n4 = t < 5 ? (f1 - f0 + 3) / 4 : 0;  // sh_rest is not handled here
+        if (offsets[t] / 4 + f0 / 4 + n4 > 0xffffffffull) return fail("fgs_peer_adam_small_step: buffers too large");
+        a.begin[t] = (uint32_t)(offsets[t] / 4 + f0 / 4);
+        a.count[t] = (uint32_t)n4;
+        a.shard_off[t] = (uint32_t)(shard / 4);
+        shard += per * kf[t];
+        total += n4;
+        a.step_size[t] = (float)(lr[t] / (1.0 - std::pow(beta1, (double)step[t])));
+        a.b2[t] = (float)(1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step[t])));
+    }
+    a.beta1 = (float)beta1;
+    a.beta2 = (float)beta2;
+    a.eps = (float)eps;
+    a.world = world;
+    a.rank = rank;
+    a.total = (uint32_t)total;
+    if (total == 0) return 0;
+    int cur_dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0) cur_dev = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_adam_kernel, kPeerBlock, 0);
+    const uint64_t cap = (uint64_t)(sms > 0 ? sms : 1) * (uint64_t)(occ > 0 ? occ : 1);
+    const uint64_t want = (total + kPeerBlock - 1) / kPeerBlock;
+    const int grid = (int)(want < cap ? want : cap);
+    auto k = peer_adam_kernel;
+    FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_small_step: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
 int fgs_peer_broadcast_multicast(const float* local_buffer, float* multicast_buffer, uint64_t first_float, uint64_t n_floats,
                                  int32_t max_ctas, void* stream) {
 #ifdef FGS_CUDA_EMU
@@ -744,7 +826,8 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
                             float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
                             int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
                             const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
-                            const float* grads_multicast, float* params_multicast, void* stream) {
+                            const float* grads_multicast, float* params_multicast, const float* means_old,
+                            int32_t max_ctas_per_sm, void* stream) {
     auto fail = [](const char* msg) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
         return -1;
@@ -792,6 +875,8 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
         return fail("fgs_peer_adam_rows_step: multicast addresses must be 16-byte aligned");
     a.grads_mc = grads_multicast;
     a.params_mc = params_multicast;
+    a.rest_only = means_old != nullptr;
+    a.means_old = means_old;
     a.beta1 = (float)beta1;
     a.beta2 = (float)beta2;
     a.eps = (float)eps;
@@ -816,7 +901,9 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
     }
     const uint32_t groups = (a.row_count + 31u) / 32u;
     const uint32_t want = (groups + kRowsWarps - 1) / kRowsWarps;
-    const int grid = want < (uint32_t)grid_cap ? (int)want : grid_cap;
+    int cap = grid_cap;
+    if (max_ctas_per_sm > 0 && max_ctas_per_sm < 3) cap = grid_cap / 3 * max_ctas_per_sm;  // next to another stream's kernels
+    const int grid = want < (uint32_t)cap ? (int)want : cap;
     if (mc) {
         auto k = peer_adam_rows_kernel<true>;
         FGS_LAUNCH_SMEM(k, dim3((unsigned)grid), dim3(kRowsBlock), smem, reinterpret_cast<cudaStream_t>(stream), a);

@@ -165,7 +165,7 @@ class PeerAdam:
 
     def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
                  group=None, multicast: bool | str = 'auto', compact: bool = False, active_sh_bases: int = 16,
-                 overlap_sh_broadcast: bool = True) -> None:
+                 overlap_sh_broadcast: bool = True, split: bool = True) -> None:
         """`multicast`: True = reduce and broadcast inside the NVSwitch through the buffers' multicast addresses
         (multimem.ld_reduce / multimem.st, fgs_peer_adam_step_multicast), False = W peer loads / stores per element,
         'auto' = multicast when the symmetric-memory handles expose a multicast address.
@@ -176,7 +176,14 @@ class PeerAdam:
         the sh_rest gradient (`p.grad` of sh_rest stays None).  With `overlap_sh_broadcast` the new sh_rest parameters
         (three quarters of the parameter bytes) travel to the peers on a side stream, by copy engines, while the next
         forward's geometry pass and sorts run; that forward must be `forward_settings()`-aware: pass
-        `color_event=opt.sh_ready` and `defer_color=True` (fgs_b200.parallel.diff_rasterize_dp does)."""
+        `color_event=opt.sh_ready` and `defer_color=True` (PeerAdam installs that for `diff_rasterize` itself).
+
+        `split` (default, with `compact`): two kernels instead of one.  The five small tensors (56 of the 236 bytes of a
+        Gaussian) go through the float4-sliced kernel at full occupancy on the caller's stream -- the only part the next
+        forward's geometry pass has to wait for; sh_rest (rebuild the gradient from the peers' sh0 gradients, Adam,
+        broadcast to the peers) is a second kernel on the side stream.  `split=False`: one row-sliced kernel does
+        everything and only the broadcast of the new sh_rest parameters is overlapped (measured slower: the row-sliced
+        kernel is a chain of remote round trips at 12 warps per SM)."""
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -204,7 +211,7 @@ class PeerAdam:
                 view(self._pbuf, i).copy_(t)
         self.params = [view(self._pbuf, i).requires_grad_(True) for i in range(6)]
         self.grads = [view(self._gbuf, i) for i in range(6)]
-        self.compact, self.active_sh_bases = bool(compact), int(active_sh_bases)
+        self.compact, self.active_sh_bases, self.split = bool(compact), int(active_sh_bases), bool(split) and bool(compact)
         self.overlap_sh_broadcast = bool(overlap_sh_broadcast) and self.compact and self.world > 1
         self.n_rows = int(self.shapes[0][0])
         self.n_rest = int(self.shapes[5][1]) if len(self.shapes[5]) > 1 else 0
@@ -241,6 +248,9 @@ class PeerAdam:
             k = 3 * self.n_rest
             self._rest_lo, self._rest_hi = self.offsets[5] + lo * k, self.offsets[5] + hi * k
             self._peer_pbufs = [self._ph.get_buffer(q, (total,), torch.float32) for q in range(self.world)]
+            if self.split:
+                self.multicast = False  # measured: multimem's latency costs more than its volume saves on 14 floats per Gaussian
+                self._means_old = torch.zeros(self.rows_per_rank * 3 + 4, dtype=torch.float32, device=dev)
             if self.overlap_sh_broadcast:  # every diff_rasterize forward from now on defers its colour kernel behind sh_ready
                 from .torch_bindings import rasterization as _rast
                 _rast.set_forward_kwargs(self.forward_kwargs)
@@ -306,7 +316,48 @@ class PeerAdam:
         self._timings = []
         return {k: round(sum(v) / len(v), 4) for k, v in out.items()}
 
+    side_ctas_per_sm = 2  # grid bound of the sh_rest kernel when it runs on the side stream, next to the forward
+
+    def _step_split(self, stream: int, ev=None) -> None:
+        C = self._ctypes
+        common = ((C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs), float(self.betas[0]), float(self.betas[1]), self.eps)
+        rc = self._lib.fgs_peer_adam_small_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
+                                                self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets), self.n_rows,
+                                                self.n_rest, *common, self._means_old.data_ptr(), stream)
+        if rc != 0:
+            raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+        self._mark('kernel', ev)
+
+        def rest(on_stream: int, ctas: int) -> None:
+            rc2 = self._lib.fgs_peer_adam_rows_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
+                                                    self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets), self.n_rows,
+                                                    self.n_rest, self.active_sh_bases, self._cam_off, 1, *common, None, None,
+                                                    self._means_old.data_ptr(), ctas, on_stream)
+            if rc2 != 0:
+                raise RuntimeError(self._lib.fgs_peer_last_error().decode())
+
+        if self.overlap_sh_broadcast:
+            self._k1_done.record()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._k1_done)
+                sev = self._mark('side: start')
+                rest(self._capi.current_stream(), self.side_ctas_per_sm)
+                self._mark('side: sh_rest kernel (rebuild gradient + Adam + broadcast)', sev)
+                self._ph.barrier(channel=1)
+                self._mark('side: barrier', sev)
+                self.sh_ready.record()
+        else:
+            rest(stream, 0)
+            self._mark('sh_rest kernel', ev)
+        self._ph.barrier()  # the five small tensors of every rank's Gaussians have landed everywhere
+        self._mark('parameters landed everywhere', ev)
+        if not self.overlap_sh_broadcast:
+            self.sh_ready.record()
+
     def _step_compact(self, stream: int, ev=None) -> None:
+        if self.split:
+            self._step_split(stream, ev)
+            return
         C = self._ctypes
         overlap = self.overlap_sh_broadcast
         rc = self._lib.fgs_peer_adam_rows_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
@@ -315,7 +366,7 @@ class PeerAdam:
                                                (C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs),
                                                float(self.betas[0]), float(self.betas[1]), self.eps,
                                                self._g_mc if self.multicast else None, self._p_mc if self.multicast else None,
-                                               stream)
+                                               None, 0, stream)
         if rc != 0:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
         self._mark('kernel', ev)

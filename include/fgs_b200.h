@@ -316,7 +316,20 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
                             int32_t n_rest, int32_t active_sh_bases, uint64_t cam_offset, int32_t broadcast_rest,
                             const int32_t step[6], const double lr[6], double beta1, double beta2, double eps,
                             const float* grads_multicast /* NVLS: both multicast addresses, or both NULL */,
-                            float* params_multicast, void* stream);
+                            float* params_multicast,
+                            const float* means_old /* non-NULL: sh_rest only, means from this snapshot (split step, below) */,
+                            int32_t max_ctas_per_sm /* 0: a full wave; 1 or 2: run next to another stream's kernels */,
+                            void* stream);
+/* The split compact step: fgs_peer_adam_small_step sums the five small gradients (means, scales, rotations, opacities, sh0)
+ * over the peers, applies Adam to this rank's Gaussians and stores the new parameters to every peer with the float4 kernel
+ * of fgs_peer_adam_step (row-aligned slices, moment layout of the row-sliced step), and leaves the PRE-update means of the
+ * rank's Gaussians in `means_old` (3 * R floats).  fgs_peer_adam_rows_step(..., means_old, ...) then handles sh_rest alone --
+ * rebuild the gradient, Adam, broadcast -- and can run on a side stream under the next forward's geometry pass, whose
+ * colour kernel waits for it (fgs_forward_ex). */
+int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
+                             float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
+                             int32_t n_rest, const int32_t step[6], const double lr[6], double beta1, double beta2,
+                             double eps, float* means_old, void* stream);
 /* floats [first_float, first_float + n_floats) of this rank's buffer to the same range of every replica through the
  * buffer's multicast address (one multimem.st per 16 bytes); `max_ctas` bounds the grid (default 64) */
 int fgs_peer_broadcast_multicast(const float* local_buffer, float* multicast_buffer, uint64_t first_float, uint64_t n_floats,

@@ -148,12 +148,16 @@ def _sh_basis_np(d, active):
     return Y
 
 
-@pytest.mark.parametrize('world,n,active,broadcast', [(1, 70, 16, 1), (2, 101, 16, 1), (3, 333, 9, 1), (8, 1000, 16, 0), (2, 64, 4, 0)])
-def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast):
+@pytest.mark.parametrize('world,n,active,broadcast,split', [(1, 70, 16, 1, False), (2, 101, 16, 1, False), (3, 333, 9, 1, False),
+                                                            (8, 1000, 16, 0, False), (2, 64, 4, 0, False),
+                                                            (2, 101, 16, 1, True), (3, 333, 9, 1, True), (8, 1000, 16, 1, True)])
+def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast, split):
     """fgs_peer_adam_rows_step (compact exchange) under the emulator: W ranks, every rank's gradient buffer holds what its
     backward would have written for its view -- the five small gradients, NO sh_rest gradient (poisoned with NaN: it must
     never be read) and the view's camera position in the slot behind the tensors.  After two steps every replica equals
-    dense Adam on the SUMMED full gradients, where view q's sh_rest gradient is Y_k(dir_q) * dcol_q."""
+    dense Adam on the SUMMED full gradients, where view q's sh_rest gradient is Y_k(dir_q) * dcol_q.
+    `split`: the product's schedule -- fgs_peer_adam_small_step (five small tensors, float4 kernel, snapshot of the old means)
+    followed by fgs_peer_adam_rows_step in sh_rest-only mode."""
     import numpy as np
     from fgs_b200 import parallel
     from tests import cuda_emu
@@ -202,10 +206,18 @@ def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast):
         gp = (C.c_void_p * world)(*[g.ctypes.data for g in grads])
         pp = (C.c_void_p * world)(*[p.ctypes.data for p in params])
         for rank in range(world):
+            snap = None
+            if split:
+                snap = np.full(per * 3 + 4, np.nan, dtype=np.float32)
+                rc = lib.fgs_peer_adam_small_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data),
+                                                  C.c_void_p(v_sh[rank].ctypes.data), arr64(offsets), C.c_uint64(n), 15,
+                                                  (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs), C.c_double(b1),
+                                                  C.c_double(b2), C.c_double(eps), C.c_void_p(snap.ctypes.data), None)
+                assert rc == 0, lib.fgs_peer_last_error()
             rc = lib.fgs_peer_adam_rows_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data), C.c_void_p(v_sh[rank].ctypes.data),
                                              arr64(offsets), C.c_uint64(n), 15, active, C.c_uint64(cam_off), broadcast,
                                              (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs), C.c_double(b1), C.c_double(b2),
-                                             C.c_double(eps), None, None, None)
+                                             C.c_double(eps), None, None, None if snap is None else C.c_void_p(snap.ctypes.data), 0, None)
             assert rc == 0, lib.fgs_peer_last_error()
         if not broadcast:  # the caller's job (copy engines on a side stream in the product): hand every slice of sh_rest round
             for rank in range(world):
@@ -305,9 +317,12 @@ def _worker(rank, world, port, out):
     run_variant('peer-rows-sync', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=False))
     # ... and with the sh_rest broadcast on the side stream under the next forward (deferred colour kernel waits for it)
     run_variant('peer-rows', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True))
-    # the same over plain peer loads / stores and copy engines (no NVLS)
-    run_variant('peer-rows-p2p', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True,
-                                                           multicast=False))
+    # one row-sliced kernel for everything (NVLS where available), only the sh_rest broadcast overlapped; and over plain peer
+    # loads / stores and copy engines
+    run_variant('peer-rows-mono', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True,
+                                                            split=False))
+    run_variant('peer-rows-mono-p2p', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True,
+                                                                split=False, multicast=False))
     out[rank] = results
     dist.barrier()
     dist.destroy_process_group()
