@@ -148,7 +148,10 @@ __global__ void __launch_bounds__(256) ranges_gather_kernel(const KeyT* __restri
     const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
     const uint32_t xmin = bx & 0xffffu, xmax = bx >> 16, ymin = by & 0xffffu, ymax = by >> 16;
     const uint32_t tx0 = (key % grid_w) * kTileW, ty0 = (key / grid_w) * kTileH;
-    const float tau2 = q1.y + kLog2_255;
+    // the sub-tile cull must be a SUPERSET of the per-pixel test alpha >= 1/255 that the blend kernels apply (they evaluate
+    // log2 alpha with a different operation order): a small slack on the threshold keeps a pair whose best pixel sits on
+    // the boundary, as the reference does (it only culls sub-tiles by bounding box, kernels_forward.cuh:445-451)
+    const float tau2 = q1.y + kLog2_255 + 2e-3f;
     uint32_t mask = 0;
 #pragma unroll
     for (int sub = 0; sub < kBlendWarps; ++sub) {

@@ -16,7 +16,8 @@
 //  * early termination is per sub-tile: a warp stops streaming as soon as its 32 pixels are done;
 //  * sub-tile culling is two-level: the reference's strict bounding-box overlap, then the exact
 //    "maximum of the Gaussian inside the rectangle" test on the 8x4 sub-tile (the predicate the
-//    reference applies to 16x12 tiles); both only remove pairs whose alpha is below 1/255;
+//    reference applies to 16x12 tiles, evaluated once at gather time with a small slack on the threshold, binning.cu);
+//    both only remove pairs whose alpha is below 1/255 on every pixel of the sub-tile;
 //  * the exponent is evaluated in the base-2 domain on a pre-scaled conic, colours arrive pre-clamped,
 //    the inner loop is branch-free;
 //  * no bucket checkpoints are written: the backward pass recomputes transmittance front-to-back and

@@ -13,19 +13,21 @@ from .. import _C
 
 
 class RasterizerSettings(NamedTuple):
-    w2c: torch.Tensor  # affine transformation from model/world space to view space
-    cam_position: torch.Tensor  # camera position in world space
-    bg_color: torch.Tensor  # background color in RGB format
-    active_sh_bases: int  # number of spherical harmonics bases to use for color computation
-    width: int  # width of the image plane in pixels
-    height: int  # height of the image plane in pixels
-    focal_x: float  # focal length in x direction in pixels
-    focal_y: float  # focal length in y direction in pixels
-    center_x: float  # x coordinate of the image center in pixels (positive -> right)
-    center_y: float  # y coordinate of the image center in pixels (positive -> down)
-    near_plane: float  # near clipping plane distance
-    far_plane: float  # far clipping plane distance
-    proper_antialiasing: bool  # whether to use proper antialiasing
+    """Field names, order and types are the drop-in boundary (the reference builds this tuple in Renderer.py:19-43 and
+    unpacks it positionally into `_C.forward`); what each field means to the kernels here:"""
+    w2c: torch.Tensor            # (>=3, 4) row-major world -> camera matrix on the device; rows 0..2 are read, +z looks forward
+    cam_position: torch.Tensor   # (3,) camera centre in world coordinates, device tensor (SH view directions)
+    bg_color: torch.Tensor       # (3,) RGB added behind the last Gaussian (image += T_final * bg), device tensor
+    active_sh_bases: int         # 1, 4, 9 or 16: SH bases evaluated (degree 0..3); higher coefficients get zero gradient
+    width: int                   # image width in pixels (tiles of 16 x 12 pixels, ragged edges allowed)
+    height: int                  # image height in pixels
+    focal_x: float               # pixels: x_image = focal_x * x / z + center_x
+    focal_y: float               # pixels: y_image = focal_y * y / z + center_y
+    center_x: float              # principal point, absolute pixel coordinate, +x to the right
+    center_y: float              # principal point, absolute pixel coordinate, +y downwards
+    near_plane: float            # Gaussians with camera depth z < near_plane are culled
+    far_plane: float             # ... and those with z > far_plane
+    proper_antialiasing: bool    # 0.1 px dilation with opacity compensation instead of the plain 0.3 px dilation
 
     def as_tuple(self) -> tuple:
         return tuple(self)
