@@ -17,9 +17,9 @@
 // reduced gradient in HBM.  The caller brackets the launch with two symmetric-memory barriers (all gradients
 // written before; all parameter stores landed after).
 //
-// STATUS: written at the end of round 1 after the probe in profiles/r1_multigpu.md (peer reads 717 GB/s, NVLS
-// available); compiled, exported, covered on the host side -- NOT yet run on hardware (the round's GPU budget was
-// spent).  fgs_b200.parallel.allreduce_gradients + FusedAdam.step remains the measured default.
+// STATUS (round 2): run and measured on 2, 4 and 8 B200s (profiles/r2_results.md); the two-GPU test checks
+// every variant against all-reduce + FusedAdam.  The default of the view-parallel path is the split compact step further
+// down (fgs_peer_adam_small_step + fgs_peer_adam_rows_step); this one-kernel form serves several views per rank.
 //
 // This file is also compiled by g++ against tests/cuda_emu/cuda_emu.h (test-only emulator) -- see fgs_launch.h: the
 // slicing / sharding logic is checked on the CPU by running W "ranks" one after the other on host buffers.

@@ -276,7 +276,8 @@ int fgs_slice4d_backward(const float* means4, const float* scales4, const float*
                          float* grad_scales4, float* grad_rot_l, float* grad_rot_r, float* grad_opacities, void* stream);
 
 /* ---- view-parallel training over NVLink peer memory (no reference counterpart: the reference is single-GPU,
- * Renderer.py:58-61).  EXPERIMENTAL: compiled and host-tested, not yet run on hardware (see csrc/peer_adam.cu).
+ * Renderer.py:58-61).  Run and measured on 2 / 4 / 8 B200s (profiles/r2_results.md); semantics checked against
+ * all-reduce + fgs_adam_step on two GPUs (tests/test_peer_adam.py).
  *
  * Every rank keeps its six gradient tensors in one flat buffer and its six parameter tensors in another, both in
  * symmetric memory with the same layout on every rank: tensor t occupies floats [offsets[t], offsets[t] + counts[t]),
