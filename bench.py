@@ -213,7 +213,8 @@ def run_gpu(args, impl):
             mc = (dp_mode == 'peer-mc') if not compact else ('auto' if not dp_mode.endswith('-p2p') else False)
             opt_obj = parallel.PeerAdam([p.to(dev).contiguous() for p in sc], LRS, multicast=mc, compact=compact,
                                         active_sh_bases=SH_BASES, overlap_sh_broadcast=('sync' not in dp_mode),
-                                        split=('mono' not in dp_mode))
+                                        split=('mono' not in dp_mode),
+                                        small_multicast={'auto': 'auto', 'on': True, 'off': False}[args.small_mc])
             if args.side_ctas:
                 opt_obj.side_ctas_per_sm = args.side_ctas
         except Exception as e:  # no symmetric memory / no NVLS on this box: NCCL collectives instead, and say so
@@ -861,6 +862,8 @@ def main():
                     help='fused path with the deferred SH schedule (sh_rest Adam on a side stream under the next forward\'s geometry '
                          'pass; measured +0.5 % at C2, so not the default)')
     ap.add_argument('--no-defer-sh', action='store_true', help='(default; kept for compatibility)')
+    ap.add_argument('--small-mc', default='auto', choices=['auto', 'on', 'off'],
+                    help='N > 1, peer-rows: the small-tensor kernel through NVLS multimem (auto: at 8 ranks)')
     ap.add_argument('--side-ctas', type=int, default=0, help='experiments: CTAs per SM of the side-stream sh_rest kernel at N > 1 (default 2)')
     ap.add_argument('--defer-ctas', type=int, default=0, help='experiments: CTAs per SM of the deferred sh_rest update kernel (default 2)')
     ap.add_argument('--overlap-adam', action='store_true',

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kPeerBlock) peer_adam_multicast_kernel(const P
         float4 p = a.params[a.rank][e];
         float4 m = a.exp_avg[a.shard_off[t] + j];
         float4 v = a.exp_avg_sq[a.shard_off[t] + j];
+        if (t == 0 && a.means_old != nullptr) a.means_old[j] = p;
         const float ss = a.step_size[t], b2 = a.b2[t];
         adam1(s.x, p.x, m.x, v.x, ss, a.beta1, a.beta2, a.eps, b2);
         adam1(s.y, p.y, m.y, v.y, ss, a.beta1, a.beta2, a.eps, b2);
@@ -716,7 +717,8 @@ static int peer_adam_step_impl(const float* const* peer_grads, float* const* pee
 int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
                              float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
                              int32_t n_rest, const int32_t step[6], const double lr[6], double beta1, double beta2,
-                             double eps, float* means_old, void* stream) {
+                             double eps, float* means_old, const float* grads_multicast, float* params_multicast,
+                             void* stream) {
     auto fail = [](const char* msg) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "%s", msg);
         return -1;
@@ -739,6 +741,12 @@ int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_
     a.exp_avg = reinterpret_cast<float4*>(exp_avg_shard);
     a.exp_avg_sq = reinterpret_cast<float4*>(exp_avg_sq_shard);
     a.means_old = reinterpret_cast<float4*>(means_old);
+    if ((grads_multicast == nullptr) != (params_multicast == nullptr))
+        return fail("fgs_peer_adam_small_step: pass both multicast addresses or none");
+    if ((reinterpret_cast<uintptr_t>(grads_multicast) | reinterpret_cast<uintptr_t>(params_multicast)) & 15u)
+        return fail("fgs_peer_adam_small_step: multicast addresses must be 16-byte aligned");
+    a.grads_mc = reinterpret_cast<const float4*>(grads_multicast);
+    a.params_mc = reinterpret_cast<float4*>(params_multicast);
     const uint32_t kf[6] = {3u, 3u, 4u, 1u, 3u, 3u * (uint32_t)n_rest};
     const uint64_t per = (((n_rows + (uint64_t)world - 1) / (uint64_t)world) + 31) / 32 * 32;
     const uint64_t begin = (uint64_t)rank * per < n_rows ? (uint64_t)rank * per : n_rows;
@@ -772,8 +780,16 @@ int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_
     const uint64_t cap = (uint64_t)(sms > 0 ? sms : 1) * (uint64_t)(occ > 0 ? occ : 1);
     const uint64_t want = (total + kPeerBlock - 1) / kPeerBlock;
     const int grid = (int)(want < cap ? want : cap);
-    auto k = peer_adam_kernel;
-    FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+#ifndef FGS_CUDA_EMU
+    if (a.grads_mc != nullptr) {  // NVLS: the sum comes back from the switch, one store reaches every replica
+        auto km = peer_adam_multicast_kernel;
+        FGS_LAUNCH_SERIAL(km, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+    } else
+#endif
+    {
+        auto k = peer_adam_kernel;
+        FGS_LAUNCH_SERIAL(k, dim3((unsigned)grid), dim3(kPeerBlock), reinterpret_cast<cudaStream_t>(stream), a);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         std::snprintf(g_peer_err, sizeof(g_peer_err), "fgs_peer_adam_small_step: %s", cudaGetErrorString(e));

@@ -106,7 +106,7 @@ SIGNATURES = {
                                            C.c_uint64, C.c_int32, _I32Arr6, _F64Arr6, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                                            C.c_int32, _P]),
     'fgs_peer_adam_small_step': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _U64Arr6, C.c_uint64, C.c_int32, _I32Arr6,
-                                            _F64Arr6, C.c_double, C.c_double, C.c_double, _P, _P]),
+                                            _F64Arr6, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     'fgs_peer_broadcast_multicast': (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P]),
     'fgs_peer_adam_shard_floats': (C.c_size_t, [_U64Arr6, C.c_int32]),
     'fgs_peer_adam_slice': (C.c_int, [_U64Arr6, C.c_int32, C.c_int32, _U64Arr6, _U64Arr6, _U64Arr6]),

@@ -165,7 +165,7 @@ class PeerAdam:
 
     def __init__(self, tensors: Sequence[torch.Tensor], lrs: Sequence[float], betas=(0.9, 0.999), eps: float = 1e-15,
                  group=None, multicast: bool | str = 'auto', compact: bool = False, active_sh_bases: int = 16,
-                 overlap_sh_broadcast: bool = True, split: bool = True) -> None:
+                 overlap_sh_broadcast: bool = True, split: bool = True, small_multicast: bool | str = 'auto') -> None:
         """`multicast`: True = reduce and broadcast inside the NVSwitch through the buffers' multicast addresses
         (multimem.ld_reduce / multimem.st, fgs_peer_adam_step_multicast), False = W peer loads / stores per element,
         'auto' = multicast when the symmetric-memory handles expose a multicast address.
@@ -249,7 +249,14 @@ class PeerAdam:
             self._rest_lo, self._rest_hi = self.offsets[5] + lo * k, self.offsets[5] + hi * k
             self._peer_pbufs = [self._ph.get_buffer(q, (total,), torch.float32) for q in range(self.world)]
             if self.split:
-                self.multicast = False  # measured: multimem's latency costs more than its volume saves on 14 floats per Gaussian
+                self.multicast = False  # the sh_rest kernel: peer stores (ingress-bound either way, multimem only adds latency)
+                # the small-tensor kernel is NVLink-bound at 8 ranks (98 MB each way): there the switch's reduction and
+                # replication (56 MB each way) pays, below that multimem's latency does not
+                if small_multicast == 'auto':
+                    small_multicast = False  # the measured default; `True` is the experiment (bench.py --small-mc on)
+                if small_multicast and not (g_mc and p_mc):
+                    raise RuntimeError('PeerAdam(small_multicast=True): the symmetric-memory handles have no multicast address (no NVLS)')
+                self.small_multicast = bool(small_multicast)
                 self._means_old = torch.zeros(self.rows_per_rank * 3 + 4, dtype=torch.float32, device=dev)
             if self.overlap_sh_broadcast:  # every diff_rasterize forward from now on defers its colour kernel behind sh_ready
                 from .torch_bindings import rasterization as _rast
@@ -323,7 +330,9 @@ class PeerAdam:
         common = ((C.c_int32 * 6)(*[self.steps] * 6), (C.c_double * 6)(*self.lrs), float(self.betas[0]), float(self.betas[1]), self.eps)
         rc = self._lib.fgs_peer_adam_small_step(self._gptrs, self._pptrs, self.world, self.rank, self.exp_avg.data_ptr(),
                                                 self.exp_avg_sq.data_ptr(), (C.c_uint64 * 6)(*self.offsets), self.n_rows,
-                                                self.n_rest, *common, self._means_old.data_ptr(), stream)
+                                                self.n_rest, *common, self._means_old.data_ptr(),
+                                                self._g_mc if self.small_multicast else None,
+                                                self._p_mc if self.small_multicast else None, stream)
         if rc != 0:
             raise RuntimeError(self._lib.fgs_peer_last_error().decode())
         self._mark('kernel', ev)

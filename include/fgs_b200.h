@@ -330,7 +330,9 @@ int fgs_peer_adam_rows_step(const float* const* peer_grads, float* const* peer_p
 int fgs_peer_adam_small_step(const float* const* peer_grads, float* const* peer_params, int32_t world, int32_t rank,
                              float* exp_avg_shard, float* exp_avg_sq_shard, const uint64_t offsets[6], uint64_t n_rows,
                              int32_t n_rest, const int32_t step[6], const double lr[6], double beta1, double beta2,
-                             double eps, float* means_old, void* stream);
+                             double eps, float* means_old,
+                             const float* grads_multicast /* NVLS: both multicast addresses, or both NULL */,
+                             float* params_multicast, void* stream);
 /* floats [first_float, first_float + n_floats) of this rank's buffer to the same range of every replica through the
  * buffer's multicast address (one multimem.st per 16 bytes); `max_ctas` bounds the grid (default 64) */
 int fgs_peer_broadcast_multicast(const float* local_buffer, float* multicast_buffer, uint64_t first_float, uint64_t n_floats,

@@ -212,7 +212,7 @@ def test_peer_adam_rows_kernel_emulated_ranks(world, n, active, broadcast, split
                 rc = lib.fgs_peer_adam_small_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data),
                                                   C.c_void_p(v_sh[rank].ctypes.data), arr64(offsets), C.c_uint64(n), 15,
                                                   (C.c_int32 * 6)(*[step] * 6), (C.c_double * 6)(*lrs), C.c_double(b1),
-                                                  C.c_double(b2), C.c_double(eps), C.c_void_p(snap.ctypes.data), None)
+                                                  C.c_double(b2), C.c_double(eps), C.c_void_p(snap.ctypes.data), None, None, None)
                 assert rc == 0, lib.fgs_peer_last_error()
             rc = lib.fgs_peer_adam_rows_step(gp, pp, world, rank, C.c_void_p(m_sh[rank].ctypes.data), C.c_void_p(v_sh[rank].ctypes.data),
                                              arr64(offsets), C.c_uint64(n), 15, active, C.c_uint64(cam_off), broadcast,
@@ -317,6 +317,14 @@ def _worker(rank, world, port, out):
     run_variant('peer-rows-sync', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=False))
     # ... and with the sh_rest broadcast on the side stream under the next forward (deferred colour kernel waits for it)
     run_variant('peer-rows', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True))
+    # the same with the small tensors through the NVSwitch (multimem.ld_reduce / multimem.st), where the box has NVLS
+    try:
+        run_variant('peer-rows-small-mc', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True,
+                                                                    overlap_sh_broadcast=True, small_multicast=True))
+    except RuntimeError as e:
+        if 'no multicast address' not in str(e):
+            raise
+        results['peer-rows-small-mc'] = None
     # one row-sliced kernel for everything (NVLS where available), only the sh_rest broadcast overlapped; and over plain peer
     # loads / stores and copy engines
     run_variant('peer-rows-mono', lambda: parallel.PeerAdam([p.to(dev) for p in sc], lrs, compact=True, overlap_sh_broadcast=True,
