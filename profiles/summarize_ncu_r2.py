@@ -63,11 +63,18 @@ def main():
         if k == 'dur':
             return v * {'ns': 1e-3, 'us': 1, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1, 'msecond': 1e3}.get(u, 1)
         return v
-    print('# Round 2 -- `ncu --set full` of every kernel of the library (B200, benchmark sizes)\n')
-    print('`ncu --set full --clock-control none --profile-from-start off python profiles/evidence_run.py` (C2 scene: 1 M Gaussians, '
-          '1920x1080; 4D: 500 k; densification on a 1 M optimizer state), summarised by profiles/summarize_ncu_r2.py.  '
+    print('# Round 2 -- `ncu --set full` of the kernels round 1 left without evidence (B200, benchmark sizes)\n')
+    print('`ncu --set full --clock-control none --profile-from-start off -k regex:... python profiles/evidence_run.py` '
+          '(profiles/r2_call14_ncu.sh; profiler windows around the calls of interest; C2 scene: 1 M Gaussians, 1920x1080; 4D: 500 k; '
+          'densification on a 1 M optimizer state).  The report stays on the box (hundreds of MB); its raw page was exported there with '
+          '`ncu -i ... --page raw --csv` and is summarised here by profiles/summarize_ncu_r2.py.  The ten kernels of a plain training '
+          'step are in profiles/r1_kernels_ncu.md (unchanged since); `blend_forward_kernel<1>`, `blend_backward_kernel<0>`, '
+          '`preprocess_kernel<0,0,0>` appear again here because the windows contain whole steps.  '
           f'HBM peak = {peak:.0f} GB/s (MEASURED_PEAKS.json).  DRAM GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / duration; '
-          'kernels far below the HBM peak with a high issue-slot share are issue bound (blend), with both low are latency bound (sorts, scans).\n')
+          'ncu serialises the launches and flushes caches between passes, so durations are cold-cache.  Kernels far below the HBM peak '
+          'with a high issue-slot share are issue bound (blend, ssim), with both low are latency bound (plans, bbox) or tiny (the MCMC / '
+          'filter operators run on 4 k test inputs here).  Template arguments: `preprocess_kernel<inference, cov3d, defer_colour>`, '
+          '`blend_forward_kernel<training>`, `blend_backward_kernel<scores>`, `preprocess_backward_kernel<skip_invisible_rest, cov3d>`.\n')
     print('| kernel | launches | duration (us) | DRAM MB | DRAM GB/s | % of HBM peak | issue slots % | LSU pipe % | regs | warps active % | grid x block |')
     print('|---|---|---|---|---|---|---|---|---|---|---|')
     for name, d in agg.items():
