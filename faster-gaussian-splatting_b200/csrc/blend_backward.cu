@@ -31,7 +31,7 @@ namespace fgs {
 namespace {
 
 #ifndef FGS_BWD_MAXREG
-#define FGS_BWD_MAXREG 80
+#define FGS_BWD_MAXREG 76  // 3 CTAs per SM like 80, but no spill with the hit list; 72 / 96 / 128 measured slower (r2_results.md)
 #endif
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
@@ -46,6 +46,9 @@ struct __align__(128) WarpSmem {
     float g[3][32];         // per pixel: dL/d(colour), one plane per channel
     Rec par[kSlots];        // per slot: the Gaussian's record
     uint64_t full[kRing];
+#if FGS_HITLIST_BWD
+    uint16_t hit[kBatch + 2];  // byte offsets, inside the ring slot, of the records that reach this warp's sub-tile
+#endif
 };
 
 // Phase B: lanes k and k+16 own slot k and each reduce it over 16 of the warp's 32 pixels straight out
@@ -253,14 +256,35 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
             const bool hit = lane < count && ((__float_as_uint(recs[lane].q2.y) >> sub) & 1u) != 0u;
             uint32_t pending = __ballot_sync(0xffffffffu, hit);
             // branch-free body: alpha_eff = 0 leaves T and the colour-after terms untouched
+#if FGS_HITLIST_BWD
+            const int n_hits = __popc(pending);
+            if (hit) ws.hit[__popc(pending & ((1u << lane) - 1u))] = (uint16_t)(lane * (int)sizeof(Rec));
+            __syncwarp();
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(recs);
+            const int off_rel = n_rel * (int)sizeof(Rec);  // this pixel's last contributor as a byte offset into the batch
+            const uint16_t* hp = ws.hit;
+            uint32_t off_next = lds_u16(hp);
+#pragma unroll 1
+            for (int i = 0; i < n_hits; ++i) {
+                const uint32_t off = off_next;
+                off_next = lds_u16(++hp);  // one past the end holds a stale offset: loaded, never used
+                const Rec* rp = reinterpret_cast<const Rec*>(base + off);
+                const float4 q0 = rp->q0;
+                const float4 q1 = rp->q1;
+                const float c_b = rp->q2.x;
+                const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
+                const bool c = alpha >= kMinAlpha && (int)off < off_rel;
+#else
             while (pending) {
                 const int jj = __ffs((int)pending) - 1;
                 pending &= pending - 1;
+                const Rec* rp = &recs[jj];
                 const float4 q0 = recs[jj].q0;
                 const float4 q1 = recs[jj].q1;
                 const float c_b = recs[jj].q2.x;
                 const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                 const bool c = alpha >= kMinAlpha && jj < n_rel;
+#endif
                 FGS_STAT_ADD(st_pairs, lane == 0);
                 FGS_STAT_ADD(st_useful, c);
                 const float ae = c ? alpha : 0.0f;
@@ -284,7 +308,7 @@ __global__ void __maxnreg__(FGS_BWD_MAXREG) blend_backward_kernel(const BlendBwd
                     ws.u[nslots][lane] = u;
                     ws.w[nslots][lane] = w;
                     if (lane < 3)
-                        reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(&recs[jj])[lane];
+                        reinterpret_cast<float4*>(&ws.par[nslots])[lane] = reinterpret_cast<const float4*>(rp)[lane];
                     if (++nslots == kSlots) {
                         FGS_STAT_ADD(st_flushes, lane == 0);
                         FGS_STAT_ADD(st_slots, lane == 0 ? kSlots : 0);

@@ -37,10 +37,17 @@ constexpr int kRing = 3;                   // ring slots per warp
 struct __align__(128) WarpRing {
     Rec recs[kRing][kBatch];
     uint64_t full[kRing];
+#if FGS_HITLIST_FWD
+    uint16_t hit[kBatch + 2];  // byte offsets, inside the ring slot, of the records that reach this warp's sub-tile (fits the padding)
+#endif
 };
 
 template <bool kTraining>
+#if FGS_HITLIST_FWD
+__global__ void __launch_bounds__(kThreads, 6) blend_forward_kernel(const BlendFwdArgs a, const Cam cam) {
+#else
 __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdArgs a, const Cam cam) {
+#endif
     __shared__ WarpRing rings[kWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRing& R = rings[warp];
@@ -123,12 +130,30 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                 FGS_STAT_ADD(st_batches, lane == 0);
                 FGS_STAT_ADD(st_empty, lane == 0 && pending == 0u);
                 int last_jj = -1;  // this pixel's last contributor inside the batch
+#if FGS_HITLIST_FWD
+                const int n_hits = __popc(pending);
+                if (hit) R.hit[__popc(pending & ((1u << lane) - 1u))] = (uint16_t)(lane * (int)sizeof(Rec));
+                __syncwarp();
+                const unsigned char* base = reinterpret_cast<const unsigned char*>(recs);
+                const uint16_t* hp = R.hit;
+                uint32_t off_next = lds_u16(hp);
+                int last_off = -1;
+#pragma unroll 1
+                for (int i = 0; i < n_hits; ++i) {
+                    const uint32_t off = off_next;
+                    off_next = lds_u16(++hp);  // one past the end holds a stale offset: loaded, never used
+                    const Rec* rp = reinterpret_cast<const Rec*>(base + off);
+                    const float4 q0 = rp->q0;
+                    const float4 q1 = rp->q1;
+                    const float colb = rp->q2.x;
+#else
                 while (pending) {
                     const int jj = __ffs((int)pending) - 1;
                     pending &= pending - 1;
                     const float4 q0 = recs[jj].q0;
                     const float4 q1 = recs[jj].q1;
                     const float colb = recs[jj].q2.x;
+#endif
                     const float alpha = blend_alpha(q0.z, q0.w, q1.x, q1.y, q0.x - px, q0.y - py);
                     const bool c = alpha >= thr;
                     FGS_STAT_ADD(st_pairs, lane == 0);
@@ -140,9 +165,16 @@ __global__ void __launch_bounds__(kThreads) blend_forward_kernel(const BlendFwdA
                     cg = fmaf(w, q1.w, cg);
                     cb = fmaf(w, colb, cb);
                     T = __fmul_rn(T, __fsub_rn(1.0f, ae));
+#if FGS_HITLIST_FWD
+                    if (c) last_off = (int)off;
+#else
                     if (c) last_jj = jj;
+#endif
                     thr = T < kTransmittanceThreshold ? kDone : thr;
                 }
+#if FGS_HITLIST_FWD
+                if (last_off >= 0) last_jj = last_off / (int)sizeof(Rec);
+#endif
                 if (last_jj >= 0) n_last = (uint32_t)(offset + last_jj + 1);
                 warp_done = __all_sync(0xffffffffu, thr == kDone);
             }

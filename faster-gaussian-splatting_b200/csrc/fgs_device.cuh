@@ -270,6 +270,32 @@ __device__ __forceinline__ float blend_alpha(float A2, float B2, float C2, float
     return exp2f(fminf(la, lop));
 }
 
+// Blend inner loops: how the warp walks the records of a batch that reach its sub-tile.  0: peel the ballot mask bit by bit
+// (ffs = BREV + FLO, two XU-pipe instructions per Gaussian next to the MUFU.EX2 / MUFU.RCP).  1: compact the hits once per
+// batch into a list of byte offsets in shared memory (one POPC per lane and batch) and walk the list with broadcast loads.
+// Measured on B200 at C2 (profiles/r2_results.md, calls 17-18): backward 0.523 -> 0.498 ms (with 76 registers: 0.493);
+// forward unchanged (0.269 -> 0.271), so only the backward uses the list.
+#ifndef FGS_HITLIST
+#define FGS_HITLIST 0
+#endif
+#ifndef FGS_HITLIST_FWD
+#define FGS_HITLIST_FWD FGS_HITLIST
+#endif
+#ifndef FGS_HITLIST_BWD
+#define FGS_HITLIST_BWD 1
+#endif
+
+// 16-bit shared-memory load, zero-extended into a 32-bit register (the C++ form makes nvcc re-pack the half word)
+__device__ __forceinline__ uint32_t lds_u16(const uint16_t* p) {
+#ifdef FGS_CUDA_EMU
+    return (uint32_t)*p;
+#else
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+#endif
+}
+
 // ---- optional instrumentation of the blend kernels (build with -DFGS_BLEND_STATS=1; never in the product build) -------
 // Counters for the issue roofline (profiles/blend_stats.py): how many (Gaussian, sub-tile) pairs the inner loops execute
 // and how many of their 32 lanes do useful work.
