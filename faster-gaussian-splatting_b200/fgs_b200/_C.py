@@ -44,9 +44,6 @@ class _Scratch:
     def user(self, which: int) -> int:
         return (self.key << 2) | which
 
-    def take(self, which: int):
-        return self.buffers.pop(which, None)
-
 
 def _resize(user, nbytes):
     ctx = _contexts[int(user) >> 2]

@@ -383,6 +383,46 @@ def check_reference_bindings():
     print("reference's own torch_bindings over fgs_b200._C ok")
 
 
+def check_deferred_sh():
+    """diff_rasterize_fused(..., defer_sh=True) through the Python layer: `_C.forward_ex` (deferred colour), `_C.backward_adam`
+    with the sh_rest update deferred (on the emulator the side stream is synchronous), the keep-alive of the scratch the
+    deferred kernel reads, `join_deferred`, and an inference render in between -- same parameters and moments as the plain
+    fused path after four steps over two views."""
+    from fgs_b200 import _C
+    n, w, h = 180, 48, 36
+    sc = syn.make_scene(n, 9)
+    cams = [syn.make_camera(k, w, h) for k in range(2)]
+    rs = [fgs_b200.RasterizerSettings(*util.settings_for(c, bg=(0.2, 0.1, 0.3))) for c in cams]
+    gis = [syn.make_grad_image(w, h, k) for k in range(2)]
+
+    def run(defer):
+        params = [p.clone().requires_grad_(True) for p in sc]
+        opt = fgs_b200.FusedAdam([{'params': [p], 'lr': LRS[k]} for p, k in zip(params, NAMES)], lr=0.0, eps=1e-15)
+        imgs = []
+        for it in range(4):
+            img = fgs_b200.diff_rasterize_fused(*params, torch.empty(0), rs[it % 2], opt, defer_sh=defer)
+            img.backward(gis[it % 2])
+            opt.step()
+            opt.zero_grad()
+            imgs.append(img.detach().clone())
+            if it == 1:
+                with torch.no_grad():
+                    imgs.append(fgs_b200.rasterize(*[p.detach() for p in params], rs[0], to_chw=True))
+        fgs_b200.join_deferred('cpu')
+        return imgs, [p.detach().clone() for p in params], [opt.state[p]['exp_avg'].clone() for p in params]
+
+    ia, pa, ma = run(False)
+    ib, pb, mb = run(True)
+    assert (not _C._deferred_keepalive) is False  # the deferred path kept its scratch alive
+    for a, b in zip(ia, ib):
+        assert (a - b).abs().max().item() <= 1e-6
+    for k, a, b, p0 in zip(NAMES, pa, pb, sc):
+        assert util.rel_err(b - p0, a - p0) <= 2e-3, k
+    for k, a, b in zip(NAMES, ma, mb):
+        assert util.rel_err(b, a) <= 1e-4, k
+    print('deferred SH schedule through the Python layer ok')
+
+
 def check_gpu_test_code():
     """The bodies of the `-m gpu` tests of the widened rows, executed here with device 'cpu' (and smaller sizes where the
     test takes them as parameters): validates the TEST code that will first meet a GPU at the end of the round."""
@@ -406,5 +446,5 @@ if __name__ == '__main__':
     for name in which:
         {'rasterizer': check_rasterizer_api, 'loss': check_loss_api, 'densification': check_densification_api,
          'fourd': check_fourd_api, 'training': check_training_loop, 'gpu_tests': check_gpu_test_code, 'peer_adam': check_peer_adam_class,
-         'reference_bindings': check_reference_bindings}[name]()
+         'reference_bindings': check_reference_bindings, 'deferred_sh': check_deferred_sh}[name]()
     print('ALL OK')

@@ -12,7 +12,7 @@ import pytest
 
 SCRIPT = Path(__file__).resolve().parent / 'emu_python_layer.py'
 # two subprocesses (each pays the interpreter + torch start-up once)
-PARTS = [('rasterizer', 'reference_bindings', 'loss', 'peer_adam'), ('densification', 'fourd', 'gpu_tests')] + \
+PARTS = [('rasterizer', 'reference_bindings', 'loss', 'peer_adam', 'deferred_sh'), ('densification', 'fourd', 'gpu_tests')] + \
     ([('training',)] if os.environ.get('FGS_TEST_SLOW') == '1' else [])
 
 
