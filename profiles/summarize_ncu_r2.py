@@ -86,5 +86,12 @@ def main():
               f"{m.get('lsu', float('nan')):.1f} | {m.get('regs', float('nan')):.0f} | {m.get('occ', float('nan')):.1f} | {m.get('grid', float('nan')):.0f} x {m.get('block', float('nan')):.0f} |")
 
 
+    print('\nNot in this capture: the view-parallel kernels (`peer_adam_kernel`, `peer_adam_multicast_kernel`, `peer_adam_rows_kernel`, '
+          '`peer_broadcast_multicast_kernel`) need several ranks and ncu profiles one process on one GPU (B200_PROFILING.md: never a '
+          'multi-rank command); they are timed with CUDA events per phase and rank instead (`per_rank[].phases_ms` of the bench line, '
+          'profiles/r2_results.md section 2: small-tensor kernel 0.16 ms = 98 MB each way over NVLink at 8 GPUs, sh_rest kernel 0.30 ms = '
+          '157 MB each way).  `adam_rest_invisible_kernel` belongs to the rejected `--overlap-adam` experiment and is on no default path.')
+
+
 if __name__ == '__main__':
     main()
